@@ -1,0 +1,982 @@
+// bsq_capi.cu -- the C ABI (include/blazeseq_gpu.h): parser object, pass driver, result views.
+//
+// Host logic only decides WHERE kernels run (windows, runs, buffers) and formats errors; every
+// byte of the FASTQ stream is examined on the device.  There is no CPU parsing path.
+#include <cub/device/device_scan.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/blazeseq_gpu.h"
+#include "bsq_aux.cuh"
+#include "bsq_device.cuh"
+
+using namespace bsq;
+
+static_assert(sizeof(bsq_summary) == sizeof(BsqSummary), "ABI summary is a BsqSummary");
+
+namespace {
+
+constexpr uint64_t kWindowMax = (1ull << 31) - (1ull << 20);  // bytes per window (u32 offsets)
+constexpr uint64_t kHostWindow = 256ull << 20;                // window size while bytes stream in
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, size_t slack = 0) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + slack;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Window {
+    const uint8_t* base = nullptr;   // device, 16-byte aligned
+    uint64_t region_off = 0;         // region offset of the window's first valid byte
+    WinParams wp{};
+    ScanOut scan{};
+    int64_t rec_base = 0;            // arena index of first record
+    int64_t seq_base = 0, qual_base = 0, id_base = 0;
+    DevBuf line_ends;                // views(): newlines + 2 entries
+    DevBuf run_pre;                  // BsqPrefix per run (kept for the resolve pass)
+};
+
+struct HostMirror {                  // pinned
+    ScanOut scan;
+    unsigned long long err;
+    TailOut tail;
+};
+
+}  // namespace
+
+struct bsq_parser {
+    bsq_config cfg{};
+    int sm_count = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[6]{};             // timing marks
+    cudaEvent_t ev_copy[2]{};
+    DevBuf run_sum, scan_out, err_word, tail_out, cub_tmp, len_prefix;
+    DevBuf seq_out, qual_out, id_out, ends, id_ends, ends_base, id_ends_base, id_spans;
+    DevBuf host_input;               // device copy of a host pass
+    void* pinned_stage[2] = {nullptr, nullptr};
+    size_t pinned_stage_bytes = 0;
+    HostMirror* hm = nullptr;        // pinned
+    std::vector<Window> win;
+    std::vector<int64_t> h_ends_base, h_id_ends_base;
+    // last pass
+    bool have_pass = false;
+    uint32_t want = 0;
+    bsq_pass_result res{};
+    const uint8_t* pass_input = nullptr;
+    int64_t pass_stream_offset = 0;
+    int64_t total_records = 0;       // arena records (complete + tail)
+    int64_t total_seq = 0, total_qual = 0, total_id = 0;
+    float ms[5] = {0, 0, 0, 0, 0};
+    int64_t n_launches = 0;
+    std::string last_error;
+};
+
+namespace {
+
+bsq_status fail_cuda(bsq_parser* p, cudaError_t e, const char* what) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    p->last_error = buf;
+    cudaGetLastError();
+    return BSQ_E_CUDA;
+}
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) return fail_cuda(p, _e, #call); \
+    } while (0)
+
+// errors.mojo:71-90
+const char* code_message(int code) {
+    switch (code) {
+        case BSQ_ID_NO_AT: return "Sequence id line does not start with '@'";
+        case BSQ_SEP_NO_PLUS: return "Separator line does not start with '+'";
+        case BSQ_SEQ_QUAL_LEN_MISMATCH: return "Quality and sequence line do not match in length";
+        case BSQ_ASCII_INVALID: return "Non ASCII letters found";
+        case BSQ_QUALITY_OUT_OF_RANGE: return "Corrupt quality score according to provided schema";
+        case BSQ_UNEXPECTED_EOF: return "Unexpected end of file in FASTQ record";
+        case BSQ_BUFFER_EXCEEDED: return "FASTQ record exceeds buffer capacity";
+        case BSQ_BUFFER_AT_MAX: return "FASTQ record exceeds maximum buffer capacity";
+        default: return "Parse or validation error";
+    }
+}
+
+struct Msg {
+    char* p; size_t cap, len;
+    void bytes(const void* b, size_t n) {
+        if (len + n >= cap) n = cap - 1 - len;
+        memcpy(p + len, b, n); len += n; p[len] = 0;
+    }
+    void str(const char* z) { bytes(z, strlen(z)); }
+    void i64(int64_t v) { char t[32]; snprintf(t, sizeof t, "%lld", (long long)v); str(t); }
+};
+
+void set_plain_error(bsq_error* e, int code, const char* text) {
+    memset(e, 0, sizeof *e);
+    e->code = code;
+    Msg m{e->message, sizeof e->message, 0};
+    m.str(text);
+}
+
+size_t smem_bytes() { return sizeof(TileSmem) + 128; }
+
+template <typename K>
+cudaError_t opt_in_smem(K kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes());
+}
+
+void plan_window(bsq_parser* p, Window& w, const uint8_t* first_byte, uint64_t bytes) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(first_byte);
+    const uintptr_t al = a & ~uintptr_t(15);
+    w.base = reinterpret_cast<const uint8_t*>(al);
+    w.wp.base = w.base;
+    w.wp.begin = (uint32_t)(a - al);
+    w.wp.end = w.wp.begin + (uint32_t)bytes;
+    w.wp.first_tile = w.wp.begin / kTile;
+    w.wp.n_tiles = (w.wp.end + kTile - 1) / kTile;
+    uint32_t tiles = w.wp.n_tiles - w.wp.first_tile;
+    if (tiles == 0) tiles = 1, w.wp.n_tiles = w.wp.first_tile + 1;
+    uint32_t max_runs = (uint32_t)std::min<int>(2 * p->sm_count, kMaxRuns);
+    uint32_t runs = std::min(tiles, max_runs);
+    w.wp.tiles_per_run = (tiles + runs - 1) / runs;
+    w.wp.n_runs = (tiles + w.wp.tiles_per_run - 1) / w.wp.tiles_per_run;
+}
+
+using ResolveKernel = void (*)(const WinParams, const ResolveParams);
+
+ResolveKernel pick_resolve(bool ascii, bool qual, bool offs, bool pack) {
+    // ParserConfig(check_ascii, check_quality) x {views, batches}: one instantiation each
+    static const ResolveKernel table[16] = {
+        k_resolve<false, false, false, false>, k_resolve<false, false, false, true>,
+        k_resolve<false, false, true, false>,  k_resolve<false, false, true, true>,
+        k_resolve<false, true, false, false>,  k_resolve<false, true, false, true>,
+        k_resolve<false, true, true, false>,   k_resolve<false, true, true, true>,
+        k_resolve<true, false, false, false>,  k_resolve<true, false, false, true>,
+        k_resolve<true, false, true, false>,   k_resolve<true, false, true, true>,
+        k_resolve<true, true, false, false>,   k_resolve<true, true, false, true>,
+        k_resolve<true, true, true, false>,    k_resolve<true, true, true, true>,
+    };
+    return table[(ascii ? 8 : 0) | (qual ? 4 : 0) | (offs ? 2 : 0) | (pack ? 1 : 0)];
+}
+
+bsq_status setup_kernels(bsq_parser* p) {
+    CK(opt_in_smem(k_summarize));
+    for (int i = 0; i < 16; ++i) CK(opt_in_smem(pick_resolve(i & 8, i & 4, i & 2, i & 1)));
+    return BSQ_OK;
+}
+
+// Summarise + scan one window; leaves the ScanOut in w.scan (host) after a stream sync.
+bsq_status summarize_window(bsq_parser* p, Window& w) {
+    CK(p->run_sum.ensure(sizeof(BsqSummary) * kMaxRuns));
+    CK(w.run_pre.ensure(sizeof(BsqPrefix) * kMaxRuns));
+    CK(p->scan_out.ensure(sizeof(ScanOut)));
+    k_summarize<<<w.wp.n_runs, kThreads, smem_bytes(), p->stream>>>(w.wp, p->run_sum.as<BsqSummary>());
+    k_scan_runs<<<1, 256, 0, p->stream>>>(p->run_sum.as<BsqSummary>(), w.wp.n_runs, w.wp.begin,
+                                          w.run_pre.as<BsqPrefix>(), p->scan_out.as<ScanOut>());
+    p->n_launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&p->hm->scan, p->scan_out.p, sizeof(ScanOut), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    w.scan = p->hm->scan;
+    return BSQ_OK;
+}
+
+// D2H of a few bytes of the region (error snippets)
+bsq_status fetch_bytes(bsq_parser* p, const uint8_t* dev, size_t n, std::vector<uint8_t>& out) {
+    out.resize(n);
+    if (n) CK(cudaMemcpy(out.data(), dev, n, cudaMemcpyDeviceToHost));
+    return BSQ_OK;
+}
+
+// Offsets of window-local record k (5 values) read back from the line-end table.
+bsq_status fetch_record_offsets(bsq_parser* p, Window& w, uint32_t k, uint32_t o[5]) {
+    uint32_t le[5];
+    CK(cudaMemcpy(le, w.line_ends.as<uint32_t>() + 4ull * k, sizeof le, cudaMemcpyDeviceToHost));
+    o[0] = le[0] + 1u; o[1] = le[1] + 1u; o[2] = le[2] + 1u; o[3] = le[3] + 1u; o[4] = le[4];
+    return BSQ_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// configuration helpers
+// ------------------------------------------------------------------------------------------------
+
+extern "C" void bsq_default_config(bsq_config* c) {
+    memset(c, 0, sizeof *c);
+    c->device_id = 0;
+    c->q_lower = 33; c->q_upper = 126; c->q_offset = 33;   // generic_schema, quality_schema.mojo:26
+    c->buffer_capacity = 256 * 1024;                       // CONSTS.mojo:26
+    c->buffer_max_capacity = 1ll << 30;                    // CONSTS.mojo:27-28
+    c->batch_size = 4096;                                  // CONSTS.mojo:31
+    c->h2d_chunk_bytes = 64ll << 20;
+}
+
+extern "C" int32_t bsq_parse_schema(const char* name, uint8_t* lower, uint8_t* upper, uint8_t* offset) {
+    static const struct { const char* n; uint8_t lo, up, off; } tab[] = {
+        {"sanger", 33, 126, 33},       {"solexa", 59, 126, 64},       {"illumina_1.3", 64, 126, 64},
+        {"illumina_1.5", 66, 126, 64}, {"illumina_1.8", 33, 126, 33}, {"generic", 33, 126, 33}};
+    for (auto& t : tab)
+        if (name && strcmp(name, t.n) == 0) { *lower = t.lo; *upper = t.up; *offset = t.off; return 0; }
+    *lower = 33; *upper = 126; *offset = 33;
+    return 1;
+}
+
+extern "C" uint32_t bsq_abi_version(void) { return BSQ_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------
+
+extern "C" bsq_status bsq_create(const bsq_config* cfg, bsq_parser** out) {
+    if (!out) return BSQ_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return BSQ_E_NO_DEVICE; }
+    bsq_parser* p = new (std::nothrow) bsq_parser();
+    if (!p) return BSQ_E_NOMEM;
+    if (cfg) p->cfg = *cfg; else bsq_default_config(&p->cfg);
+    if (p->cfg.batch_size <= 0) p->cfg.batch_size = 4096;
+    if (p->cfg.h2d_chunk_bytes <= 0) p->cfg.h2d_chunk_bytes = 64ll << 20;
+    if (p->cfg.q_upper >= 128 || p->cfg.q_lower > p->cfg.q_upper || p->cfg.device_id < 0 || p->cfg.device_id >= ndev) {
+        delete p;
+        return BSQ_E_ARG;
+    }
+    bsq_status st = BSQ_OK;
+    auto init = [&]() -> bsq_status {
+        CK(cudaSetDevice(p->cfg.device_id));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, p->cfg.device_id));
+        if (prop.major < 10) { p->last_error = "this build targets sm_100a (B200)"; return BSQ_E_NO_DEVICE; }
+        p->sm_count = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+        for (auto& e : p->ev) CK(cudaEventCreate(&e));
+        for (auto& e : p->ev_copy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&p->hm), sizeof(HostMirror), cudaHostAllocDefault));
+        CK(p->err_word.ensure(sizeof(unsigned long long)));
+        CK(p->tail_out.ensure(sizeof(TailOut)));
+        return setup_kernels(p);
+    };
+    st = init();
+    if (st != BSQ_OK) { bsq_destroy(p); return st; }
+    *out = p;
+    return BSQ_OK;
+}
+
+extern "C" void bsq_destroy(bsq_parser* p) {
+    if (!p) return;
+    cudaSetDevice(p->cfg.device_id);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
+    for (auto& w : p->win) { w.line_ends.release(); w.run_pre.release(); }
+    DevBuf* bufs[] = {&p->run_sum, &p->scan_out, &p->err_word, &p->tail_out, &p->cub_tmp, &p->len_prefix,
+                      &p->seq_out, &p->qual_out, &p->id_out, &p->ends, &p->id_ends, &p->ends_base,
+                      &p->id_ends_base, &p->id_spans, &p->host_input};
+    for (auto* b : bufs) b->release();
+    for (auto& s : p->pinned_stage) if (s) cudaFreeHost(s);
+    if (p->hm) cudaFreeHost(p->hm);
+    for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : p->ev_copy) if (e) cudaEventDestroy(e);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    delete p;
+}
+
+extern "C" const char* bsq_last_error_text(const bsq_parser* p) { return p ? p->last_error.c_str() : ""; }
+
+extern "C" bsq_status bsq_set_batch_size(bsq_parser* p, int32_t batch_size) {
+    if (!p || batch_size <= 0) return BSQ_E_ARG;
+    p->cfg.batch_size = batch_size;
+    p->have_pass = false;  // views of the previous pass were cut with the old size
+    return BSQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the pass driver
+// ------------------------------------------------------------------------------------------------
+
+namespace {
+
+// `ready_upto(region_bytes)` makes sure region bytes [0, region_bytes) are on the device before a
+// kernel that reads them is enqueued on p->stream (no-op for device passes).
+struct InputFeed {
+    virtual bsq_status ready_upto(uint64_t) { return BSQ_OK; }
+    virtual ~InputFeed() {}
+};
+
+bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_offset, int64_t first_record,
+                    int32_t is_last, uint32_t want, uint64_t window_bytes, InputFeed& feed, bsq_pass_result* out) {
+    const bsq_config& cfg = p->cfg;
+    const bool want_offs = (want & BSQ_WANT_OFFSETS) != 0, want_pack = (want & BSQ_WANT_BATCHES) != 0;
+    p->have_pass = false;
+    p->want = want;
+    p->pass_input = d;
+    p->pass_stream_offset = stream_offset;
+    p->n_launches = 0;
+    memset(&p->res, 0, sizeof p->res);
+    bsq_pass_result& R = p->res;
+    CK(cudaEventRecord(p->ev[0], p->stream));
+
+    // ---- pass 1: summarise every window (host learns where the next window starts) ----------
+    size_t nw = 0;
+    uint64_t pos = 0;
+    bool oversize = false;
+    while (pos < n) {
+        if (nw >= (size_t)kMaxWindows) { p->last_error = "region needs more than kMaxWindows windows"; return BSQ_E_ARG; }
+        if (p->win.size() <= nw) p->win.emplace_back();
+        Window& w = p->win[nw];
+        const uint64_t bytes = std::min<uint64_t>(n - pos, window_bytes);
+        bsq_status st = feed.ready_upto(pos + bytes);
+        if (st != BSQ_OK) return st;
+        plan_window(p, w, d + pos, bytes);
+        w.region_off = pos;
+        st = summarize_window(p, w);
+        if (st != BSQ_OK) return st;
+        ++nw;
+        const uint64_t consumed = w.scan.totals.consumed_end - w.wp.begin;
+        const bool reaches_end = pos + bytes == n;
+        if (reaches_end) break;
+        if (consumed == 0) {
+            if (window_bytes < kWindowMax) { window_bytes = std::min<uint64_t>(window_bytes * 4, kWindowMax); --nw; continue; }
+            oversize = true;  // a single record larger than a window
+            break;
+        }
+        pos += consumed;
+    }
+    CK(cudaEventRecord(p->ev[1], p->stream));
+
+    // ---- totals, tail classification ----------------------------------------------------------
+    int64_t nrec = 0, nseq = 0, nqual = 0, nid = 0, nnl = 0;
+    bool any_strip = cfg.force_id_slow_path != 0;
+    for (size_t i = 0; i < nw; ++i) {
+        Window& w = p->win[i];
+        w.rec_base = nrec; w.seq_base = nseq; w.qual_base = nqual; w.id_base = nid;
+        nrec += w.scan.totals.records; nseq += w.scan.totals.seq_bytes; nqual += w.scan.totals.qual_bytes;
+        nid += w.scan.totals.id_bytes_unstripped;
+        nnl += (i + 1 < nw) ? 4ll * w.scan.totals.records : w.scan.totals.newlines;
+        if (w.scan.totals.flags & BSQ_SUM_ID_MAY_STRIP) any_strip = true;
+    }
+    uint64_t consumed_total = 0;
+    uint32_t rem = 0;
+    bool have_tail_candidate = false;
+    Window* lw = nw ? &p->win[nw - 1] : nullptr;
+    // SURVEY App. A Q2 (parser.mojo:484-492): the stream's first record is incomplete and the
+    // buffer may not grow -> BUFFER_EXCEEDED, whatever the tail looks like
+    bool q2 = false;
+    // ids: the scanned prefix counts an empty header line as -1; such a line is a structure error,
+    // so only records after the first error are affected -- but the arena must still hold them
+    int64_t id_room = 64;
+    for (size_t i = 0; i < nw; ++i) {
+        const Window& w = p->win[i];
+        const int64_t bytes = (int64_t)w.wp.end - w.wp.begin;
+        id_room += std::min<int64_t>(w.scan.totals.id_bytes_unstripped, bytes) + w.scan.totals.records + 1;
+    }
+    if (lw) {
+        consumed_total = lw->region_off + (lw->scan.totals.consumed_end - lw->wp.begin);
+        rem = lw->scan.totals.newlines & 3u;
+        q2 = is_last && consumed_total < n && first_record + nrec == 0 && stream_offset == 0 && !cfg.buffer_growth_enabled;
+        have_tail_candidate = is_last && !oversize && !q2 && consumed_total < n && rem == 3u &&
+                              (int64_t)lw->scan.totals.id_bytes_unstripped <= (int64_t)lw->wp.end;
+    }
+    uint32_t tail_seq = 0, tail_qual = 0, tail_id_max = 0;
+    TailParams T{};
+    if (have_tail_candidate) {
+        const BsqSummary& E = lw->scan.end_state;
+        T.base = lw->base; T.hs = lw->scan.totals.consumed_end;
+        T.nl0 = E.last[2]; T.nl1 = E.last[1]; T.nl2 = E.last[0]; T.end = lw->wp.end;
+        T.k = lw->scan.totals.records;
+        T.newline_rank = 4u * T.k + 3u;
+        tail_seq = T.nl1 - T.nl0 - 1u; tail_qual = T.end - T.nl2 - 1u;
+        tail_id_max = T.nl0 > T.hs ? T.nl0 - T.hs - 1u : 0u;
+    }
+
+    // ---- outputs -------------------------------------------------------------------------------
+    const int64_t arena_rec = nrec + (have_tail_candidate ? 1 : 0);
+    const int32_t m = cfg.batch_size;
+    const int64_t nb_cap = arena_rec / m + 2;
+    CK(p->err_word.ensure(8));
+    CK(cudaMemsetAsync(p->err_word.p, 0xFF, 8, p->stream));
+    if (want_offs || want_pack) CK(p->id_spans.ensure(8ull * (arena_rec + 1), 1 << 20));
+    if (want_pack) {
+        CK(p->seq_out.ensure((size_t)nseq + tail_seq + 64, 1 << 20));
+        CK(p->qual_out.ensure((size_t)nqual + tail_qual + 64, 1 << 20));
+        CK(p->id_out.ensure((size_t)id_room + tail_id_max, 1 << 20));
+        CK(p->ends.ensure(8ull * (arena_rec + 1), 1 << 20));
+        CK(p->id_ends.ensure(8ull * (arena_rec + 1), 1 << 20));
+        CK(p->ends_base.ensure(8ull * nb_cap, 1 << 16));
+        CK(p->id_ends_base.ensure(8ull * nb_cap, 1 << 16));
+        CK(cudaMemsetAsync(p->ends_base.p, 0, 8ull * nb_cap, p->stream));
+        CK(cudaMemsetAsync(p->id_ends_base.p, 0, 8ull * nb_cap, p->stream));
+    }
+    const bool id_fast = !any_strip;
+
+    // ---- pass 2: resolve / validate / pack ------------------------------------------------------
+    auto make_params = [&](Window& w) {
+        ResolveParams P{};
+        P.run_pre = w.run_pre.as<BsqPrefix>();
+        P.n_complete = w.scan.totals.records;
+        P.id_fast = id_fast ? 1u : 0u;
+        P.rec_base = w.rec_base;
+        P.first_record = first_record;
+        P.line_ends = w.line_ends.as<uint32_t>();
+        P.id_spans = p->id_spans.p ? p->id_spans.as<uint32_t>() + 2 * w.rec_base : nullptr;
+        P.seq_out = p->seq_out.as<uint8_t>(); P.qual_out = p->qual_out.as<uint8_t>(); P.id_out = p->id_out.as<uint8_t>();
+        P.seq_base64 = w.seq_base; P.qual_base64 = w.qual_base; P.id_base64 = w.id_base;
+        P.ends_abs = p->ends.as<int64_t>(); P.id_ends_abs = p->id_ends.as<int64_t>();
+        P.ends_base = p->ends_base.as<int64_t>(); P.id_ends_base = p->id_ends_base.as<int64_t>();
+        P.id_cap = (int64_t)p->id_out.cap;
+        P.batch_size = m;
+        P.lower = cfg.q_lower; P.upper = cfg.q_upper;
+        P.err = p->err_word.as<unsigned long long>();
+        return P;
+    };
+    ResolveKernel kern = pick_resolve(cfg.check_ascii, cfg.check_quality, want_offs, want_pack);
+    for (size_t i = 0; i < nw; ++i) {
+        Window& w = p->win[i];
+        if (want_offs) CK(w.line_ends.ensure(4ull * ((size_t)w.scan.totals.newlines + 2), 1 << 16));
+        ResolveParams P = make_params(w);
+        kern<<<w.wp.n_runs, kThreads, smem_bytes(), p->stream>>>(w.wp, P);
+        p->n_launches += 1;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(p->ev[2], p->stream));
+
+    if (have_tail_candidate) {
+        ResolveParams P = make_params(*lw);
+        T.check_ascii = cfg.check_ascii; T.check_quality = cfg.check_quality;
+        T.lower = cfg.q_lower; T.upper = cfg.q_upper;
+        T.want_offsets = want_offs; T.want_pack = want_pack; T.id_fast = id_fast;
+        T.seq_rel = lw->scan.totals.seq_bytes; T.qual_rel = lw->scan.totals.qual_bytes;
+        T.id_rel = lw->scan.totals.id_bytes_unstripped;
+        k_tail<<<1, 256, 0, p->stream>>>(T, P, p->tail_out.as<TailOut>());
+        p->n_launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&p->hm->tail, p->tail_out.p, sizeof(TailOut), cudaMemcpyDeviceToHost, p->stream));
+    }
+    CK(cudaMemcpyAsync(&p->hm->err, p->err_word.p, 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+
+    // ---- how far did the pass get? ------------------------------------------------------------
+    bsq_error stop;
+    memset(&stop, 0, sizeof stop);
+    int64_t good = nrec;             // records before the stop
+    bool tail_emitted = false;
+    if (have_tail_candidate && p->hm->tail.status == 0) tail_emitted = true;
+    const unsigned long long key = p->hm->err;
+    const bool have_err = key != ~0ull;
+    int64_t err_rec = -1; int err_code = 0;
+    if (have_err) { err_rec = (int64_t)(key >> 8) - first_record; err_code = (int)(key & 0xFF); }
+    int64_t arena_final = nrec + (tail_emitted ? 1 : 0);
+    if (have_err && err_rec < arena_final) {
+        good = err_rec;
+    } else {
+        good = arena_final;
+        err_code = 0;
+    }
+
+    // ---- id strip pipeline + rebase over the records that count ------------------------------
+    if (want_pack && arena_final > 0) {
+        const int grid = std::max(1, std::min<int>(p->sm_count * 8, (int)((arena_final + 255) / 256)));
+        if (!id_fast) {
+            k_id_lens<<<grid, 256, 0, p->stream>>>(p->id_spans.as<uint32_t>(), p->id_ends.as<int64_t>(), arena_final);
+            size_t tmp = 0;
+            CK(cub::DeviceScan::InclusiveSum(nullptr, tmp, p->id_ends.as<int64_t>(), p->id_ends.as<int64_t>(),
+                                             (int)arena_final, p->stream));
+            CK(p->cub_tmp.ensure(tmp + 16));
+            CK(cub::DeviceScan::InclusiveSum(p->cub_tmp.p, tmp, p->id_ends.as<int64_t>(), p->id_ends.as<int64_t>(),
+                                             (int)arena_final, p->stream));
+            k_id_bases<<<std::max<int>(1, (int)((arena_final / m + 256) / 256)), 256, 0, p->stream>>>(
+                p->id_ends.as<int64_t>(), p->id_ends_base.as<int64_t>(), arena_final, m);
+            WindowTable WT{};
+            WT.n = (int32_t)nw;
+            for (size_t i = 0; i < nw; ++i) { WT.base[i] = p->win[i].base; WT.rec_base[i] = p->win[i].rec_base; }
+            WT.rec_base[nw] = arena_final;
+            k_id_copy<<<grid, 256, 0, p->stream>>>(WT, p->id_spans.as<uint32_t>(), p->id_ends.as<int64_t>(),
+                                                   p->id_out.as<uint8_t>(), arena_final);
+            p->n_launches += 5;
+        }
+        // cumulative totals at the end (before rebasing) -> batch directory on the host
+        const int64_t nbat = (arena_final + m - 1) / m;
+        p->h_ends_base.assign(nbat + 1, 0);
+        p->h_id_ends_base.assign(nbat + 1, 0);
+        CK(cudaMemcpyAsync(p->h_ends_base.data(), p->ends_base.p, 8ull * nbat, cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaMemcpyAsync(p->h_id_ends_base.data(), p->id_ends_base.p, 8ull * nbat, cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaMemcpyAsync(&p->h_ends_base[nbat], p->ends.as<int64_t>() + (arena_final - 1), 8, cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaMemcpyAsync(&p->h_id_ends_base[nbat], p->id_ends.as<int64_t>() + (arena_final - 1), 8, cudaMemcpyDeviceToHost, p->stream));
+        k_rebase<<<grid, 256, 0, p->stream>>>(p->ends.as<int64_t>(), p->id_ends.as<int64_t>(), p->ends_base.as<int64_t>(),
+                                              p->id_ends_base.as<int64_t>(), arena_final, m);
+        p->n_launches += 1;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(p->ev[3], p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    p->total_records = arena_final;
+    p->total_seq = nseq + (tail_emitted ? tail_seq : 0);
+    p->total_qual = nqual + (tail_emitted ? tail_qual : 0);
+
+    // ---- the stop reason, with the reference's context and text -------------------------------
+    R.n_newlines = nnl;
+    R.n_windows = (int32_t)nw;
+    R.id_slow_path = id_fast ? 0 : 1;
+    uint64_t consumed_final = consumed_total;
+    if (good < arena_final || (have_err && err_code != 0)) {
+        // first error at arena record `good`: find its window and offsets
+        size_t wi = 0;
+        while (wi + 1 < nw && good >= p->win[wi + 1].rec_base) ++wi;
+        Window& w = p->win[wi];
+        const uint32_t k = (uint32_t)(good - w.rec_base);
+        const bool is_tail_rec = tail_emitted && good == nrec;
+        uint32_t o[5];
+        if (is_tail_rec) {
+            o[0] = T.hs; o[1] = T.nl0 + 1u; o[2] = T.nl1 + 1u; o[3] = T.nl2 + 1u; o[4] = T.end;
+        } else {
+            if (!want_offs) {  // cold path: materialise this window's line-end table
+                CK(w.line_ends.ensure(4ull * ((size_t)w.scan.totals.newlines + 2), 1 << 16));
+                CK(p->id_spans.ensure(8ull * (arena_rec + 1), 1 << 20));
+                ResolveParams P = make_params(w);
+                DevBuf scratch;
+                CK(scratch.ensure(8));
+                CK(cudaMemset(scratch.p, 0xFF, 8));
+                P.err = scratch.as<unsigned long long>();
+                k_resolve<false, false, true, false><<<w.wp.n_runs, kThreads, smem_bytes(), p->stream>>>(w.wp, P);
+                p->n_launches += 1;
+                CK(cudaStreamSynchronize(p->stream));
+                scratch.release();
+            }
+            bsq_status st = fetch_record_offsets(p, w, k, o);
+            if (st != BSQ_OK) return st;
+        }
+        const int64_t win_stream_base = stream_offset + (int64_t)w.region_off - (int64_t)w.wp.begin;
+        const int64_t gidx = first_record + good;  // 0-based global record index
+        consumed_final = w.region_off + (o[0] - w.wp.begin);
+        memset(&stop, 0, sizeof stop);
+        stop.code = err_code;
+        Msg msg{stop.message, sizeof stop.message, 0};
+        msg.str(code_message(err_code));
+        if (err_code <= 3) {
+            // ParseError: parser.mojo:332-338 + errors.mojo:178-192
+            stop.record_number = gidx + 1; stop.line_number = 4 * gidx + 1; stop.file_position = win_stream_base + o[0];
+            std::vector<uint8_t> sn;
+            size_t len = std::min<size_t>((size_t)(o[4] + 1u - o[0]), 200);
+            bsq_status st = fetch_bytes(p, w.base + o[0], len, sn);
+            if (st != BSQ_OK) return st;
+            msg.str("\n  Record number: "); msg.i64(stop.record_number);
+            msg.str("\n  Line number: "); msg.i64(stop.line_number);
+            if (stop.file_position > 0) { msg.str("\n  File position: "); msg.i64(stop.file_position); }
+            if (!sn.empty()) { msg.str("\n  Record snippet: "); msg.bytes(sn.data(), sn.size()); }
+        } else {
+            // ValidationError: parser.mojo:163-169,597-610 + errors.mojo:223-234
+            stop.record_number = gidx + 1;
+            uint32_t sp[2];
+            CK(cudaMemcpy(sp, p->id_spans.as<uint32_t>() + 2 * good, sizeof sp, cudaMemcpyDeviceToHost));
+            const uint32_t seq_len = o[2] - o[1] - 1u;
+            std::vector<uint8_t> idb, sqb;
+            bsq_status st = fetch_bytes(p, w.base + sp[0], std::min<size_t>(sp[1], 400), idb);
+            if (st != BSQ_OK) return st;
+            std::string snip(idb.begin(), idb.end());
+            if (!snip.empty() && snip.size() < 200) snip.push_back('\n');
+            if (snip.size() < 200 && seq_len > 0) {
+                st = fetch_bytes(p, w.base + o[1], std::min<size_t>(seq_len, 200 - snip.size()), sqb);
+                if (st != BSQ_OK) return st;
+                snip.append(sqb.begin(), sqb.end());
+            }
+            if (snip.size() > 200) { snip.resize(197); snip += "..."; }
+            msg.str("\n  Record number: "); msg.i64(stop.record_number);
+            if (!snip.empty()) { msg.str("\n  Record snippet: "); msg.bytes(snip.data(), snip.size()); }
+        }
+    } else if (oversize) {
+        char t[200];
+        snprintf(t, sizeof t, "FASTQ record exceeds maximum buffer capacity (%lld bytes). Enable buffer growth or increase max_capacity.",
+                 (long long)kWindowMax);
+        set_plain_error(&stop, BSQ_BUFFER_AT_MAX, t);
+    } else if (!is_last) {
+        stop.code = BSQ_OK;  // more input needed; the caller re-presents the unconsumed tail
+    } else if (tail_emitted) {
+        consumed_final = n;
+        set_plain_error(&stop, BSQ_EOF, "EOF");
+    } else if (consumed_total == n) {
+        set_plain_error(&stop, BSQ_EOF, "EOF");       // parser.mojo:316-317
+    } else if (q2) {
+        char t[200];
+        snprintf(t, sizeof t, "FASTQ record exceeds buffer capacity (%lld bytes). Enable buffer growth or increase buffer_capacity.",
+                 (long long)cfg.buffer_capacity);
+        set_plain_error(&stop, BSQ_BUFFER_EXCEEDED, t);
+    } else if (rem < 3u) {
+        char t[96];                                   // parser.mojo:295-298
+        snprintf(t, sizeof t, "Unexpected end of file in FASTQ record at phase %u", rem);
+        set_plain_error(&stop, BSQ_UNEXPECTED_EOF, t);
+    } else {
+        set_plain_error(&stop, BSQ_EMPTY_ERROR, "");  // parser.mojo:350-351
+    }
+
+    R.n_records = good;
+    R.bytes_consumed = (int64_t)consumed_final;
+    R.n_batches = want_pack ? (good + m - 1) / m : 0;
+    R.stop = stop;
+    // bases: sum of sequence lengths of the good records
+    if (good == arena_final) {
+        R.n_bases = p->total_seq;
+    } else if (want_pack && good > 0) {
+        // cumulative quality == sequence length for structurally valid records
+        int64_t v = 0;
+        const int64_t b = (good - 1) / m;
+        CK(cudaMemcpy(&v, p->ends.as<int64_t>() + (good - 1), 8, cudaMemcpyDeviceToHost));
+        R.n_bases = v + p->h_ends_base[b];
+    } else {
+        R.n_bases = -1;  // not materialised (views only, error before the end)
+    }
+    if (want_pack) {
+        // total id bytes of the arena
+        p->total_id = p->h_id_ends_base.empty() ? 0 : p->h_id_ends_base.back();
+    }
+    CK(cudaEventRecord(p->ev[4], p->stream));
+    CK(cudaEventSynchronize(p->ev[4]));
+    cudaEventElapsedTime(&p->ms[0], p->ev[0], p->ev[1]);
+    cudaEventElapsedTime(&p->ms[2], p->ev[1], p->ev[2]);
+    cudaEventElapsedTime(&p->ms[3], p->ev[2], p->ev[3]);
+    cudaEventElapsedTime(&p->ms[4], p->ev[0], p->ev[4]);
+    p->ms[1] = 0.f;
+    p->have_pass = true;
+    if (out) *out = R;
+    return BSQ_OK;
+}
+
+struct HostFeed : InputFeed {
+    bsq_parser* p; const uint8_t* h; uint8_t* d; uint64_t n; uint64_t sent = 0; uint64_t ahead = 0; bool pinned = false; int slot = 0;
+    bsq_status send_upto(uint64_t upto) {
+        const uint64_t chunk = (uint64_t)p->cfg.h2d_chunk_bytes;
+        if (upto > n) upto = n;
+        while (sent < upto) {
+            const uint64_t len = std::min<uint64_t>(chunk, n - sent);
+            if (pinned) {
+                CK(cudaMemcpyAsync(d + sent, h + sent, len, cudaMemcpyHostToDevice, p->copy_stream));
+            } else {
+                // pageable source: bounce through two pinned buffers
+                CK(cudaEventSynchronize(p->ev_copy[slot]));
+                memcpy(p->pinned_stage[slot], h + sent, len);
+                CK(cudaMemcpyAsync(d + sent, p->pinned_stage[slot], len, cudaMemcpyHostToDevice, p->copy_stream));
+                CK(cudaEventRecord(p->ev_copy[slot], p->copy_stream));
+                slot ^= 1;
+            }
+            sent += len;
+        }
+        return BSQ_OK;
+    }
+    bsq_status ready_upto(uint64_t upto) override {
+        bsq_status st = send_upto(upto);
+        if (st != BSQ_OK) return st;
+        // the scan stream may read the bytes once the copies enqueued so far have landed ...
+        CK(cudaEventRecord(p->ev[5], p->copy_stream));
+        CK(cudaStreamWaitEvent(p->stream, p->ev[5], 0));
+        // ... and the next window's bytes travel while this one is scanned
+        return send_upto(upto + ahead);
+    }
+};
+
+}  // namespace
+
+extern "C" bsq_status bsq_parse_device(bsq_parser* p, const uint8_t* dev_bytes, uint64_t n, int64_t stream_offset,
+                                       int64_t first_record, int32_t is_last, uint32_t want, bsq_pass_result* out) {
+    if (!p || (!dev_bytes && n)) return BSQ_E_ARG;
+    CK(cudaSetDevice(p->cfg.device_id));
+    InputFeed none;
+    return run_pass(p, dev_bytes, n, stream_offset, first_record, is_last, want, kWindowMax, none, out);
+}
+
+extern "C" bsq_status bsq_parse_host(bsq_parser* p, const uint8_t* host_bytes, uint64_t n, int64_t stream_offset,
+                                     int64_t first_record, int32_t is_last, uint32_t want, bsq_pass_result* out) {
+    if (!p || (!host_bytes && n)) return BSQ_E_ARG;
+    CK(cudaSetDevice(p->cfg.device_id));
+    CK(p->host_input.ensure(n + 256, 1 << 20));
+    HostFeed feed;
+    feed.p = p; feed.h = host_bytes; feed.d = p->host_input.as<uint8_t>(); feed.n = n;
+    cudaPointerAttributes attr{};
+    if (n && cudaPointerGetAttributes(&attr, host_bytes) == cudaSuccess && attr.type == cudaMemoryTypeHost) feed.pinned = true;
+    cudaGetLastError();
+    if (!feed.pinned && n) {
+        const size_t chunk = (size_t)p->cfg.h2d_chunk_bytes;
+        if (p->pinned_stage_bytes < chunk) {
+            for (auto& s : p->pinned_stage) { if (s) cudaFreeHost(s); s = nullptr; }
+            for (auto& s : p->pinned_stage) CK(cudaHostAlloc(&s, chunk, cudaHostAllocDefault));
+            p->pinned_stage_bytes = chunk;
+        }
+    }
+    const uint64_t window = std::min<uint64_t>(kWindowMax, std::max<uint64_t>(kHostWindow, (uint64_t)p->cfg.h2d_chunk_bytes));
+    feed.ahead = window;
+    bsq_status st = run_pass(p, feed.d, n, stream_offset, first_record, is_last, want, window, feed, out);
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// result views
+// ------------------------------------------------------------------------------------------------
+
+extern "C" bsq_status bsq_get_offsets(const bsq_parser* p, int32_t window, bsq_offsets_view* out) {
+    if (!p || !out) return BSQ_E_ARG;
+    if (!p->have_pass || !(p->want & BSQ_WANT_OFFSETS)) return BSQ_E_STATE;
+    if (window < 0 || window >= p->res.n_windows) return BSQ_E_ARG;
+    const Window& w = p->win[window];
+    const int64_t next_base = (window + 1 < p->res.n_windows) ? p->win[window + 1].rec_base : p->total_records;
+    int64_t nrec = next_base - w.rec_base;
+    if (w.rec_base + nrec > p->res.n_records) nrec = std::max<int64_t>(0, p->res.n_records - w.rec_base);
+    out->stream_base = p->pass_stream_offset + (int64_t)w.region_off - (int64_t)w.wp.begin;
+    out->first_record = w.rec_base;
+    out->n_records = nrec;
+    out->line_ends = w.line_ends.as<uint32_t>();
+    out->id_spans = p->id_spans.as<uint32_t>() + 2 * w.rec_base;
+    out->window_bytes = w.base;
+    return BSQ_OK;
+}
+
+static bsq_status fill_batch(const bsq_parser* p, int64_t first, int64_t count, int64_t b0, bsq_batch_view* out) {
+    memset(out, 0, sizeof *out);
+    out->quality_offset = 33;  // parser.mojo:243 never passes the schema offset
+    out->num_records = count;
+    if (count <= 0) return BSQ_OK;
+    const int32_t m = p->cfg.batch_size;
+    const int64_t qb = p->h_ends_base[b0], ib = p->h_id_ends_base[b0];
+    out->sequence_buffer = p->seq_out.as<uint8_t>() + qb;
+    out->qual_buffer = p->qual_out.as<uint8_t>() + qb;
+    out->id_buffer = p->id_out.as<uint8_t>() + ib;
+    out->ends = p->ends.as<int64_t>() + first;
+    out->id_ends = p->id_ends.as<int64_t>() + first;
+    // sizes: a full batch ends where the next one begins
+    const int64_t last = first + count;  // exclusive
+    int64_t q_end, i_end;
+    if (last % m == 0 || last == p->total_records) {
+        const int64_t nb = (last + m - 1) / m;
+        q_end = p->h_ends_base[nb]; i_end = p->h_id_ends_base[nb];
+    } else {
+        // a batch cut short by an error: read the cumulative values of its last record
+        int64_t v[2];
+        cudaMemcpy(&v[0], p->ends.as<int64_t>() + (last - 1), 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&v[1], p->id_ends.as<int64_t>() + (last - 1), 8, cudaMemcpyDeviceToHost);
+        q_end = qb + v[0]; i_end = ib + v[1];
+    }
+    out->seq_len = q_end - qb;
+    out->total_id_bytes = i_end - ib;
+    return BSQ_OK;
+}
+
+extern "C" bsq_status bsq_get_batch(const bsq_parser* p, int64_t b, bsq_batch_view* out) {
+    if (!p || !out) return BSQ_E_ARG;
+    if (!p->have_pass || !(p->want & BSQ_WANT_BATCHES)) return BSQ_E_STATE;
+    if (b < 0 || b >= p->res.n_batches) return BSQ_E_ARG;
+    const int32_t m = p->cfg.batch_size;
+    const int64_t first = b * m;
+    const int64_t count = std::min<int64_t>(m, p->res.n_records - first);
+    return fill_batch(p, first, count, b, out);
+}
+
+extern "C" bsq_status bsq_get_soa(const bsq_parser* p, bsq_batch_view* out) {
+    if (!p || !out) return BSQ_E_ARG;
+    if (!p->have_pass || !(p->want & BSQ_WANT_BATCHES)) return BSQ_E_STATE;
+    memset(out, 0, sizeof *out);
+    out->quality_offset = 33;
+    out->num_records = p->res.n_records;
+    if (p->res.n_records == 0) return BSQ_OK;
+    out->sequence_buffer = p->seq_out.as<uint8_t>();
+    out->qual_buffer = p->qual_out.as<uint8_t>();
+    out->id_buffer = p->id_out.as<uint8_t>();
+    out->ends = p->ends.as<int64_t>();
+    out->id_ends = p->id_ends.as<int64_t>();
+    bsq_batch_view last;
+    const int64_t lb = p->res.n_batches - 1;
+    bsq_status st = bsq_get_batch(p, lb, &last);
+    if (st != BSQ_OK) return st;
+    out->seq_len = p->h_ends_base[lb] + last.seq_len;
+    out->total_id_bytes = p->h_id_ends_base[lb] + last.total_id_bytes;
+    return BSQ_OK;
+}
+
+extern "C" bsq_status bsq_batch_to_host(bsq_parser* p, int64_t b, uint8_t* seq, uint8_t* qual, uint8_t* id,
+                                        int64_t* ends, int64_t* id_ends) {
+    bsq_batch_view v;
+    bsq_status st = bsq_get_batch(p, b, &v);
+    if (st != BSQ_OK) return st;
+    if (v.num_records == 0) return BSQ_OK;
+    CK(cudaSetDevice(p->cfg.device_id));
+    if (seq) CK(cudaMemcpyAsync(seq, v.sequence_buffer, v.seq_len, cudaMemcpyDeviceToHost, p->stream));
+    if (qual) CK(cudaMemcpyAsync(qual, v.qual_buffer, v.seq_len, cudaMemcpyDeviceToHost, p->stream));
+    if (id) CK(cudaMemcpyAsync(id, v.id_buffer, v.total_id_bytes, cudaMemcpyDeviceToHost, p->stream));
+    if (ends) CK(cudaMemcpyAsync(ends, v.ends, 8 * v.num_records, cudaMemcpyDeviceToHost, p->stream));
+    if (id_ends) CK(cudaMemcpyAsync(id_ends, v.id_ends, 8 * v.num_records, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return BSQ_OK;
+}
+
+extern "C" bsq_status bsq_offsets_to_host(bsq_parser* p, int32_t window, uint32_t* line_ends, uint32_t* id_spans) {
+    bsq_offsets_view v;
+    bsq_status st = bsq_get_offsets(p, window, &v);
+    if (st != BSQ_OK) return st;
+    CK(cudaSetDevice(p->cfg.device_id));
+    if (line_ends) CK(cudaMemcpyAsync(line_ends, v.line_ends, 4 * (4 * v.n_records + 1), cudaMemcpyDeviceToHost, p->stream));
+    if (id_spans && v.n_records) CK(cudaMemcpyAsync(id_spans, v.id_spans, 8 * v.n_records, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return BSQ_OK;
+}
+
+extern "C" const uint8_t* bsq_pass_device_input(const bsq_parser* p) { return p && p->have_pass ? p->pass_input : nullptr; }
+
+extern "C" bsq_status bsq_last_timing(const bsq_parser* p, float ms[5], int64_t* n_launches) {
+    if (!p || !p->have_pass) return BSQ_E_STATE;
+    if (ms) memcpy(ms, p->ms, sizeof p->ms);
+    if (n_launches) *n_launches = p->n_launches;
+    return BSQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic input
+// ------------------------------------------------------------------------------------------------
+
+static int ndigits(int64_t v) { int d = 1; while (v >= 10) { v /= 10; ++d; } return d; }
+
+extern "C" int64_t bsq_compute_num_reads_for_size(int64_t target, int64_t mn, int64_t mx) {
+    if (target <= 0) return 0;                       // utils.mojo:640-678
+    const int64_t avg = (mn + mx) / 2;
+    const int64_t est = target / (15 + 2 * avg + 4);
+    if (est <= 0) return 0;
+    const int64_t digits = est > 1 ? ndigits(est - 1) : 1;
+    return target / (6 + digits + 1 + 2 * avg + 4);
+}
+
+static void len_prefix_table(int64_t mn, int64_t mx, std::vector<uint64_t>& t) {
+    const int64_t m = mx - mn + 1;
+    t.assign(m + 1, 0);
+    for (int64_t j = 0; j < m; ++j) t[j + 1] = t[j] + (uint64_t)((j * 31 + 7) % m);
+}
+
+static uint64_t synth_offset_host(int64_t i, int64_t mn, int64_t mx, int digits, const std::vector<uint64_t>& t) {
+    const uint64_t m = (uint64_t)(mx - mn + 1);
+    const uint64_t lens = (uint64_t)i * mn + ((uint64_t)i / m) * t[m] + t[(uint64_t)i % m];
+    return (uint64_t)i * (6 + digits + 1 + 4) + 2 * lens;
+}
+
+extern "C" int64_t bsq_synth_size(int64_t num_reads, int64_t mn, int64_t mx) {
+    if (num_reads <= 0 || mn > mx || mn < 0) return 0;
+    std::vector<uint64_t> t;
+    len_prefix_table(mn, mx, t);
+    return (int64_t)synth_offset_host(num_reads, mn, mx, num_reads > 1 ? ndigits(num_reads - 1) : 1, t);
+}
+
+extern "C" bsq_status bsq_synth_device(bsq_parser* p, uint8_t* dev_out, uint64_t capacity, int64_t num_reads,
+                                       int64_t first, int64_t count, int64_t mn, int64_t mx, int64_t min_phred,
+                                       int64_t max_phred, uint8_t q_lower, uint8_t q_upper, uint8_t q_offset,
+                                       uint64_t* written) {
+    if (!p || !dev_out || num_reads <= 0 || first < 0 || count < 0 || first + count > num_reads || mn < 0 || mn > mx ||
+        min_phred < 0 || min_phred > max_phred || mx - mn > (1 << 24))
+        return BSQ_E_ARG;
+    CK(cudaSetDevice(p->cfg.device_id));
+    std::vector<uint64_t> t;
+    len_prefix_table(mn, mx, t);
+    SynthParams G{};
+    G.num_reads = num_reads; G.first = first; G.count = count;
+    G.min_len = mn; G.max_len = mx; G.min_phred = min_phred; G.max_phred = max_phred;
+    G.digits = num_reads > 1 ? ndigits(num_reads - 1) : 1;
+    G.q_lower = q_lower; G.q_upper = q_upper; G.q_offset = q_offset;
+    G.origin = synth_offset_host(first, mn, mx, G.digits, t);
+    const uint64_t end = synth_offset_host(first + count, mn, mx, G.digits, t);
+    if (end - G.origin > capacity) return BSQ_E_ARG;
+    CK(p->len_prefix.ensure(8 * t.size()));
+    CK(cudaMemcpyAsync(p->len_prefix.p, t.data(), 8 * t.size(), cudaMemcpyHostToDevice, p->stream));
+    G.len_prefix = p->len_prefix.as<uint64_t>();
+    G.period_sum = t.back();
+    // 32-step jump of x -> a x + c (mod 2^64)
+    auto jump = [](uint64_t a, uint64_t c, uint64_t& a32, uint64_t& c32) {
+        a32 = 1; c32 = 0;
+        for (int i = 0; i < 32; ++i) { c32 = c32 * a + c; a32 = a32 * a; }
+    };
+    jump(6364136223846793005ull, 1442695040888963407ull, G.a32_seq, G.c32_seq);
+    jump(1664525ull, 1013904223ull, G.a32_q, G.c32_q);
+    if (count > 0) {
+        const int64_t warps_per_block = 8;
+        const int grid = (int)std::min<int64_t>((count + warps_per_block - 1) / warps_per_block, (int64_t)p->sm_count * 32);
+        k_synth<<<grid, 256, 0, p->stream>>>(G, dev_out);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    if (written) *written = end - G.origin;
+    return BSQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shard stitching
+// ------------------------------------------------------------------------------------------------
+
+extern "C" bsq_status bsq_summarize_device(bsq_parser* p, const uint8_t* dev_bytes, uint64_t n, bsq_summary* out) {
+    if (!p || !out || (!dev_bytes && n)) return BSQ_E_ARG;
+    CK(cudaSetDevice(p->cfg.device_id));
+    // positions in the summary are relative to the shard start; shards larger than a window are
+    // folded window by window with the positions rebased on the host
+    BsqSummary acc = bsq_summary_identity();
+    uint64_t pos = 0;
+    Window w;
+    while (pos < n) {
+        const uint64_t bytes = std::min<uint64_t>(n - pos, kWindowMax);
+        plan_window(p, w, dev_bytes + pos, bytes);
+        bsq_status st = summarize_window(p, w);
+        if (st != BSQ_OK) { w.run_pre.release(); return st; }
+        BsqSummary s = w.scan.region;
+        // rebase window-relative positions to shard-relative (mod 2^32, like all rank algebra)
+        const uint32_t shift = (uint32_t)(pos - w.wp.begin);
+        for (int i = 0; i < 4; ++i) s.last[i] += shift;
+        for (uint32_t k = 0; k < 4; ++k) {
+            const uint32_t cnt_k = (s.count + 3u - k) >> 2;  // newlines with index == k (mod 4)
+            s.P[k] += shift * cnt_k;
+        }
+        acc = bsq_combine(acc, s);
+        pos += bytes;
+    }
+    w.run_pre.release();
+    memcpy(out, &acc, sizeof acc);
+    return BSQ_OK;
+}
+
+extern "C" bsq_status bsq_shard_prefix(const bsq_summary* shards, const uint64_t* shard_bytes, int32_t n_shards,
+                                       bsq_shard_start* start) {
+    if (!shards || !shard_bytes || !start || n_shards <= 0) return BSQ_E_ARG;
+    int64_t rank = 0;
+    bool prev_ends_with_newline = true;  // the stream start is a record start
+    for (int32_t i = 0; i < n_shards; ++i) {
+        BsqSummary s;
+        memcpy(&s, &shards[i], sizeof s);
+        start[i].newline_rank = rank;
+        start[i].phase = (int32_t)(rank & 3);
+        start[i]._pad = 0;
+        // records are owned by the shard that holds their first byte
+        uint64_t skip;
+        const bool at_record_start = (rank & 3) == 0 && prev_ends_with_newline;
+        if (at_record_start) {
+            skip = 0;
+        } else {
+            const uint32_t j = (uint32_t)((3 - (rank & 3)) & 3);  // first newline of class 3 in the shard
+            skip = j < s.count ? (uint64_t)s.first[j] + 1u : shard_bytes[i];
+        }
+        start[i].skip_bytes = (int64_t)skip;
+        // records completed before the first byte this shard owns
+        start[i].first_record = at_record_start ? (rank >> 2) : (rank >> 2) + 1;
+        if (s.count > 0) prev_ends_with_newline = (uint64_t)s.last[0] + 1u == shard_bytes[i];
+        else if (shard_bytes[i] > 0) prev_ends_with_newline = false;
+        rank += s.count;
+    }
+    return BSQ_OK;
+}

@@ -1,0 +1,700 @@
+// bsq_device.cuh -- sm_100a kernels of the FASTQ hot path.
+//
+// Two streaming passes over a window (<= 2 GiB of the byte stream, 16-byte aligned base):
+//
+//   k_summarize   every CTA owns a contiguous RUN of 32 KiB tiles.  Tiles arrive in shared memory
+//                 through a ring of TMA bulk copies (cp.async.bulk + mbarrier).  Per tile: 16-byte
+//                 shared loads -> byte-lane compare -> per-warp newline bitmap -> block prefix scan
+//                 -> ordered newline list.  The run is reduced to a 64-byte BsqSummary.
+//   k_scan_runs   one CTA scans the run summaries (tile_math.h) and gives every run the state it
+//                 starts from (newline rank, previous newline positions, SoA destinations).
+//   k_resolve     same tiling; with the prefix known every line that ENDS in a tile is resolved
+//                 in place: '@' / '+' / length checks (utils.mojo:448-462), id strip
+//                 (utils.mojo:221-242), ASCII and quality-range validation from the HI/BAD bitmaps
+//                 (record.mojo:76-116), the line-end table for views() and the FastqBatch SoA copy
+//                 (record_batch.mojo:77-87) as aligned 16-byte stores assembled from shared memory.
+//
+// No CTA ever waits on another CTA: the only cross-CTA dependency is the kernel boundary.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tile_math.h"
+
+namespace bsq {
+
+constexpr int kTile = 32768;              // bytes per tile
+constexpr int kThreads = 256;             // threads per CTA (8 warps)
+constexpr int kWarps = kThreads / 32;
+constexpr int kStages = 2;                // TMA ring depth per CTA (2 CTAs/SM -> 128 KiB in flight/SM)
+constexpr int kChunks = kTile / 16;       // 16-byte chunks per tile (2048)
+constexpr int kChunksPerThread = kChunks / kThreads;  // 8
+constexpr int kWords = kTile / 32;        // bitmap words per tile (1024)
+constexpr int kWordsPerThread = kWords / kThreads;    // 4 -> a thread ranks 128 contiguous bytes
+constexpr int kNlCap = 2048;              // newline-list capacity per pass over a tile
+constexpr int kHead = 4;                  // carried newline positions in front of the list
+constexpr int kLinesCap = kNlCap / 4 + 2; // lines of one class per pass (+ sentinel)
+constexpr int kTilePad = 32;              // readable slack after a tile for unaligned 16-byte loads
+constexpr int kMaxWindows = 64;
+
+static_assert(kThreads % 4 == 0 && kWordsPerThread == 4 && kChunksPerThread * kThreads == kChunks, "");
+
+struct WinParams {
+    const uint8_t* base;     // window base, 16-byte aligned
+    uint32_t begin, end;     // valid bytes [begin, end) relative to base
+    uint32_t first_tile;     // begin / kTile
+    uint32_t n_tiles;        // tiles [first_tile, n_tiles) cover [begin, end)
+    uint32_t tiles_per_run;
+    uint32_t n_runs;
+};
+
+struct ScanOut {             // written by k_scan_runs, read by the host
+    BsqTotals totals;        // 32 B
+    BsqSummary end_state;    // 64 B: init (+) all runs
+    BsqSummary region;       // 64 B: all runs WITHOUT the window init (for shard stitching)
+};
+
+struct ResolveParams {
+    const BsqPrefix* run_pre;
+    uint32_t n_complete;         // complete records of this window
+    uint32_t id_fast;            // 1: no id needs stripping in this window -> ids packed here
+    int64_t rec_base;            // arena index of the window's first record
+    int64_t first_record;        // global index of the pass's first record (error context)
+    // views()
+    uint32_t* line_ends;         // [newlines + 1]
+    uint32_t* id_spans;          // pass-wide, already offset to this window: [2 * n_complete]
+    // batches(): arena pointers are pass-wide; *_base64 = bytes written by earlier windows
+    uint8_t* seq_out; uint8_t* qual_out; uint8_t* id_out;
+    int64_t seq_base64, qual_base64, id_base64;
+    int64_t* ends_abs; int64_t* id_ends_abs;      // pass-wide, indexed by arena record
+    int64_t* ends_base; int64_t* id_ends_base;    // per batch: cumulative at the batch start
+    int64_t id_cap;              // bytes allocated for id_out
+    int32_t batch_size;
+    uint32_t lower, upper;       // quality bounds
+    unsigned long long* err;     // min over ((global record << 8) | code)
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + 1-D TMA bulk copy
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a TMA that never lands (bad address) must fault the kernel, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory layout of one CTA
+// ------------------------------------------------------------------------------------------------
+
+struct alignas(128) TileSmem {
+    uint8_t data[kStages][kTile + kTilePad];  // TMA destinations
+    uint32_t bm_nl[kWords];                   // 1 bit per byte: '\n'
+    uint32_t bm_hi[kWords];                   // 1 bit per byte: bit 7 set
+    uint32_t bm_bad[kWords];                  // 1 bit per byte: outside [lower, upper]
+    uint32_t nlx[kHead + kNlCap];             // nlx[kHead + j] = position of local newline j;
+                                              // nlx[kHead-1-i] = i-th newline before the list
+    uint32_t sdst[3][kLinesCap];              // per class stream: destination of each line
+    uint32_t ssrc[3][kLinesCap];              //                   source position of each line
+    uint32_t warp_tot[kWarps][4];
+    uint32_t carry[4];
+    uint64_t full_bar[kStages];
+};
+
+// ------------------------------------------------------------------------------------------------
+// tile pipeline: a CTA walks its run, tile by tile, through a kStages-deep TMA ring
+// ------------------------------------------------------------------------------------------------
+
+struct TileCursor {
+    uint32_t tile;        // current tile index in the window
+    uint32_t lo, hi;      // valid window offsets of the tile [lo, hi)
+    uint32_t origin;      // window offset of data[stage][0]
+    uint32_t stage;
+};
+
+__device__ __forceinline__ uint32_t tile_bytes_rounded(const WinParams& W, uint32_t tile) {
+    const uint32_t origin = tile * (uint32_t)kTile;
+    uint32_t n = W.end - origin;
+    if (n > (uint32_t)kTile) n = kTile;
+    return (n + 15u) & ~15u;  // stays inside the 16-byte granule that holds the last valid byte
+}
+
+__device__ __forceinline__ void issue_tile_load(TileSmem& S, const WinParams& W, uint32_t tile, uint32_t stage) {
+    const uint32_t bytes = tile_bytes_rounded(W, tile);
+    mbar_expect_tx(&S.full_bar[stage], bytes);
+    tma_load_1d(S.data[stage], W.base + (size_t)tile * kTile, bytes, &S.full_bar[stage]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// front end: bitmaps + block scan + ordered newline list
+// ------------------------------------------------------------------------------------------------
+
+// 16 flag bits (byte order) of one 16-byte chunk from four lane-flag words
+__device__ __forceinline__ uint32_t mask16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
+    uint32_t m = bsq_gather_top(f3) >> 28;
+    m = __funnelshift_l(bsq_gather_top(f2), m, 4);
+    m = __funnelshift_l(bsq_gather_top(f1), m, 4);
+    m = __funnelshift_l(bsq_gather_top(f0), m, 4);
+    return m;
+}
+
+template <bool kHi, bool kBad>
+__device__ __forceinline__ void build_bitmaps(TileSmem& S, const TileCursor& c, uint32_t addlo, uint32_t addup) {
+    const uint8_t* tile = S.data[c.stage];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t vlo = c.lo - c.origin, vhi = c.hi - c.origin;  // valid offsets in the tile
+#pragma unroll
+    for (int j = 0; j < kChunksPerThread; ++j) {
+        const uint32_t chunk = j * kThreads + tid;
+        const uint32_t off = chunk * 16u;
+        uint32_t m_nl = 0, m_hi = 0, m_bad = 0;
+        if (off < vhi && off + 16u > vlo) {  // warp-uniform except at the two edges of the stream
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + off);
+            m_nl = mask16(bsq_nl_flags(v.x), bsq_nl_flags(v.y), bsq_nl_flags(v.z), bsq_nl_flags(v.w));
+            if (kHi) m_hi = mask16(bsq_hi_flags(v.x), bsq_hi_flags(v.y), bsq_hi_flags(v.z), bsq_hi_flags(v.w));
+            if (kBad)
+                m_bad = mask16(bsq_badq_flags(v.x, addlo, addup), bsq_badq_flags(v.y, addlo, addup),
+                               bsq_badq_flags(v.z, addlo, addup), bsq_badq_flags(v.w, addlo, addup));
+            if (off < vlo || off + 16u > vhi) {
+                uint32_t keep = 0xFFFFu;
+                if (off < vlo) keep &= 0xFFFFu << (vlo - off);
+                if (off + 16u > vhi) keep &= 0xFFFFu >> (off + 16u - vhi);
+                m_nl &= keep; m_hi &= keep; m_bad &= keep;
+            }
+        }
+        // two adjacent lanes hold the two halves of one 32-bit bitmap word
+        const uint32_t x = m_nl | (m_hi << 16);
+        const uint32_t xo = __shfl_down_sync(0xFFFFFFFFu, x, 1);
+        uint32_t bo = 0;
+        if (kBad) bo = __shfl_down_sync(0xFFFFFFFFu, m_bad, 1);
+        if ((tid & 1u) == 0u) {
+            const uint32_t w = chunk >> 1;
+            S.bm_nl[w] = (x & 0xFFFFu) | (xo << 16);
+            if (kHi) S.bm_hi[w] = (x >> 16) | (xo & 0xFFFF0000u);
+            if (kBad) S.bm_bad[w] = m_bad | (bo << 16);
+        }
+    }
+}
+
+// Exclusive prefix of `v` over the block (in thread order) and the block total.  Two barriers.
+__device__ __forceinline__ uint32_t block_exclusive_scan(TileSmem& S, uint32_t v, uint32_t& total) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t)d) inc += t;
+    }
+    if (lane == 31u) S.warp_tot[warp][0] = inc;
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        const uint32_t t = S.warp_tot[w][0];
+        if ((uint32_t)w < warp) before += t;
+        tot += t;
+    }
+    __syncthreads();  // warp_tot is reused by the next scan
+    total = tot;
+    return before + inc - v;
+}
+
+// Same for three values at once (the id / seq / qual streams).
+__device__ __forceinline__ void block_exclusive_scan3(TileSmem& S, uint32_t v0, uint32_t v1, uint32_t v2,
+                                                      uint32_t& e0, uint32_t& e1, uint32_t& e2,
+                                                      uint32_t& t0, uint32_t& t1, uint32_t& t2) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t i0 = v0, i1 = v1, i2 = v2;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, i0, d);
+        const uint32_t b = __shfl_up_sync(0xFFFFFFFFu, i1, d);
+        const uint32_t c = __shfl_up_sync(0xFFFFFFFFu, i2, d);
+        if (lane >= (uint32_t)d) { i0 += a; i1 += b; i2 += c; }
+    }
+    if (lane == 31u) { S.warp_tot[warp][0] = i0; S.warp_tot[warp][1] = i1; S.warp_tot[warp][2] = i2; }
+    __syncthreads();
+    uint32_t b0 = 0, b1 = 0, b2 = 0, s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        const uint32_t x0 = S.warp_tot[w][0], x1 = S.warp_tot[w][1], x2 = S.warp_tot[w][2];
+        if ((uint32_t)w < warp) { b0 += x0; b1 += x1; b2 += x2; }
+        s0 += x0; s1 += x1; s2 += x2;
+    }
+    __syncthreads();
+    e0 = b0 + i0 - v0; e1 = b1 + i1 - v1; e2 = b2 + i2 - v2;
+    t0 = s0; t1 = s1; t2 = s2;
+}
+
+// Writes the positions of the local newlines with rank in [pass_base, pass_base + kNlCap) to
+// nlx[kHead + rank - pass_base].  `excl` = rank of the first newline of this thread's 128 bytes.
+__device__ __forceinline__ void fill_newline_list(TileSmem& S, const TileCursor& c, const uint4& words,
+                                                  uint32_t excl, uint32_t pass_base) {
+    const uint32_t base_pos = c.origin + threadIdx.x * 128u;
+    uint32_t r = excl;
+    const uint32_t w[4] = {words.x, words.y, words.z, words.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t m = w[i];
+        while (m) {
+            const uint32_t b = __ffs(m) - 1u;
+            m &= m - 1u;
+            const uint32_t rel = r - pass_base;
+            if (rel < (uint32_t)kNlCap) S.nlx[kHead + rel] = base_pos + 32u * i + b;
+            ++r;
+        }
+    }
+}
+
+// After a pass of n entries: the kHead most recent newline positions move to the front.
+__device__ __forceinline__ void rotate_head(TileSmem& S, uint32_t n) {
+    // caller guarantees a barrier before (all readers done) and after
+    if (threadIdx.x == 0) {
+        uint32_t t[kHead];
+#pragma unroll
+        for (int i = 0; i < kHead; ++i) t[i] = S.nlx[n + i];
+#pragma unroll
+        for (int i = 0; i < kHead; ++i) S.nlx[i] = t[i];
+    }
+}
+
+// byte of the window at offset pos: shared memory when the current tile holds it
+__device__ __forceinline__ uint32_t byte_at(const TileSmem& S, const TileCursor& c, const WinParams& W,
+                                            uint32_t pos) {
+    const uint32_t rel = pos - c.origin;  // wraps to a large value for pos < origin
+    if (rel < (uint32_t)kTile) return S.data[c.stage][rel];
+    return __ldg(W.base + pos);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_summarize
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void run_tiles(const WinParams& W, uint32_t run, uint32_t& ta, uint32_t& tb) {
+    ta = W.first_tile + run * W.tiles_per_run;
+    tb = ta + W.tiles_per_run;
+    if (tb > W.n_tiles) tb = W.n_tiles;
+    if (ta > tb) ta = tb;
+}
+
+__device__ __forceinline__ TileCursor make_cursor(const WinParams& W, uint32_t tile, uint32_t stage) {
+    TileCursor c;
+    c.tile = tile;
+    c.origin = tile * (uint32_t)kTile;
+    c.lo = c.origin < W.begin ? W.begin : c.origin;
+    const uint32_t e = c.origin + (uint32_t)kTile;
+    c.hi = (e > W.end || e < c.origin) ? W.end : e;
+    c.stage = stage;
+    return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 2) k_summarize(const WinParams W, BsqSummary* __restrict__ run_sum) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    uint32_t ta, tb;
+    run_tiles(W, blockIdx.x, ta, tb);
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&S.full_bar[s], 1);
+        mbar_fence_init();
+    }
+    if (tid < kHead) S.nlx[tid] = 0;
+    __syncthreads();
+    if (tid == 0)
+        for (uint32_t s = 0; s < (uint32_t)kStages && ta + s < tb; ++s) issue_tile_load(S, W, ta + s, s);
+
+    uint32_t run_count = 0;           // newlines of the run so far (uniform)
+    uint32_t acc[4] = {0, 0, 0, 0};   // position sums by (index in run) mod 4, this thread's share
+    uint32_t flag = 0;
+
+    for (uint32_t t = ta; t < tb; ++t) {
+        const uint32_t it = t - ta;
+        const TileCursor c = make_cursor(W, t, it % kStages);
+        mbar_wait(&S.full_bar[c.stage], (it / kStages) & 1u);
+        build_bitmaps<false, false>(S, c, 0, 0);
+        __syncthreads();
+        const uint4 words = *reinterpret_cast<const uint4*>(&S.bm_nl[tid * 4]);
+        const uint32_t cnt = __popc(words.x) + __popc(words.y) + __popc(words.z) + __popc(words.w);
+        uint32_t total;
+        const uint32_t excl = block_exclusive_scan(S, cnt, total);
+        uint32_t sum = 0;
+        for (uint32_t pass = 0; pass < total; pass += kNlCap) {
+            const uint32_t n = total - pass < (uint32_t)kNlCap ? total - pass : (uint32_t)kNlCap;
+            fill_newline_list(S, c, words, excl, pass);
+            __syncthreads();
+            for (uint32_t j = tid; j < n; j += kThreads) {
+                const uint32_t p = S.nlx[kHead + j];
+                sum += p;
+                if (run_count + pass + j < 4u) S.carry[run_count + pass + j] = p;  // first[] of the run
+                // may some header need _strip_spaces?  (conservative: every line is looked at)
+                if (p > W.begin && bsq_is_space(byte_at(S, c, W, p - 1u))) flag = BSQ_SUM_ID_MAY_STRIP;
+                if (p + 2u < W.end && byte_at(S, c, W, p + 1u) == '@' && bsq_is_space(byte_at(S, c, W, p + 2u)))
+                    flag = BSQ_SUM_ID_MAY_STRIP;
+            }
+            __syncthreads();
+            rotate_head(S, n);
+            __syncthreads();
+        }
+        // kNlCap and kThreads are multiples of 4: every newline this thread summed has the same class
+        const uint32_t cls = (run_count + tid) & 3u;
+        acc[0] += cls == 0u ? sum : 0u;
+        acc[1] += cls == 1u ? sum : 0u;
+        acc[2] += cls == 2u ? sum : 0u;
+        acc[3] += cls == 3u ? sum : 0u;
+        run_count += total;
+        __syncthreads();  // every thread is done with data[stage]
+        if (tid == 0 && t + kStages < tb) issue_tile_load(S, W, t + kStages, c.stage);
+    }
+    if (blockIdx.x == 0 && tid == 0 && W.begin + 1u < W.end && __ldg(W.base + W.begin) == '@' &&
+        bsq_is_space(__ldg(W.base + W.begin + 1u)))
+        flag = BSQ_SUM_ID_MAY_STRIP;
+
+    // block reduction of acc[4] and flag
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += __shfl_xor_sync(0xFFFFFFFFu, acc[k], d);
+        flag |= __shfl_xor_sync(0xFFFFFFFFu, flag, d);
+    }
+    __syncthreads();
+    if ((tid & 31u) == 0u) {
+        for (int k = 0; k < 4; ++k) S.sdst[0][(tid >> 5) * 4 + k] = acc[k];
+        S.sdst[1][tid >> 5] = flag;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        BsqSummary s = bsq_summary_identity();
+        s.count = run_count;
+        for (int w = 0; w < kWarps; ++w) {
+            for (int k = 0; k < 4; ++k) s.P[k] += S.sdst[0][w * 4 + k];
+            s.flags |= S.sdst[1][w];
+        }
+        for (int i = 0; i < 4; ++i) s.last[i] = S.nlx[kHead - 1 - i];
+        for (uint32_t i = 0; i < 4u; ++i) s.first[i] = i < run_count ? S.carry[i] : 0u;
+        run_sum[blockIdx.x] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_scan_runs: one CTA; n_runs is a few hundred
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kMaxRuns = 384;
+
+__global__ void __launch_bounds__(256, 1) k_scan_runs(const BsqSummary* __restrict__ run_sum, uint32_t n_runs,
+                                                      uint32_t begin, BsqPrefix* __restrict__ run_pre,
+                                                      ScanOut* __restrict__ out) {
+    __shared__ BsqSummary s_sum[kMaxRuns];
+    __shared__ BsqPrefix s_pre[kMaxRuns];
+    // stage the summaries with all threads (16-byte pieces), scan with one, write back with all
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(run_sum);
+        uint4* dst = reinterpret_cast<uint4*>(s_sum);
+        for (uint32_t i = threadIdx.x; i < n_runs * 4u; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        BsqSummary E = bsq_summary_window_init(begin);
+        BsqSummary R = bsq_summary_identity();
+        for (uint32_t r = 0; r < n_runs; ++r) {
+            s_pre[r] = bsq_prefix_from(E, begin);
+            E = bsq_combine(E, s_sum[r]);
+            R = bsq_combine(R, s_sum[r]);
+        }
+        out->totals = bsq_totals_from(E, begin);
+        out->end_state = E;
+        out->region = R;
+    }
+    __syncthreads();
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(s_pre);
+        uint4* dst = reinterpret_cast<uint4*>(run_pre);
+        for (uint32_t i = threadIdx.x; i < n_runs * 2u; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_resolve
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void report(const ResolveParams& P, uint32_t k, uint32_t code) {
+    const unsigned long long key = ((unsigned long long)(P.first_record + P.rec_base + (int64_t)k) << 8) | code;
+    atomicMin(P.err, key);
+}
+
+// 16 source bytes starting at window offset pos (any alignment).  Lines end inside the current
+// tile, so pos + 16 never runs past the tile padding.
+__device__ __forceinline__ uint4 load16(const TileSmem& S, const TileCursor& c, const WinParams& W, uint32_t pos) {
+    const uint32_t rel = pos - c.origin;
+    uint4 r;
+    if (rel < (uint32_t)kTile) {
+        const uint8_t* t = S.data[c.stage];
+        const uint32_t a = rel & ~15u;
+        const uint4 lo = *reinterpret_cast<const uint4*>(t + a);
+        const uint4 hi = *reinterpret_cast<const uint4*>(t + a + 16u);
+        const uint32_t sh = (rel & 3u) * 8u;
+        uint32_t w0, w1, w2, w3, w4;
+        switch ((rel >> 2) & 3u) {
+            case 0: w0 = lo.x; w1 = lo.y; w2 = lo.z; w3 = lo.w; w4 = hi.x; break;
+            case 1: w0 = lo.y; w1 = lo.z; w2 = lo.w; w3 = hi.x; w4 = hi.y; break;
+            case 2: w0 = lo.z; w1 = lo.w; w2 = hi.x; w3 = hi.y; w4 = hi.z; break;
+            default: w0 = lo.w; w1 = hi.x; w2 = hi.y; w3 = hi.z; w4 = hi.w; break;
+        }
+        r.x = __funnelshift_r(w0, w1, sh);
+        r.y = __funnelshift_r(w1, w2, sh);
+        r.z = __funnelshift_r(w2, w3, sh);
+        r.w = __funnelshift_r(w3, w4, sh);
+    } else {  // the line started in an earlier tile: bytes come from global memory (L2)
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) x |= byte_at(S, c, W, pos + 4 * i + b) << (8 * b);
+            w[i] = x;
+        }
+        r = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return r;
+}
+
+// Copies the lines of one class stream that ended in this pass: destination range [d0, d1) of the
+// stream (virtual offsets: out is 16-byte aligned and d includes the sub-16 shift).
+__device__ __forceinline__ void copy_stream(const TileSmem& S, const TileCursor& c, const WinParams& W,
+                                            const uint32_t* __restrict__ sdst, const uint32_t* __restrict__ ssrc,
+                                            uint32_t n_lines, uint32_t d0, uint32_t d1, uint8_t* __restrict__ out,
+                                            int64_t room) {
+    // room = bytes the arena can still take from `out`.  Destinations past it only arise after
+    // a structure error (an empty header line makes the id prefix diverge); nothing there counts.
+    if (d1 <= d0 || (int64_t)d1 > room) return;
+    const uint32_t v0 = d0 >> 4, v1 = (d1 + 15u) >> 4;
+    for (uint32_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+        const uint32_t lo = v * 16u < d0 ? d0 : v * 16u;
+        const uint32_t hi = v * 16u + 16u > d1 ? d1 : v * 16u + 16u;
+        // last line with sdst <= lo; sdst[n_lines] = d1 is the sentinel
+        uint32_t a = 0, b = n_lines;
+        while (b - a > 1u) {
+            const uint32_t m = (a + b) >> 1;
+            if (sdst[m] <= lo) a = m; else b = m;
+        }
+        uint32_t i = a;
+        if (hi - lo == 16u && sdst[i + 1] >= hi) {
+            const uint4 x = load16(S, c, W, ssrc[i] + (lo - sdst[i]));
+            *reinterpret_cast<uint4*>(out + (size_t)v * 16u) = x;
+        } else {
+            for (uint32_t d = lo; d < hi; ++d) {
+                while (sdst[i + 1] <= d) ++i;  // skips empty lines; the sentinel stops it
+                out[d] = (uint8_t)byte_at(S, c, W, ssrc[i] + (d - sdst[i]));
+            }
+        }
+    }
+}
+
+template <bool kAscii, bool kQual, bool kOffsets, bool kPack>
+__global__ void __launch_bounds__(kThreads, 2) k_resolve(const WinParams W, const ResolveParams P) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    uint32_t ta, tb;
+    run_tiles(W, blockIdx.x, ta, tb);
+    const BsqPrefix pre = P.run_pre[blockIdx.x];
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&S.full_bar[s], 1);
+        mbar_fence_init();
+        S.nlx[0] = 0; S.nlx[1] = pre.prev[2]; S.nlx[2] = pre.prev[1]; S.nlx[3] = pre.prev[0];
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (uint32_t s = 0; s < (uint32_t)kStages && ta + s < tb; ++s) issue_tile_load(S, W, ta + s, s);
+    if (kOffsets && blockIdx.x == 0 && tid == 0) P.line_ends[0] = W.begin - 1u;
+
+    const uint32_t addlo = (128u - P.lower) * 0x01010101u, addup = (127u - P.upper) * 0x01010101u;
+    uint32_t rank = pre.rank;                                            // rank of the tile's first newline
+    uint32_t cum_id = pre.cum_id, cum_seq = pre.cum_seq, cum_qual = pre.cum_qual;  // stream destinations
+    // virtual destination offsets: out pointers rounded down to 16 bytes, offsets shifted up
+    const uint32_t sh_id = (uint32_t)(P.id_base64 & 15), sh_seq = (uint32_t)(P.seq_base64 & 15),
+                   sh_qual = (uint32_t)(P.qual_base64 & 15);
+    uint8_t* const out_id = kPack ? P.id_out + (P.id_base64 - sh_id) : nullptr;
+    uint8_t* const out_seq = kPack ? P.seq_out + (P.seq_base64 - sh_seq) : nullptr;
+    uint8_t* const out_qual = kPack ? P.qual_out + (P.qual_base64 - sh_qual) : nullptr;
+
+    for (uint32_t t = ta; t < tb; ++t) {
+        const uint32_t it = t - ta;
+        const TileCursor c = make_cursor(W, t, it % kStages);
+        mbar_wait(&S.full_bar[c.stage], (it / kStages) & 1u);
+        build_bitmaps<kAscii, kQual>(S, c, addlo, addup);
+        __syncthreads();
+        const uint4 words = *reinterpret_cast<const uint4*>(&S.bm_nl[tid * 4]);
+        const uint32_t cnt = __popc(words.x) + __popc(words.y) + __popc(words.z) + __popc(words.w);
+        uint32_t total;
+        const uint32_t excl = block_exclusive_scan(S, cnt, total);
+
+        // ---- validation from the bitmaps: this thread's 128 bytes, line class known from the rank
+        if (kAscii || kQual) {
+            uint32_t r = rank + excl;
+            const uint32_t nlw[4] = {words.x, words.y, words.z, words.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t nl = nlw[i];
+                const uint32_t hiw = kAscii ? S.bm_hi[tid * 4 + i] : 0u;
+                const uint32_t badw = kQual ? (S.bm_bad[tid * 4 + i] & ~nl) : 0u;
+                if ((hiw | badw) != 0u) {
+                    uint32_t rest = 0xFFFFFFFFu, m = nl, rr = r;
+                    while (rest) {
+                        // segment = bytes up to and including the next newline (or the word's end)
+                        uint32_t seg = rest;
+                        if (m) { const uint32_t b = __ffs(m) - 1u; seg = rest & (0xFFFFFFFFu >> (31u - b)); m &= m - 1u; }
+                        const uint32_t cls = rr & 3u, k = rr >> 2;
+                        if (k < P.n_complete) {
+                            if (kAscii && cls != 2u && (hiw & seg)) report(P, k, 4u);
+                            if (kQual && cls == 3u && (badw & seg)) report(P, k, 5u);
+                        }
+                        rest &= ~seg;
+                        ++rr;
+                    }
+                }
+                r += __popc(nl);
+            }
+        }
+
+        for (uint32_t pass = 0; pass < total; pass += kNlCap) {
+            const uint32_t n = total - pass < (uint32_t)kNlCap ? total - pass : (uint32_t)kNlCap;
+            fill_newline_list(S, c, words, excl, pass);
+            __syncthreads();
+            const uint32_t r0 = rank + pass;  // rank of list entry 0
+            // stream bookkeeping for this pass
+            const uint32_t d0_id = cum_id, d0_seq = cum_seq, d0_qual = cum_qual;
+            const uint32_t j_id = (0u - r0) & 3u, j_seq = (1u - r0) & 3u, j_qual = (3u - r0) & 3u;
+
+            for (uint32_t jb = 0; jb < n; jb += kThreads) {
+                const uint32_t j = jb + tid;
+                uint32_t v_id = 0, v_seq = 0, v_qual = 0, cls = 4, k = 0, p = 0, q1 = 0, len = 0, src = 0;
+                bool live = false;
+                if (j < n) {
+                    p = S.nlx[kHead + j];
+                    q1 = S.nlx[kHead + j - 1];
+                    const uint32_t r = r0 + j;
+                    cls = r & 3u; k = r >> 2;
+                    live = k < P.n_complete;
+                    len = p - q1 - 1u;
+                    if (live) {
+                        if (cls == 0u) {
+                            // header line: '@' check (utils.mojo:454), id = line minus '@', stripped
+                            const uint32_t hs = q1 + 1u;
+                            if (byte_at(S, c, W, hs) != '@') report(P, k, 1u);
+                            uint32_t a = hs + 1u, nid = len > 0u ? len - 1u : 0u;
+                            if (nid > 0u && (bsq_is_space(byte_at(S, c, W, a)) || bsq_is_space(byte_at(S, c, W, p - 1u)))) {
+                                uint32_t e = p;
+                                while (a < e && bsq_is_space(byte_at(S, c, W, a))) ++a;
+                                while (e > a && bsq_is_space(byte_at(S, c, W, e - 1u))) --e;
+                                nid = e - a;
+                            }
+                            if (kOffsets || (kPack && !P.id_fast)) { P.id_spans[2u * k] = a; P.id_spans[2u * k + 1u] = nid; }
+                            v_id = nid; src = a;
+                        } else if (cls == 1u) {
+                            v_seq = len; src = q1 + 1u;
+                        } else if (cls == 2u) {
+                            if (byte_at(S, c, W, q1 + 1u) != '+') report(P, k, 2u);  // utils.mojo:456
+                        } else {
+                            const uint32_t q2 = S.nlx[kHead + j - 2], q3 = S.nlx[kHead + j - 3];
+                            if (q2 - q3 - 1u != len) report(P, k, 3u);              // utils.mojo:458-461
+                            v_qual = len; src = q1 + 1u;
+                        }
+                    }
+                    if (kOffsets) P.line_ends[1u + r] = p;
+                }
+                if (kPack) {
+                    uint32_t e_id, e_seq, e_qual, t_id, t_seq, t_qual;
+                    block_exclusive_scan3(S, v_id, v_seq, v_qual, e_id, e_seq, e_qual, t_id, t_seq, t_qual);
+                    if (j < n && cls != 2u && cls != 4u) {
+                        // one entry per line of the class, live or not (dead lines have length 0)
+                        if (cls == 0u) {
+                            const uint32_t i = (j - j_id) >> 2;
+                            S.sdst[0][i] = cum_id + e_id + sh_id; S.ssrc[0][i] = src;
+                            if (live && P.id_fast) {
+                                const int64_t endv = P.id_base64 + (int64_t)(cum_id + e_id + v_id);
+                                const int64_t gk = P.rec_base + (int64_t)k;
+                                P.id_ends_abs[gk] = endv;
+                                if ((gk + 1) % P.batch_size == 0) P.id_ends_base[(gk + 1) / P.batch_size] = endv;
+                            }
+                        } else if (cls == 1u) {
+                            const uint32_t i = (j - j_seq) >> 2;
+                            S.sdst[1][i] = cum_seq + e_seq + sh_seq; S.ssrc[1][i] = src;
+                        } else {
+                            const uint32_t i = (j - j_qual) >> 2;
+                            S.sdst[2][i] = cum_qual + e_qual + sh_qual; S.ssrc[2][i] = src;
+                            if (live) {
+                                const int64_t endv = P.qual_base64 + (int64_t)(cum_qual + e_qual + v_qual);
+                                const int64_t gk = P.rec_base + (int64_t)k;
+                                P.ends_abs[gk] = endv;
+                                if ((gk + 1) % P.batch_size == 0) P.ends_base[(gk + 1) / P.batch_size] = endv;
+                            }
+                        }
+                    }
+                    cum_id += t_id; cum_seq += t_seq; cum_qual += t_qual;
+                }
+            }
+            if (kPack) {
+                const uint32_t n_id = j_id < n ? ((n - 1u - j_id) >> 2) + 1u : 0u;
+                const uint32_t n_seq = j_seq < n ? ((n - 1u - j_seq) >> 2) + 1u : 0u;
+                const uint32_t n_qual = j_qual < n ? ((n - 1u - j_qual) >> 2) + 1u : 0u;
+                if (tid == 0) {
+                    S.sdst[0][n_id] = cum_id + sh_id; S.sdst[1][n_seq] = cum_seq + sh_seq;
+                    S.sdst[2][n_qual] = cum_qual + sh_qual;
+                }
+                __syncthreads();
+                const int64_t big = (int64_t)1 << 40;
+                if (P.id_fast)
+                    copy_stream(S, c, W, S.sdst[0], S.ssrc[0], n_id, d0_id + sh_id, cum_id + sh_id, out_id,
+                                P.id_cap - (P.id_base64 - sh_id));
+                copy_stream(S, c, W, S.sdst[1], S.ssrc[1], n_seq, d0_seq + sh_seq, cum_seq + sh_seq, out_seq, big);
+                copy_stream(S, c, W, S.sdst[2], S.ssrc[2], n_qual, d0_qual + sh_qual, cum_qual + sh_qual, out_qual, big);
+            }
+            __syncthreads();
+            rotate_head(S, n);
+            __syncthreads();
+        }
+        rank += total;
+        __syncthreads();
+        if (tid == 0 && t + kStages < tb) issue_tile_load(S, W, t + kStages, c.stage);
+    }
+}
+
+}  // namespace bsq

@@ -1,0 +1,237 @@
+/*
+ * blazeseq_gpu.h -- C ABI of the B200 FASTQ record tokenizer / validator / SoA packer.
+ *
+ * Drop-in boundary for the hot path of MoSafi2/BlazeSeq (reference paths are relative to its
+ * repository root).  The reference has no FFI for this path -- it is a generic Mojo struct
+ * consumed in-process -- so every entry point names the reference symbol it stands in for.  Mojo
+ * reaches C through OwnedDLHandle(...).get_function (blazeseq/io/readers.mojo:242-280), hence:
+ * plain C, POD structs, no callbacks, no exceptions; every function returns a bsq_status.
+ *
+ * Model.  A parser parses one contiguous region of a FASTQ byte stream per call ("pass").  The
+ * pass finds every complete 4-line record, checks structure ('@', '+', equal seq/qual length),
+ * optionally validates ASCII and the quality range, and leaves on the device:
+ *   - the offsets table  (views():   blazeseq/fastq/parser.mojo:160-170,311-379)
+ *   - the FastqBatch SoA (batches(): blazeseq/fastq/parser.mojo:239-251,
+ *                                    blazeseq/fastq/record_batch.mojo:19-87,210-220)
+ * It reports how many bytes it consumed (through the last complete record), exactly like
+ * BufferedReader.consume (blazeseq/io/buffered.mojo:156-164); the caller re-presents the
+ * unconsumed tail in front of the next region (the reference's _compact_from, :239-260).
+ * All compute runs in CUDA kernels on the parser's device; there is no CPU fallback.
+ */
+#ifndef BLAZESEQ_GPU_H
+#define BLAZESEQ_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSQ_ABI_VERSION 1
+
+/* >= 0: FastxErrorCode, identical to blazeseq/errors.mojo:43-56.  < 0: library failures. */
+typedef int32_t bsq_status;
+enum {
+    BSQ_OK = 0,
+    BSQ_ID_NO_AT = 1,
+    BSQ_SEP_NO_PLUS = 2,
+    BSQ_SEQ_QUAL_LEN_MISMATCH = 3,
+    BSQ_ASCII_INVALID = 4,
+    BSQ_QUALITY_OUT_OF_RANGE = 5,
+    BSQ_EOF = 6,
+    BSQ_UNEXPECTED_EOF = 7,
+    BSQ_BUFFER_EXCEEDED = 8,
+    BSQ_BUFFER_AT_MAX = 9,
+    BSQ_OTHER = 10,
+    BSQ_EMPTY_ERROR = 11,      /* `raise Error()` with empty text, parser.mojo:350-351 */
+    BSQ_E_CUDA = -1,           /* a CUDA runtime call failed; see bsq_last_error_text */
+    BSQ_E_ARG = -2,            /* bad argument */
+    BSQ_E_NO_DEVICE = -3,      /* no usable CUDA device: this library never parses on the CPU */
+    BSQ_E_NOMEM = -4,
+    BSQ_E_STATE = -5           /* call sequence error (e.g. results requested before a pass) */
+};
+
+/* what a pass materialises */
+#define BSQ_WANT_OFFSETS 1u    /* views(): line-end table + stripped id spans */
+#define BSQ_WANT_BATCHES 2u    /* batches(): FastqBatch SoA */
+
+/* ParserConfig (parser.mojo:33-74) + the resolved QualitySchema (quality_schema.mojo:9-31).
+ * check_ascii / check_quality select the kernel instantiation (the reference's comptime
+ * toggles). */
+typedef struct bsq_config {
+    int32_t device_id;             /* CUDA ordinal */
+    int32_t check_ascii;           /* ParserConfig.check_ascii */
+    int32_t check_quality;         /* ParserConfig.check_quality */
+    uint8_t q_lower, q_upper, q_offset, _pad0; /* QualitySchema.LOWER/UPPER/OFFSET */
+    int64_t buffer_capacity;       /* ParserConfig.buffer_capacity (error text, tail rule Q2) */
+    int64_t buffer_max_capacity;   /* ParserConfig.buffer_max_capacity */
+    int32_t buffer_growth_enabled; /* ParserConfig.buffer_growth_enabled */
+    int32_t batch_size;            /* FastqParser._batch_size, DEFAULT_BATCH_SIZE = 4096 */
+    int64_t h2d_chunk_bytes;       /* staging chunk for bsq_parse_host (default 64 MiB) */
+    int32_t force_id_slow_path;    /* tests: always take the id strip pipeline */
+    int32_t _pad1;
+} bsq_config;
+
+/* The first error of a pass, with the context the reference prints
+ * (errors.mojo:178-192,223-234; parser.mojo:332-338,163-169). */
+typedef struct bsq_error {
+    int32_t code;                  /* BSQ_OK / BSQ_EOF when the pass ended cleanly */
+    int32_t _pad;
+    int64_t record_number;         /* 1-based; 0 = not reported */
+    int64_t line_number;           /* 1-based; 0 = not reported */
+    int64_t file_position;         /* stream offset; 0 = not reported */
+    char message[1024];            /* String(e) of the reference, NUL-terminated */
+} bsq_error;
+
+/* Result of one pass. */
+typedef struct bsq_pass_result {
+    int64_t n_records;             /* records before the stop (EOF or first error) */
+    int64_t n_bases;               /* sum of sequence lengths over those records */
+    int64_t bytes_consumed;        /* through the last complete record (== n when is_last) */
+    int64_t n_newlines;            /* '\n' count of the region */
+    int64_t n_batches;             /* ceil(n_records / batch_size) when BSQ_WANT_BATCHES */
+    int32_t n_windows;             /* offsets tables are per window (<= 2 GiB of input each) */
+    int32_t id_slow_path;          /* 1 if some id needed _strip_spaces (utils.mojo:221-242) */
+    bsq_error stop;                /* why the pass stopped: BSQ_EOF, BSQ_OK (more input needed)
+                                      or the first error */
+} bsq_pass_result;
+
+/* views(): one window of the offsets table.  Record i of the window (global record
+ * first_record + i) has, relative to the window base (stream offset stream_base):
+ *   header_start = line_ends[4i]+1   seq_start = line_ends[4i+1]+1   sep_start = line_ends[4i+2]+1
+ *   qual_start   = line_ends[4i+3]+1 record_end = line_ends[4i+4]
+ * (RecordOffsets, utils.mojo:37-93: u32 arithmetic, the leading sentinel makes i = 0 regular)
+ * and the id after _strip_spaces is [id_spans[2i], id_spans[2i] + id_spans[2i+1]).
+ * Pointers are DEVICE pointers, valid until the next pass or bsq_destroy. */
+typedef struct bsq_offsets_view {
+    int64_t stream_base;
+    int64_t first_record;
+    int64_t n_records;
+    const uint32_t* line_ends;     /* 4*n_records + 1 entries */
+    const uint32_t* id_spans;      /* 2*n_records entries */
+    const uint8_t* window_bytes;   /* device address of stream_base (NULL for host passes whose
+                                      input was streamed through the staging ring) */
+} bsq_offsets_view;
+
+/* batches(): one FastqBatch / DeviceFastqBatch (record_batch.mojo:22-27,210-220).  ends and
+ * id_ends are inclusive cumulative Int64 restarting at 0 for the batch (:82-87).  DEVICE
+ * pointers, valid until the next pass or bsq_destroy. */
+typedef struct bsq_batch_view {
+    int64_t num_records;
+    int64_t seq_len;               /* == ends[num_records-1] */
+    int64_t total_id_bytes;
+    uint8_t quality_offset;        /* always 33 on this path (parser.mojo:243) */
+    uint8_t _pad[7];
+    const uint8_t* sequence_buffer;
+    const uint8_t* qual_buffer;
+    const uint8_t* id_buffer;
+    const int64_t* ends;
+    const int64_t* id_ends;
+} bsq_batch_view;
+
+/* ---- configuration helpers (host only) --------------------------------------------------- */
+
+/* ParserConfig() defaults (parser.mojo:60-74) with generic_schema (quality_schema.mojo:26). */
+void bsq_default_config(bsq_config* cfg);
+/* _parse_schema (utils.mojo:612-637).  Returns 0, or 1 for an unknown name (falls back to
+ * generic like the reference, which prints a warning). */
+int32_t bsq_parse_schema(const char* name, uint8_t* lower, uint8_t* upper, uint8_t* offset);
+uint32_t bsq_abi_version(void);
+
+/* ---- parser lifetime ------------------------------------------------------------------------ */
+
+typedef struct bsq_parser bsq_parser;
+
+/* FastqParser.__init__ (parser.mojo:89-145).  One parser = one device, one stream pair. */
+bsq_status bsq_create(const bsq_config* cfg, bsq_parser** out);
+void bsq_destroy(bsq_parser* p);
+/* Text of the last library failure (status < 0) on this parser ("" if none). */
+const char* bsq_last_error_text(const bsq_parser* p);
+/* FastqParser.batches(max_records) / next_batch(max_records) (parser.mojo:239-274): the batch
+ * size used by the passes that follow. */
+bsq_status bsq_set_batch_size(bsq_parser* p, int32_t batch_size);
+
+/* ---- passes ------------------------------------------------------------------------------------ */
+
+/* Parse n bytes that are already in DEVICE memory.  stream_offset = position of dev_bytes[0] in
+ * the stream (only used for error context); first_record = number of records before it
+ * (record/line numbers in errors, batch cutting).  is_last: the region ends the stream, so the
+ * tail rule applies (parser.mojo:460-492, utils.mojo:292-329).  `want` = BSQ_WANT_* bits.
+ * Synchronous.  Stands in for the _find_and_consume_ref_record loop (parser.mojo:311-379) over a
+ * MemoryReader-style buffer. */
+bsq_status bsq_parse_device(bsq_parser* p, const uint8_t* dev_bytes, uint64_t n,
+                            int64_t stream_offset, int64_t first_record, int32_t is_last,
+                            uint32_t want, bsq_pass_result* out);
+
+/* Same, for n bytes in HOST memory (pinned or pageable).  The bytes are copied to the device in
+ * h2d_chunk_bytes pieces on a side stream, double-buffered through pinned staging when the source
+ * is pageable, overlapped with the first scan pass.  Replaces Reader.read_to_buffer +
+ * BufferedReader (readers.mojo:51-79, buffered.mojo:115-327) + the parse loop. */
+bsq_status bsq_parse_host(bsq_parser* p, const uint8_t* host_bytes, uint64_t n,
+                          int64_t stream_offset, int64_t first_record, int32_t is_last,
+                          uint32_t want, bsq_pass_result* out);
+
+/* ---- results of the last pass -------------------------------------------------------------- */
+
+bsq_status bsq_get_offsets(const bsq_parser* p, int32_t window, bsq_offsets_view* out);
+/* FastqParser.next_batch(max_records) restricted to the pass: batch b holds records
+ * [b*batch_size, min((b+1)*batch_size, n_records)). */
+bsq_status bsq_get_batch(const bsq_parser* p, int64_t batch_index, bsq_batch_view* out);
+/* Whole-pass SoA (all batches back to back; ends/id_ends are the per-batch rebased values). */
+bsq_status bsq_get_soa(const bsq_parser* p, bsq_batch_view* out);
+/* DeviceFastqBatch.copy_to_host (record_batch.mojo:222-241): copies one batch into caller
+ * arrays sized from bsq_batch_view (seq_len, seq_len, total_id_bytes, num_records, num_records). */
+bsq_status bsq_batch_to_host(bsq_parser* p, int64_t batch_index, uint8_t* seq, uint8_t* qual,
+                             uint8_t* id, int64_t* ends, int64_t* id_ends);
+/* Copies one window's offsets table to the host (line_ends: 4n+1, id_spans: 2n entries). */
+bsq_status bsq_offsets_to_host(bsq_parser* p, int32_t window, uint32_t* line_ends,
+                               uint32_t* id_spans);
+/* Device address of the input of the last pass (the staged copy for host passes). */
+const uint8_t* bsq_pass_device_input(const bsq_parser* p);
+
+/* ---- measurement hooks ------------------------------------------------------------------------ */
+
+/* Device time (ms, CUDA events on the parser's stream) of the kernels of the last pass:
+ * [0] summarise runs, [1] scan, [2] resolve/validate/pack, [3] id pipeline + tail + rebase,
+ * [4] whole pass including H2D for host passes.  n_launches = kernels launched by the pass. */
+bsq_status bsq_last_timing(const bsq_parser* p, float ms[5], int64_t* n_launches);
+
+/* ---- synthetic input (blazeseq/utils.mojo:640-678,831-917), generated on the device -------- */
+
+int64_t bsq_compute_num_reads_for_size(int64_t target_size_bytes, int64_t min_length,
+                                       int64_t max_length);
+int64_t bsq_synth_size(int64_t num_reads, int64_t min_length, int64_t max_length);
+/* Writes records [first, first+count) of generate_synthetic_fastq_buffer(num_reads, ...) to
+ * dev_out (device memory, capacity bytes); returns bytes written through *written. */
+bsq_status bsq_synth_device(bsq_parser* p, uint8_t* dev_out, uint64_t capacity, int64_t num_reads,
+                            int64_t first, int64_t count, int64_t min_length, int64_t max_length,
+                            int64_t min_phred, int64_t max_phred, uint8_t q_lower,
+                            uint8_t q_upper, uint8_t q_offset, uint64_t* written);
+
+/* ---- multi-GPU: shard stitching (host arithmetic) ------------------------------- */
+
+/* Summary of a byte range under the newline-rank algebra (csrc/tile_math.h).  A rank summarises
+ * its shard with bsq_summarize_device, all-gathers the 64-byte records, and every rank derives
+ * where its first record starts with bsq_shard_prefix -- only 64 bytes per rank cross GPUs. */
+typedef struct bsq_summary { uint32_t w[16]; } bsq_summary;
+typedef struct bsq_shard_start {
+    int64_t newline_rank;          /* rank of the shard's first newline in the whole stream */
+    int64_t first_record;          /* index of the first record that STARTS in the shard */
+    int64_t skip_bytes;            /* leading bytes that belong to a record of the previous shard;
+                                      == shard size when no record starts in the shard */
+    int32_t phase;                 /* newline_rank mod 4: lines of the open record already seen */
+    int32_t _pad;
+} bsq_shard_start;
+bsq_status bsq_summarize_device(bsq_parser* p, const uint8_t* dev_bytes, uint64_t n,
+                                bsq_summary* out);
+/* shards[0..n_shards) in stream order with their sizes; fills start[i] for every shard.  A record
+ * is owned by the shard that holds its first byte, so rank i parses the bytes
+ * [skip_bytes[i], shard_bytes[i] + skip_bytes[i+1]) of its shard (+ halo) as one region. */
+bsq_status bsq_shard_prefix(const bsq_summary* shards, const uint64_t* shard_bytes, int32_t n_shards,
+                            bsq_shard_start* start);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLAZESEQ_GPU_H */

@@ -1,0 +1,220 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports what the header
+declares, configuration helpers, host containers and readers, shard stitching arithmetic, and the
+N > 1 path over gloo (world_size 2).  No kernel runs here."""
+import ctypes as C
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def B():
+    import blazeseq_b200
+    return blazeseq_b200
+
+
+def test_library_exports_every_declared_symbol(B):
+    hdr = open(os.path.join(ROOT, "include", "blazeseq_gpu.h")).read()
+    declared = set(re.findall(r"\b(bsq_[a-z_0-9]+)\(", hdr))
+    assert declared == set(B._capi.SYMBOLS), declared ^ set(B._capi.SYMBOLS)
+    L = B._capi.lib()
+    for name in declared:
+        assert getattr(L, name) is not None
+    assert L.bsq_abi_version() == 1
+
+
+def test_struct_layouts_match_header(B):
+    c = B._capi
+    assert C.sizeof(c.Config) == 56 and C.sizeof(c.Error) == 1056 and C.sizeof(c.Summary) == 64
+    assert C.sizeof(c.PassResult) == 48 + 1056 and C.sizeof(c.OffsetsView) == 48
+    assert C.sizeof(c.BatchView) == 72 and C.sizeof(c.ShardStart) == 32
+
+
+def test_no_cpu_fallback(B):
+    """Without a CUDA device the product refuses to construct a parser."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(B._capi.BsqLibraryError):
+        B.FastqParser(B.MemoryReader(b"@a\nA\n+\n!\n"))
+    h = C.c_void_p()
+    assert B._capi.lib().bsq_create(None, C.byref(h)) == B._capi.E_NO_DEVICE
+
+
+def test_product_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "blazeseq_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in src.lower() or f in (), (f, "product code must not reference oracle/")
+
+
+def test_config_defaults_and_schema_table(B, oracle):
+    cfg = B._capi.default_config()
+    assert (cfg.buffer_capacity, cfg.buffer_max_capacity, cfg.batch_size) == (256 * 1024, 1 << 30, 4096)
+    assert (cfg.check_ascii, cfg.check_quality, cfg.buffer_growth_enabled) == (0, 0, 0)
+    assert (cfg.q_lower, cfg.q_upper, cfg.q_offset) == (33, 126, 33)
+    for name in ("generic", "sanger", "solexa", "illumina_1.3", "illumina_1.5", "illumina_1.8", "bogus"):
+        assert B._capi.parse_schema(name) == oracle.schema(name)
+    pc = B.ParserConfig()
+    assert (pc.buffer_capacity, pc.check_ascii, pc.check_quality, pc.quality_schema) == (262144, False, False, None)
+
+
+def test_synthetic_size_arithmetic(B, oracle):
+    L = B._capi.lib()
+    for t in (3 << 30, 10 << 30, 1 << 20, 0):
+        for mn, mx in ((100, 100), (150, 150), (75, 300), (5, 12)):
+            assert L.bsq_compute_num_reads_for_size(t, mn, mx) == oracle.compute_num_reads_for_size(t, mn, mx)
+    for n, mn, mx in ((1000, 150, 150), (1000, 75, 300), (20, 5, 12), (1, 3, 3), (12345, 1, 500)):
+        assert L.bsq_synth_size(n, mn, mx) == oracle.synth_size(n, mn, mx)
+    assert L.bsq_synth_size(33659618, 150, 150) == 10737418142
+
+
+def test_host_batch_container(B):
+    """tests/fastq/test_record_batch.mojo:26-134 on the host-side FastqBatch."""
+    batch = B.FastqBatch()
+    batch.add(B.FastqRecord("a", "AC", "!!"))
+    batch.add(B.FastqRecord("b", "GT", "!!"))
+    assert batch.num_records() == 2 and batch.seq_len() == 4
+    assert batch._ends.tolist() == [2, 4] and len(batch._quality_bytes) == 4 and len(batch._sequence_bytes) == 4
+    recs = [B.FastqRecord("@a", "ACGT", "!!!!"), B.FastqRecord("@b", "TGCA", "!!!!"), B.FastqRecord("@c", "N", "!")]
+    batch = B.FastqBatch()
+    for r in recs:
+        batch.add(r)
+    assert batch.to_records() == recs and batch.get_record(2) == recs[2]
+    assert batch.get_ref(1).sequence() == b"TGCA"
+    with pytest.raises(B.BlazeSeqError):
+        batch.get_record(3)
+    assert recs[0].phred_scores == [0, 0, 0, 0] and len(recs[0]) == 4
+
+
+def test_readers(B, tmp_path, golden_dir):
+    data = b"@r1\nACGT\n+\n!!!!\n"
+    r = B.MemoryReader(data)
+    buf = np.zeros(10, np.uint8)
+    assert r.read_to_buffer(buf, 10, 0) == 10 and bytes(buf) == data[:10]
+    assert r.read_to_buffer(buf, 10, 0) == 6 and r.read_to_buffer(buf, 10, 0) == 0
+    with pytest.raises(B.BlazeSeqError):
+        r.read_to_buffer(buf, 11, 0)
+    with pytest.raises(B.BlazeSeqError):
+        r.read_to_buffer(buf, 1, 11)
+    f = tmp_path / "x.fastq"
+    f.write_bytes(data)
+    fr = B.FileReader(f)
+    big = np.zeros(64, np.uint8)
+    assert fr.read_to_buffer(big, 64, 0) == len(data) and fr.read_to_buffer(big, 64, 0) == 0
+    gz = B.RapidgzipReader(os.path.join(golden_dir, "corpus", "example.fastq.gz"))
+    plain = open(os.path.join(golden_dir, "corpus", "example.fastq"), "rb").read()
+    out = np.zeros(1024, np.uint8)
+    n = gz.read_to_buffer(out, 1024, 0)
+    assert bytes(out[:n]) == plain and gz.read_to_buffer(out, 1024, 0) == 0
+
+
+# ------------------------------------------------------------------ shard stitching
+
+
+def _tm():
+    import oracle_py
+    oracle_py.build()
+    L = C.CDLL(os.path.join(ROOT, "oracle", "libbsq_tile_model.so"))
+    L.tm_summarize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    return L
+
+
+def _cpu_summary(B, tm, arr, lo, hi):
+    s = B._capi.Summary()
+    tm.tm_summarize(arr.ctypes.data, lo, hi, C.byref(s))
+    return s
+
+
+def test_shard_prefix_against_oracle(B, oracle):
+    tm = _tm()
+    rng = np.random.default_rng(0)
+    streams = [oracle.synth(300, 5, 60, 2, 40, "sanger"), np.frombuffer(b"@a\nAC\n+\n!!\n" * 40, np.uint8),
+               np.frombuffer(b"@a b\r\nAC\r\n+\r\n!!\r\n" * 30, np.uint8)]
+    for data in streams:
+        views, _, _ = oracle.parse_all(data)
+        starts = views["header_start"]
+        for _ in range(50):
+            k = int(rng.integers(2, 9))
+            cuts = np.sort(rng.integers(0, data.size + 1, k - 1))
+            bounds = [0] + cuts.tolist() + [data.size]
+            sums = [_cpu_summary(B, tm, data, bounds[i], bounds[i + 1]) for i in range(k)]
+            st = B.shard_prefix(sums, [bounds[i + 1] - bounds[i] for i in range(k)])
+            for i in range(k):
+                first_own = int(np.searchsorted(starts, bounds[i]))
+                assert st[i].first_record == first_own
+                assert st[i].newline_rank == int((data[:bounds[i]] == 10).sum())
+                owns = first_own < len(starts) and starts[first_own] < bounds[i + 1]
+                if owns:
+                    assert bounds[i] + st[i].skip_bytes == starts[first_own]
+                else:
+                    assert st[i].skip_bytes == bounds[i + 1] - bounds[i] or first_own == len(starts)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, data_bytes, cuts, out_q):
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch.distributed as dist
+    import blazeseq_b200 as B
+    from blazeseq_b200 import sharding
+    import oracle_py as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    data = np.frombuffer(data_bytes, np.uint8)
+    bounds = [0] + list(cuts) + [data.size]
+    lo, hi = bounds[rank], bounds[rank + 1]
+    tm = _tm()
+    # stand-in for bsq_summarize_device: the same BsqSummary, computed by the CPU tile model
+    local = _cpu_summary(B, tm, data, lo, hi)
+    plan = sharding.plan(dist, local, hi - lo)
+    # stand-in for bsq_parse_device on the rank's own region (own shard + halo)
+    region = data[lo + plan.begin: lo + plan.end]
+    views, bases, err = O.parse_all(region, O.config(buffer_growth_enabled=True))
+    reads, total_bases = sharding.allreduce_counts(dist, len(views), bases)
+    out_q.put((rank, plan.first_record, len(views), reads, total_bases, err.code))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_parse_over_gloo(oracle, world):
+    """world_size-2/3 on CPU: summaries all-gathered over gloo, each rank parses only the records
+    that start in its shard, totals all-reduced.  The device steps are replaced by CPU stand-ins;
+    the stitching (blazeseq_b200/sharding.py + bsq_shard_prefix) is the code under test."""
+    import torch.multiprocessing as mp
+    data = oracle.synth(5000, 20, 120, 2, 40, "illumina_1.8")
+    views, bases, err = oracle.parse_all(data)
+    rng = np.random.default_rng(world)
+    cuts = sorted(int(x) for x in rng.integers(1, data.size - 1, world - 1))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, data.tobytes(), cuts, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sum(r[2] for r in results) == len(views)
+    first = 0
+    for rank, first_record, n, reads, total_bases, code in results:
+        assert first_record == first and code == oracle.EOF
+        assert (reads, total_bases) == (len(views), bases)
+        first += n
