@@ -66,7 +66,7 @@ class OffsetsView(C.Structure):
 class BatchView(C.Structure):
     _fields_ = [
         ("num_records", C.c_int64), ("seq_len", C.c_int64), ("total_id_bytes", C.c_int64),
-        ("quality_offset", C.c_uint8), ("_pad", C.c_uint8 * 7),
+        ("quality_offset", C.c_uint8), ("_pad", C.c_uint8 * 7), ("sequence_bytes", C.c_int64),
         ("sequence_buffer", C.c_void_p), ("qual_buffer", C.c_void_p), ("id_buffer", C.c_void_p),
         ("ends", C.c_void_p), ("id_ends", C.c_void_p),
     ]

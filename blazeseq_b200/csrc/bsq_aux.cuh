@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256, 1) k_tail(const TailParams T, const Resol
             const int64_t gk = P.rec_base + (int64_t)T.k;
             const int64_t endv = P.qual_base64 + (int64_t)T.qual_rel + (int64_t)qual_len;
             P.ends_abs[gk] = endv;
-            if ((gk + 1) % P.batch_size == 0) P.ends_base[(gk + 1) / P.batch_size] = endv;
+            if ((gk + 1) % P.batch_size == 0) P.ends_base[(gk + 1) / P.batch_size] = endv;   // cold: one thread
             if (T.id_fast) {
                 const int64_t iend = P.id_base64 + (int64_t)T.id_rel + (int64_t)id_len;
                 P.id_ends_abs[gk] = iend;

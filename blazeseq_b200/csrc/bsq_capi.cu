@@ -56,7 +56,7 @@ struct Window {
 
 struct HostMirror {                  // pinned
     ScanOut scan;
-    unsigned long long err;
+    unsigned long long err[4];       // [0] min error key, [1] "some id needed stripping", [2] bases
     TailOut tail;
 };
 
@@ -68,7 +68,7 @@ struct bsq_parser {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[6]{};             // timing marks
     cudaEvent_t ev_copy[2]{};
-    DevBuf run_sum, scan_out, err_word, tail_out, cub_tmp, len_prefix;
+    DevBuf run_sum, scan_out, err_word, tail_out, cub_tmp, len_prefix;   // err_word: [0] error key, [1] strip flag
     DevBuf seq_out, qual_out, id_out, ends, id_ends, ends_base, id_ends_base, id_spans;
     DevBuf host_input;               // device copy of a host pass
     void* pinned_stage[2] = {nullptr, nullptr};
@@ -84,6 +84,8 @@ struct bsq_parser {
     int64_t pass_stream_offset = 0;
     int64_t total_records = 0;       // arena records (complete + tail)
     int64_t total_seq = 0, total_qual = 0, total_id = 0;
+    bool tail_emitted = false;       // the arena's last record is a newline-less tail
+    int64_t tail_seq = 0, tail_qual = 0;
     float ms[5] = {0, 0, 0, 0, 0};
     int64_t n_launches = 0;
     std::string last_error;
@@ -136,11 +138,13 @@ void set_plain_error(bsq_error* e, int code, const char* text) {
     m.str(text);
 }
 
-size_t smem_bytes() { return sizeof(TileSmem) + 128; }
+size_t smem_bytes() { return sizeof(TileSmem) + 128; }                      // k_resolve: 2 CTAs / SM
+size_t smem_bytes_summarize() { return offsetof(TileSmem, bm_hi) + 128; }   // k_summarize: 3 CTAs / SM
+size_t smem_bytes_scan(uint32_t n_runs) { return (size_t)n_runs * (sizeof(BsqSummary) + sizeof(BsqPrefix)); }
 
 template <typename K>
-cudaError_t opt_in_smem(K kernel) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes());
+cudaError_t opt_in_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 void plan_window(bsq_parser* p, Window& w, const uint8_t* first_byte, uint64_t bytes) {
@@ -154,7 +158,8 @@ void plan_window(bsq_parser* p, Window& w, const uint8_t* first_byte, uint64_t b
     w.wp.n_tiles = (w.wp.end + kTile - 1) / kTile;
     uint32_t tiles = w.wp.n_tiles - w.wp.first_tile;
     if (tiles == 0) tiles = 1, w.wp.n_tiles = w.wp.first_tile + 1;
-    uint32_t max_runs = (uint32_t)std::min<int>(2 * p->sm_count, kMaxRuns);
+    // runs per window: a whole number of waves for both kernels (2 and 3 resident CTAs per SM)
+    uint32_t max_runs = (uint32_t)std::min<int>(6 * p->sm_count, kMaxRuns);
     uint32_t runs = std::min(tiles, max_runs);
     w.wp.tiles_per_run = (tiles + runs - 1) / runs;
     w.wp.n_runs = (tiles + w.wp.tiles_per_run - 1) / w.wp.tiles_per_run;
@@ -178,18 +183,21 @@ ResolveKernel pick_resolve(bool ascii, bool qual, bool offs, bool pack) {
 }
 
 bsq_status setup_kernels(bsq_parser* p) {
-    CK(opt_in_smem(k_summarize));
-    for (int i = 0; i < 16; ++i) CK(opt_in_smem(pick_resolve(i & 8, i & 4, i & 2, i & 1)));
+    CK(opt_in_smem(k_summarize<true>, smem_bytes_summarize()));
+    CK(opt_in_smem(k_summarize<false>, smem_bytes_summarize()));
+    CK(opt_in_smem(k_scan_runs, smem_bytes_scan(kMaxRuns)));
+    for (int i = 0; i < 16; ++i) CK(opt_in_smem(pick_resolve(i & 8, i & 4, i & 2, i & 1), smem_bytes()));
     return BSQ_OK;
 }
 
 // Summarise + scan one window; leaves the ScanOut in w.scan (host) after a stream sync.
-bsq_status summarize_window(bsq_parser* p, Window& w) {
+bsq_status summarize_window(bsq_parser* p, Window& w, bool sums) {
     CK(p->run_sum.ensure(sizeof(BsqSummary) * kMaxRuns));
     CK(w.run_pre.ensure(sizeof(BsqPrefix) * kMaxRuns));
     CK(p->scan_out.ensure(sizeof(ScanOut)));
-    k_summarize<<<w.wp.n_runs, kThreads, smem_bytes(), p->stream>>>(w.wp, p->run_sum.as<BsqSummary>());
-    k_scan_runs<<<1, 256, 0, p->stream>>>(p->run_sum.as<BsqSummary>(), w.wp.n_runs, w.wp.begin,
+    if (sums) k_summarize<true><<<w.wp.n_runs, kThreads, smem_bytes_summarize(), p->stream>>>(w.wp, p->run_sum.as<BsqSummary>());
+    else k_summarize<false><<<w.wp.n_runs, kThreads, smem_bytes_summarize(), p->stream>>>(w.wp, p->run_sum.as<BsqSummary>());
+    k_scan_runs<<<1, 256, smem_bytes_scan(w.wp.n_runs), p->stream>>>(p->run_sum.as<BsqSummary>(), w.wp.n_runs, w.wp.begin,
                                           w.run_pre.as<BsqPrefix>(), p->scan_out.as<ScanOut>());
     p->n_launches += 2;
     CK(cudaGetLastError());
@@ -349,7 +357,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         if (st != BSQ_OK) return st;
         plan_window(p, w, d + pos, bytes);
         w.region_off = pos;
-        st = summarize_window(p, w);
+        st = summarize_window(p, w, want_pack);
         if (st != BSQ_OK) return st;
         ++nw;
         const uint64_t consumed = w.scan.totals.consumed_end - w.wp.begin;
@@ -373,7 +381,6 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         nrec += w.scan.totals.records; nseq += w.scan.totals.seq_bytes; nqual += w.scan.totals.qual_bytes;
         nid += w.scan.totals.id_bytes_unstripped;
         nnl += (i + 1 < nw) ? 4ll * w.scan.totals.records : w.scan.totals.newlines;
-        if (w.scan.totals.flags & BSQ_SUM_ID_MAY_STRIP) any_strip = true;
     }
     uint64_t consumed_total = 0;
     uint32_t rem = 0;
@@ -413,8 +420,9 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     const int64_t arena_rec = nrec + (have_tail_candidate ? 1 : 0);
     const int32_t m = cfg.batch_size;
     const int64_t nb_cap = arena_rec / m + 2;
-    CK(p->err_word.ensure(8));
+    CK(p->err_word.ensure(32));
     CK(cudaMemsetAsync(p->err_word.p, 0xFF, 8, p->stream));
+    CK(cudaMemsetAsync(p->err_word.as<uint8_t>() + 8, 0, 24, p->stream));
     if (want_offs || want_pack) CK(p->id_spans.ensure(8ull * (arena_rec + 1), 1 << 20));
     if (want_pack) {
         CK(p->seq_out.ensure((size_t)nseq + tail_seq + 64, 1 << 20));
@@ -427,7 +435,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         CK(cudaMemsetAsync(p->ends_base.p, 0, 8ull * nb_cap, p->stream));
         CK(cudaMemsetAsync(p->id_ends_base.p, 0, 8ull * nb_cap, p->stream));
     }
-    const bool id_fast = !any_strip;
+    bool id_fast = !any_strip;   // optimistic: k_resolve raises the strip flag when an id needs stripping
 
     // ---- pass 2: resolve / validate / pack ------------------------------------------------------
     auto make_params = [&](Window& w) {
@@ -435,6 +443,10 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         P.run_pre = w.run_pre.as<BsqPrefix>();
         P.n_complete = w.scan.totals.records;
         P.id_fast = id_fast ? 1u : 0u;
+        P.strip_flag = reinterpret_cast<uint32_t*>(p->err_word.as<uint8_t>() + 8);
+        P.bases = p->err_word.as<unsigned long long>() + 2;
+        P.rec_mod = (uint32_t)(w.rec_base % m);
+        P.rec_div = w.rec_base / m;
         P.rec_base = w.rec_base;
         P.first_record = first_record;
         P.line_ends = w.line_ends.as<uint32_t>();
@@ -459,6 +471,23 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->ev[2], p->stream));
+    if (want_pack && id_fast) {
+        // did the optimistic id packing hold?  (CRLF input and padded ids need _strip_spaces)
+        CK(cudaMemcpyAsync(p->hm->err, p->err_word.p, 32, cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        if (p->hm->err[1] != 0) {
+            id_fast = false;   // redo with the id spans materialised; the strip pipeline packs the ids
+            CK(cudaMemsetAsync(p->err_word.p, 0xFF, 8, p->stream));
+            CK(cudaMemsetAsync(p->err_word.as<uint8_t>() + 16, 0, 8, p->stream));
+            for (size_t i = 0; i < nw; ++i) {
+                Window& w = p->win[i];
+                ResolveParams P = make_params(w);
+                kern<<<w.wp.n_runs, kThreads, smem_bytes(), p->stream>>>(w.wp, P);
+                p->n_launches += 1;
+            }
+            CK(cudaGetLastError());
+        }
+    }
 
     if (have_tail_candidate) {
         ResolveParams P = make_params(*lw);
@@ -472,7 +501,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(&p->hm->tail, p->tail_out.p, sizeof(TailOut), cudaMemcpyDeviceToHost, p->stream));
     }
-    CK(cudaMemcpyAsync(&p->hm->err, p->err_word.p, 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(p->hm->err, p->err_word.p, 32, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
 
     // ---- how far did the pass get? ------------------------------------------------------------
@@ -481,7 +510,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     int64_t good = nrec;             // records before the stop
     bool tail_emitted = false;
     if (have_tail_candidate && p->hm->tail.status == 0) tail_emitted = true;
-    const unsigned long long key = p->hm->err;
+    const unsigned long long key = p->hm->err[0];
     const bool have_err = key != ~0ull;
     int64_t err_rec = -1; int err_code = 0;
     if (have_err) { err_rec = (int64_t)(key >> 8) - first_record; err_code = (int)(key & 0xFF); }
@@ -530,7 +559,8 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     CK(cudaEventRecord(p->ev[3], p->stream));
     CK(cudaStreamSynchronize(p->stream));
     p->total_records = arena_final;
-    p->total_seq = nseq + (tail_emitted ? tail_seq : 0);
+    p->tail_emitted = tail_emitted; p->tail_seq = tail_seq; p->tail_qual = tail_qual;
+    p->total_seq = (int64_t)p->hm->err[2] + (tail_emitted ? tail_seq : 0);   // counted by k_resolve
     p->total_qual = nqual + (tail_emitted ? tail_qual : 0);
 
     // ---- the stop reason, with the reference's context and text -------------------------------
@@ -773,6 +803,8 @@ static bsq_status fill_batch(const bsq_parser* p, int64_t first, int64_t count, 
         q_end = qb + v[0]; i_end = ib + v[1];
     }
     out->seq_len = q_end - qb;
+    out->sequence_bytes = out->seq_len;
+    if (p->tail_emitted && last == p->total_records) out->sequence_bytes += p->tail_seq - p->tail_qual;
     out->total_id_bytes = i_end - ib;
     return BSQ_OK;
 }
@@ -804,6 +836,7 @@ extern "C" bsq_status bsq_get_soa(const bsq_parser* p, bsq_batch_view* out) {
     bsq_status st = bsq_get_batch(p, lb, &last);
     if (st != BSQ_OK) return st;
     out->seq_len = p->h_ends_base[lb] + last.seq_len;
+    out->sequence_bytes = p->h_ends_base[lb] + last.sequence_bytes;
     out->total_id_bytes = p->h_id_ends_base[lb] + last.total_id_bytes;
     return BSQ_OK;
 }
@@ -815,7 +848,7 @@ extern "C" bsq_status bsq_batch_to_host(bsq_parser* p, int64_t b, uint8_t* seq, 
     if (st != BSQ_OK) return st;
     if (v.num_records == 0) return BSQ_OK;
     CK(cudaSetDevice(p->cfg.device_id));
-    if (seq) CK(cudaMemcpyAsync(seq, v.sequence_buffer, v.seq_len, cudaMemcpyDeviceToHost, p->stream));
+    if (seq) CK(cudaMemcpyAsync(seq, v.sequence_buffer, v.sequence_bytes, cudaMemcpyDeviceToHost, p->stream));
     if (qual) CK(cudaMemcpyAsync(qual, v.qual_buffer, v.seq_len, cudaMemcpyDeviceToHost, p->stream));
     if (id) CK(cudaMemcpyAsync(id, v.id_buffer, v.total_id_bytes, cudaMemcpyDeviceToHost, p->stream));
     if (ends) CK(cudaMemcpyAsync(ends, v.ends, 8 * v.num_records, cudaMemcpyDeviceToHost, p->stream));
@@ -933,12 +966,12 @@ extern "C" bsq_status bsq_summarize_device(bsq_parser* p, const uint8_t* dev_byt
     while (pos < n) {
         const uint64_t bytes = std::min<uint64_t>(n - pos, kWindowMax);
         plan_window(p, w, dev_bytes + pos, bytes);
-        bsq_status st = summarize_window(p, w);
+        bsq_status st = summarize_window(p, w, true);
         if (st != BSQ_OK) { w.run_pre.release(); return st; }
         BsqSummary s = w.scan.region;
         // rebase window-relative positions to shard-relative (mod 2^32, like all rank algebra)
         const uint32_t shift = (uint32_t)(pos - w.wp.begin);
-        for (int i = 0; i < 4; ++i) s.last[i] += shift;
+        for (int i = 0; i < 4; ++i) { s.last[i] += shift; s.first[i] += shift; }
         for (uint32_t k = 0; k < 4; ++k) {
             const uint32_t cnt_k = (s.count + 3u - k) >> 2;  // newlines with index == k (mod 4)
             s.P[k] += shift * cnt_k;

@@ -57,7 +57,12 @@ struct ScanOut {             // written by k_scan_runs, read by the host
 struct ResolveParams {
     const BsqPrefix* run_pre;
     uint32_t n_complete;         // complete records of this window
-    uint32_t id_fast;            // 1: no id needs stripping in this window -> ids packed here
+    uint32_t id_fast;            // 1: ids are packed here on the assumption that none needs stripping;
+                                 //    *strip_flag is raised if one does and the host redoes the ids
+    uint32_t* strip_flag;
+    unsigned long long* bases;   // sum of the sequence lengths of the complete records (all windows)
+    uint32_t rec_mod;            // rec_base % batch_size
+    int64_t rec_div;             // rec_base / batch_size
     int64_t rec_base;            // arena index of the window's first record
     int64_t first_record;        // global index of the pass's first record (error context)
     // views()
@@ -123,17 +128,21 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
 // ------------------------------------------------------------------------------------------------
 
 struct alignas(128) TileSmem {
+    // ---- used by both kernels (k_summarize allocates only up to bm_hi) ----
     uint8_t data[kStages][kTile + kTilePad];  // TMA destinations
+    uint64_t full_bar[kStages];
+    uint32_t warp_tot[2][kWarps][4];          // block scans, double buffered: one barrier per scan
+    uint32_t carry[8];
+    uint32_t k1_head[8];                      // k_summarize: [0..3] last four newlines, [4..7] first four
+    uint32_t k1_red[kWarps * 4];
     uint32_t bm_nl[kWords];                   // 1 bit per byte: '\n'
+    // ---- k_resolve only ----
     uint32_t bm_hi[kWords];                   // 1 bit per byte: bit 7 set
     uint32_t bm_bad[kWords];                  // 1 bit per byte: outside [lower, upper]
     uint32_t nlx[kHead + kNlCap];             // nlx[kHead + j] = position of local newline j;
                                               // nlx[kHead-1-i] = i-th newline before the list
     uint32_t sdst[3][kLinesCap];              // per class stream: destination of each line
     uint32_t ssrc[3][kLinesCap];              //                   source position of each line
-    uint32_t warp_tot[kWarps][4];
-    uint32_t carry[4];
-    uint64_t full_bar[kStages];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -211,8 +220,9 @@ __device__ __forceinline__ void build_bitmaps(TileSmem& S, const TileCursor& c, 
     }
 }
 
-// Exclusive prefix of `v` over the block (in thread order) and the block total.  Two barriers.
-__device__ __forceinline__ uint32_t block_exclusive_scan(TileSmem& S, uint32_t v, uint32_t& total) {
+// Exclusive prefix of `v` over the block (in thread order) and the block total.  One barrier:
+// the warp totals are double buffered (`par` alternates between consecutive scans of a CTA).
+__device__ __forceinline__ uint32_t block_exclusive_scan(TileSmem& S, uint32_t v, uint32_t& total, uint32_t& par) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t inc = v;
 #pragma unroll
@@ -220,16 +230,16 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(TileSmem& S, uint32_t v
         const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
         if (lane >= (uint32_t)d) inc += t;
     }
-    if (lane == 31u) S.warp_tot[warp][0] = inc;
+    par ^= 1u;
+    if (lane == 31u) S.warp_tot[par][warp][0] = inc;
     __syncthreads();
     uint32_t before = 0, tot = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
-        const uint32_t t = S.warp_tot[w][0];
+        const uint32_t t = S.warp_tot[par][w][0];
         if ((uint32_t)w < warp) before += t;
         tot += t;
     }
-    __syncthreads();  // warp_tot is reused by the next scan
     total = tot;
     return before + inc - v;
 }
@@ -237,7 +247,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(TileSmem& S, uint32_t v
 // Same for three values at once (the id / seq / qual streams).
 __device__ __forceinline__ void block_exclusive_scan3(TileSmem& S, uint32_t v0, uint32_t v1, uint32_t v2,
                                                       uint32_t& e0, uint32_t& e1, uint32_t& e2,
-                                                      uint32_t& t0, uint32_t& t1, uint32_t& t2) {
+                                                      uint32_t& t0, uint32_t& t1, uint32_t& t2, uint32_t& par) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t i0 = v0, i1 = v1, i2 = v2;
 #pragma unroll
@@ -247,38 +257,59 @@ __device__ __forceinline__ void block_exclusive_scan3(TileSmem& S, uint32_t v0, 
         const uint32_t c = __shfl_up_sync(0xFFFFFFFFu, i2, d);
         if (lane >= (uint32_t)d) { i0 += a; i1 += b; i2 += c; }
     }
-    if (lane == 31u) { S.warp_tot[warp][0] = i0; S.warp_tot[warp][1] = i1; S.warp_tot[warp][2] = i2; }
+    par ^= 1u;
+    if (lane == 31u) { S.warp_tot[par][warp][0] = i0; S.warp_tot[par][warp][1] = i1; S.warp_tot[par][warp][2] = i2; }
     __syncthreads();
     uint32_t b0 = 0, b1 = 0, b2 = 0, s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
-        const uint32_t x0 = S.warp_tot[w][0], x1 = S.warp_tot[w][1], x2 = S.warp_tot[w][2];
+        const uint32_t x0 = S.warp_tot[par][w][0], x1 = S.warp_tot[par][w][1], x2 = S.warp_tot[par][w][2];
         if ((uint32_t)w < warp) { b0 += x0; b1 += x1; b2 += x2; }
         s0 += x0; s1 += x1; s2 += x2;
     }
-    __syncthreads();
     e0 = b0 + i0 - v0; e1 = b1 + i1 - v1; e2 = b2 + i2 - v2;
     t0 = s0; t1 = s1; t2 = s2;
 }
 
-// Writes the positions of the local newlines with rank in [pass_base, pass_base + kNlCap) to
-// nlx[kHead + rank - pass_base].  `excl` = rank of the first newline of this thread's 128 bytes.
-__device__ __forceinline__ void fill_newline_list(TileSmem& S, const TileCursor& c, const uint4& words,
-                                                  uint32_t excl, uint32_t pass_base) {
-    const uint32_t base_pos = c.origin + threadIdx.x * 128u;
+// Visits the newlines of this thread's 128 bytes in order: f(rank, position).  Most 32-byte words
+// hold none, one or two newlines ("\n+\n"): the first and the last set bit are found without a
+// loop; only words with three or more take the loop.
+template <typename F>
+__device__ __forceinline__ void for_each_newline(const uint4& words, uint32_t pos0, uint32_t excl, F&& f) {
     uint32_t r = excl;
     const uint32_t w[4] = {words.x, words.y, words.z, words.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         uint32_t m = w[i];
-        while (m) {
-            const uint32_t b = __ffs(m) - 1u;
-            m &= m - 1u;
-            const uint32_t rel = r - pass_base;
-            if (rel < (uint32_t)kNlCap) S.nlx[kHead + rel] = base_pos + 32u * i + b;
-            ++r;
+        if (m) {
+            const uint32_t lsb = m & (0u - m);
+            f(r++, pos0 + (31u - __clz(lsb)));
+            m ^= lsb;
+            if (m) {
+                const uint32_t top = 31u - __clz(m);
+                m ^= 1u << top;
+                while (m) {                       // rare: >= 3 newlines within 32 bytes
+                    const uint32_t l2 = m & (0u - m);
+                    f(r++, pos0 + (31u - __clz(l2)));
+                    m ^= l2;
+                }
+                f(r++, pos0 + top);
+            }
         }
+        pos0 += 32u;
     }
+}
+
+// Writes the positions of the local newlines with rank in [pass_base, pass_base + kNlCap) to
+// nlx[kHead + rank - pass_base].  `excl` = rank of the first newline of this thread's 128 bytes.
+// kChecked = false when the whole tile fits one pass (the common case): no bound check per entry.
+template <bool kChecked>
+__device__ __forceinline__ void fill_newline_list(TileSmem& S, const TileCursor& c, const uint4& words,
+                                                  uint32_t excl, uint32_t pass_base) {
+    uint32_t* const list = &S.nlx[kHead];
+    for_each_newline(words, c.origin + threadIdx.x * 128u, excl - pass_base, [&](uint32_t rel, uint32_t p) {
+        if (!kChecked || rel < (uint32_t)kNlCap) list[rel] = p;
+    });
 }
 
 // After a pass of n entries: the kHead most recent newline positions move to the front.
@@ -323,7 +354,11 @@ __device__ __forceinline__ TileCursor make_cursor(const WinParams& W, uint32_t t
     return c;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) k_summarize(const WinParams W, BsqSummary* __restrict__ run_sum) {
+// kSums = false (views-only passes): only the newline count and the first/last positions of the
+// run are needed; the per-class position sums that give the SoA destinations are skipped.
+// Shared memory: the part of TileSmem before bm_hi (three CTAs per SM).
+template <bool kSums>
+__global__ void __launch_bounds__(kThreads, 3) k_summarize(const WinParams W, BsqSummary* __restrict__ run_sum) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x;
@@ -334,14 +369,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_summarize(const WinParams W, Bs
         for (int s = 0; s < kStages; ++s) mbar_init(&S.full_bar[s], 1);
         mbar_fence_init();
     }
-    if (tid < kHead) S.nlx[tid] = 0;
+    if (tid < 8) S.k1_head[tid] = 0;
     __syncthreads();
     if (tid == 0)
         for (uint32_t s = 0; s < (uint32_t)kStages && ta + s < tb; ++s) issue_tile_load(S, W, ta + s, s);
 
     uint32_t run_count = 0;           // newlines of the run so far (uniform)
     uint32_t acc[4] = {0, 0, 0, 0};   // position sums by (index in run) mod 4, this thread's share
-    uint32_t flag = 0;
+    uint32_t par = 0;
 
     for (uint32_t t = ta; t < tb; ++t) {
         const uint32_t it = t - ta;
@@ -352,61 +387,54 @@ __global__ void __launch_bounds__(kThreads, 2) k_summarize(const WinParams W, Bs
         const uint4 words = *reinterpret_cast<const uint4*>(&S.bm_nl[tid * 4]);
         const uint32_t cnt = __popc(words.x) + __popc(words.y) + __popc(words.z) + __popc(words.w);
         uint32_t total;
-        const uint32_t excl = block_exclusive_scan(S, cnt, total);
-        uint32_t sum = 0;
-        for (uint32_t pass = 0; pass < total; pass += kNlCap) {
-            const uint32_t n = total - pass < (uint32_t)kNlCap ? total - pass : (uint32_t)kNlCap;
-            fill_newline_list(S, c, words, excl, pass);
-            __syncthreads();
-            for (uint32_t j = tid; j < n; j += kThreads) {
-                const uint32_t p = S.nlx[kHead + j];
-                sum += p;
-                if (run_count + pass + j < 4u) S.carry[run_count + pass + j] = p;  // first[] of the run
-                // may some header need _strip_spaces?  (conservative: every line is looked at)
-                if (p > W.begin && bsq_is_space(byte_at(S, c, W, p - 1u))) flag = BSQ_SUM_ID_MAY_STRIP;
-                if (p + 2u < W.end && byte_at(S, c, W, p + 1u) == '@' && bsq_is_space(byte_at(S, c, W, p + 2u)))
-                    flag = BSQ_SUM_ID_MAY_STRIP;
-            }
-            __syncthreads();
-            rotate_head(S, n);
-            __syncthreads();
+        const uint32_t excl = block_exclusive_scan(S, cnt, total, par);
+        // this thread's newlines: index in the run = run_count + excl + k
+        const bool edge = run_count + excl < 4u || excl + cnt + 4u > total;   // among the first / last four
+        if (cnt != 0u && (kSums || edge)) {
+            for_each_newline(words, c.origin + tid * 128u, excl, [&](uint32_t r, uint32_t p) {
+                if (kSums) {
+                    const uint32_t cls = (run_count + r) & 3u;
+                    acc[0] += cls == 0u ? p : 0u;
+                    acc[1] += cls == 1u ? p : 0u;
+                    acc[2] += cls == 2u ? p : 0u;
+                    acc[3] += cls == 3u ? p : 0u;
+                }
+                if (edge) {
+                    if (run_count + r < 4u) S.k1_head[4u + run_count + r] = p;     // first[] of the run
+                    if (r + 4u >= total) S.carry[r + 4u - total] = p;             // last four of the tile
+                }
+            });
         }
-        // kNlCap and kThreads are multiples of 4: every newline this thread summed has the same class
-        const uint32_t cls = (run_count + tid) & 3u;
-        acc[0] += cls == 0u ? sum : 0u;
-        acc[1] += cls == 1u ? sum : 0u;
-        acc[2] += cls == 2u ? sum : 0u;
-        acc[3] += cls == 3u ? sum : 0u;
+        __syncthreads();
+        if (tid == 0 && total != 0u) {
+            // merge the tile's last (up to four) newlines into the run's last four (oldest first)
+            const uint32_t k = total < 4u ? total : 4u;
+            uint32_t h[4];
+            for (uint32_t i = 0; i < 4u; ++i) h[i] = i + k < 4u ? S.k1_head[i + k] : S.carry[i];
+            for (uint32_t i = 0; i < 4u; ++i) S.k1_head[i] = h[i];
+        }
         run_count += total;
-        __syncthreads();  // every thread is done with data[stage]
+        __syncthreads();  // every thread is done with data[stage] and the head is updated
         if (tid == 0 && t + kStages < tb) issue_tile_load(S, W, t + kStages, c.stage);
     }
-    if (blockIdx.x == 0 && tid == 0 && W.begin + 1u < W.end && __ldg(W.base + W.begin) == '@' &&
-        bsq_is_space(__ldg(W.base + W.begin + 1u)))
-        flag = BSQ_SUM_ID_MAY_STRIP;
 
-    // block reduction of acc[4] and flag
+    // block reduction of acc[4]
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[k] += __shfl_xor_sync(0xFFFFFFFFu, acc[k], d);
-        flag |= __shfl_xor_sync(0xFFFFFFFFu, flag, d);
     }
     __syncthreads();
-    if ((tid & 31u) == 0u) {
-        for (int k = 0; k < 4; ++k) S.sdst[0][(tid >> 5) * 4 + k] = acc[k];
-        S.sdst[1][tid >> 5] = flag;
-    }
+    if ((tid & 31u) == 0u)
+        for (int k = 0; k < 4; ++k) S.k1_red[(tid >> 5) * 4 + k] = acc[k];
     __syncthreads();
     if (tid == 0) {
         BsqSummary s = bsq_summary_identity();
         s.count = run_count;
-        for (int w = 0; w < kWarps; ++w) {
-            for (int k = 0; k < 4; ++k) s.P[k] += S.sdst[0][w * 4 + k];
-            s.flags |= S.sdst[1][w];
-        }
-        for (int i = 0; i < 4; ++i) s.last[i] = S.nlx[kHead - 1 - i];
-        for (uint32_t i = 0; i < 4u; ++i) s.first[i] = i < run_count ? S.carry[i] : 0u;
+        for (int w = 0; w < kWarps; ++w)
+            for (int k = 0; k < 4; ++k) s.P[k] += S.k1_red[w * 4 + k];
+        for (int i = 0; i < 4; ++i) s.last[i] = S.k1_head[3 - i];
+        for (uint32_t i = 0; i < 4u; ++i) s.first[i] = i < run_count ? S.k1_head[4u + i] : 0u;
         run_sum[blockIdx.x] = s;
     }
 }
@@ -415,13 +443,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_summarize(const WinParams W, Bs
 // k_scan_runs: one CTA; n_runs is a few hundred
 // ------------------------------------------------------------------------------------------------
 
-constexpr int kMaxRuns = 384;
+constexpr int kMaxRuns = 1024;
 
+// dynamic shared memory: n_runs * (sizeof(BsqSummary) + sizeof(BsqPrefix))
 __global__ void __launch_bounds__(256, 1) k_scan_runs(const BsqSummary* __restrict__ run_sum, uint32_t n_runs,
                                                       uint32_t begin, BsqPrefix* __restrict__ run_pre,
                                                       ScanOut* __restrict__ out) {
-    __shared__ BsqSummary s_sum[kMaxRuns];
-    __shared__ BsqPrefix s_pre[kMaxRuns];
+    extern __shared__ __align__(128) uint8_t scan_raw[];
+    BsqSummary* s_sum = reinterpret_cast<BsqSummary*>(scan_raw);
+    BsqPrefix* s_pre = reinterpret_cast<BsqPrefix*>(scan_raw + (size_t)n_runs * sizeof(BsqSummary));
     // stage the summaries with all threads (16-byte pieces), scan with one, write back with all
     {
         const uint4* src = reinterpret_cast<const uint4*>(run_sum);
@@ -458,71 +488,119 @@ __device__ __forceinline__ void report(const ResolveParams& P, uint32_t k, uint3
     atomicMin(P.err, key);
 }
 
-// 16 source bytes starting at window offset pos (any alignment).  Lines end inside the current
-// tile, so pos + 16 never runs past the tile padding.
+// 16 source bytes starting at window offset pos (any alignment; pos may wrap below 0 when a line
+// begins inside the destination vector -- those leading bytes are never used).  The current tile is
+// read from shared memory (two aligned 16-byte loads + funnel shifts); bytes of a line that began
+// in an earlier tile come from global memory (L2), word by word, guarded to the window.
 __device__ __forceinline__ uint4 load16(const TileSmem& S, const TileCursor& c, const WinParams& W, uint32_t pos) {
     const uint32_t rel = pos - c.origin;
-    uint4 r;
+    const uint32_t sh = (pos & 3u) * 8u;
+    uint32_t w0, w1, w2, w3, w4;
     if (rel < (uint32_t)kTile) {
         const uint8_t* t = S.data[c.stage];
         const uint32_t a = rel & ~15u;
         const uint4 lo = *reinterpret_cast<const uint4*>(t + a);
         const uint4 hi = *reinterpret_cast<const uint4*>(t + a + 16u);
-        const uint32_t sh = (rel & 3u) * 8u;
-        uint32_t w0, w1, w2, w3, w4;
-        switch ((rel >> 2) & 3u) {
-            case 0: w0 = lo.x; w1 = lo.y; w2 = lo.z; w3 = lo.w; w4 = hi.x; break;
-            case 1: w0 = lo.y; w1 = lo.z; w2 = lo.w; w3 = hi.x; w4 = hi.y; break;
-            case 2: w0 = lo.z; w1 = lo.w; w2 = hi.x; w3 = hi.y; w4 = hi.z; break;
-            default: w0 = lo.w; w1 = hi.x; w2 = hi.y; w3 = hi.z; w4 = hi.w; break;
-        }
-        r.x = __funnelshift_r(w0, w1, sh);
-        r.y = __funnelshift_r(w1, w2, sh);
-        r.z = __funnelshift_r(w2, w3, sh);
-        r.w = __funnelshift_r(w3, w4, sh);
-    } else {  // the line started in an earlier tile: bytes come from global memory (L2)
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            uint32_t x = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) x |= byte_at(S, c, W, pos + 4 * i + b) << (8 * b);
-            w[i] = x;
-        }
-        r = make_uint4(w[0], w[1], w[2], w[3]);
+        // five consecutive words starting at word (rel >> 2) & 3 of {lo, hi}: two select levels, no branch
+        const bool s2 = (rel & 8u) != 0u, s1 = (rel & 4u) != 0u;
+        const uint32_t v0 = s2 ? lo.z : lo.x, v1 = s2 ? lo.w : lo.y, v2 = s2 ? hi.x : lo.z,
+                       v3 = s2 ? hi.y : lo.w, v4 = s2 ? hi.z : hi.x, v5 = s2 ? hi.w : hi.y;
+        w0 = s1 ? v1 : v0; w1 = s1 ? v2 : v1; w2 = s1 ? v3 : v2; w3 = s1 ? v4 : v3; w4 = s1 ? v5 : v4;
+    } else {
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(W.base);
+        const uint32_t wi = pos >> 2;                       // garbage when pos wrapped: guarded
+        const uint32_t wend = (W.end + 3u) >> 2;            // words that hold window bytes
+        const bool neg = (int32_t)pos < 0;
+        w0 = (!neg && wi + 0u < wend) ? __ldg(g + wi + 0u) : 0u;
+        w1 = (!neg && wi + 1u < wend) ? __ldg(g + wi + 1u) : 0u;
+        w2 = (!neg && wi + 2u < wend) ? __ldg(g + wi + 2u) : 0u;
+        w3 = (!neg && wi + 3u < wend) ? __ldg(g + wi + 3u) : 0u;
+        w4 = (!neg && wi + 4u < wend) ? __ldg(g + wi + 4u) : 0u;
     }
+    uint4 r;
+    r.x = __funnelshift_r(w0, w1, sh);
+    r.y = __funnelshift_r(w1, w2, sh);
+    r.z = __funnelshift_r(w2, w3, sh);
+    r.w = __funnelshift_r(w3, w4, sh);
     return r;
 }
 
+// bytes [0, a) of the result come from acc, bytes [a, 16) from x   (0 < a < 16)
+__device__ __forceinline__ uint4 splice16(uint4 acc, uint4 x, uint32_t a) {
+    // per word: the k = clamp(a - 4w, 0, 4) low bytes stay from acc; mask = 0xFFFFFFFF >> 8(4 - k),
+    // with the shift clamped at 32 (funnel shift) so that k == 0 gives 0
+    auto keep = [&](int w) -> uint32_t {
+        int k = (int)a - 4 * w;
+        k = k < 0 ? 0 : (k > 4 ? 4 : k);
+        return __funnelshift_rc(0xFFFFFFFFu, 0u, 8u * (uint32_t)(4 - k));
+    };
+    const uint32_t m0 = keep(0), m1 = keep(1), m2 = keep(2), m3 = keep(3);
+    acc.x = (acc.x & m0) | (x.x & ~m0);
+    acc.y = (acc.y & m1) | (x.y & ~m1);
+    acc.z = (acc.z & m2) | (x.z & ~m2);
+    acc.w = (acc.w & m3) | (x.w & ~m3);
+    return acc;
+}
+
+// stores bytes [a, b) of v at p[a..b)   (p 16-byte aligned; used for the two edge vectors of a range)
+__device__ __forceinline__ void store_partial16(uint8_t* p, uint4 v, uint32_t a, uint32_t b) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (uint32_t i = 0; i < 4u; ++i) {
+        if (a <= 4u * i && b >= 4u * i + 4u) {
+            *reinterpret_cast<uint32_t*>(p + 4u * i) = w[i];
+        } else {
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k)
+                if (4u * i + k >= a && 4u * i + k < b) p[4u * i + k] = (uint8_t)(w[i] >> (8u * k));
+        }
+    }
+}
+
 // Copies the lines of one class stream that ended in this pass: destination range [d0, d1) of the
-// stream (virtual offsets: out is 16-byte aligned and d includes the sub-16 shift).
+// stream (virtual offsets: `out` is 16-byte aligned and d includes the sub-16 shift).  One 16-byte
+// destination vector per thread and step: the vector is assembled from the (usually one, sometimes
+// two or three) lines that intersect it and written with one aligned 16-byte store.
 __device__ __forceinline__ void copy_stream(const TileSmem& S, const TileCursor& c, const WinParams& W,
                                             const uint32_t* __restrict__ sdst, const uint32_t* __restrict__ ssrc,
                                             uint32_t n_lines, uint32_t d0, uint32_t d1, uint8_t* __restrict__ out,
                                             int64_t room) {
     // room = bytes the arena can still take from `out`.  Destinations past it only arise after
     // a structure error (an empty header line makes the id prefix diverge); nothing there counts.
-    if (d1 <= d0 || (int64_t)d1 > room) return;
+    if (d1 <= d0 || (int64_t)d1 > room || n_lines == 0u) return;
     const uint32_t v0 = d0 >> 4, v1 = (d1 + 15u) >> 4;
+    const float inv = (float)n_lines / (float)(d1 - d0);   // lines are of similar length: first guess
     for (uint32_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
-        const uint32_t lo = v * 16u < d0 ? d0 : v * 16u;
-        const uint32_t hi = v * 16u + 16u > d1 ? d1 : v * 16u + 16u;
-        // last line with sdst <= lo; sdst[n_lines] = d1 is the sentinel
-        uint32_t a = 0, b = n_lines;
-        while (b - a > 1u) {
-            const uint32_t m = (a + b) >> 1;
-            if (sdst[m] <= lo) a = m; else b = m;
-        }
-        uint32_t i = a;
-        if (hi - lo == 16u && sdst[i + 1] >= hi) {
-            const uint4 x = load16(S, c, W, ssrc[i] + (lo - sdst[i]));
-            *reinterpret_cast<uint4*>(out + (size_t)v * 16u) = x;
-        } else {
-            for (uint32_t d = lo; d < hi; ++d) {
-                while (sdst[i + 1] <= d) ++i;  // skips empty lines; the sentinel stops it
-                out[d] = (uint8_t)byte_at(S, c, W, ssrc[i] + (d - sdst[i]));
+        const uint32_t vs = v * 16u;
+        const uint32_t lo = vs < d0 ? d0 : vs;
+        const uint32_t hi = vs + 16u > d1 ? d1 : vs + 16u;
+        // line i with sdst[i] <= lo < sdst[i + 1]   (sdst[0] == d0, sdst[n_lines] == d1 > lo)
+        uint32_t i = (uint32_t)((float)(lo - d0) * inv);
+        if (i >= n_lines) i = n_lines - 1u;
+        int steps = 0;
+        while (sdst[i] > lo && steps < 8) { --i; ++steps; }
+        while (sdst[i + 1] <= lo && steps < 8) { ++i; ++steps; }
+        if (sdst[i] > lo || sdst[i + 1] <= lo) {   // far from the guess (very uneven lines): bisect
+            uint32_t a = 0, b = n_lines;
+            while (b - a > 1u) {
+                const uint32_t m = (a + b) >> 1;
+                if (sdst[m] <= lo) a = m; else b = m;
             }
+            i = a;
         }
+        // byte k of acc <-> destination vs + k
+        uint4 acc = load16(S, c, W, ssrc[i] + (vs - sdst[i]));
+        uint32_t e = sdst[i + 1];
+        while (e < hi) {                           // the next line begins inside this vector
+            ++i;
+            while (sdst[i + 1] == e) ++i;          // skip empty lines (the sentinel d1 >= hi > e stops it)
+            const uint32_t a = e - vs;
+            acc = splice16(acc, load16(S, c, W, ssrc[i] - a), a);
+            e = sdst[i + 1];
+        }
+        uint8_t* p = out + (size_t)v * 16u;
+        if (hi - lo == 16u) *reinterpret_cast<uint4*>(p) = acc;
+        else store_partial16(p, acc, lo - vs, hi - vs);
     }
 }
 
@@ -546,14 +624,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_resolve(const WinParams W, cons
     if (kOffsets && blockIdx.x == 0 && tid == 0) P.line_ends[0] = W.begin - 1u;
 
     const uint32_t addlo = (128u - P.lower) * 0x01010101u, addup = (127u - P.upper) * 0x01010101u;
+    uint32_t bases_acc = 0;                                              // this thread's share of sum(seq_len)
     uint32_t rank = pre.rank;                                            // rank of the tile's first newline
     uint32_t cum_id = pre.cum_id, cum_seq = pre.cum_seq, cum_qual = pre.cum_qual;  // stream destinations
+    uint32_t par = 0;
     // virtual destination offsets: out pointers rounded down to 16 bytes, offsets shifted up
     const uint32_t sh_id = (uint32_t)(P.id_base64 & 15), sh_seq = (uint32_t)(P.seq_base64 & 15),
                    sh_qual = (uint32_t)(P.qual_base64 & 15);
     uint8_t* const out_id = kPack ? P.id_out + (P.id_base64 - sh_id) : nullptr;
     uint8_t* const out_seq = kPack ? P.seq_out + (P.seq_base64 - sh_seq) : nullptr;
     uint8_t* const out_qual = kPack ? P.qual_out + (P.qual_base64 - sh_qual) : nullptr;
+    const uint32_t bsz = (uint32_t)P.batch_size;
 
     for (uint32_t t = ta; t < tb; ++t) {
         const uint32_t it = t - ta;
@@ -564,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_resolve(const WinParams W, cons
         const uint4 words = *reinterpret_cast<const uint4*>(&S.bm_nl[tid * 4]);
         const uint32_t cnt = __popc(words.x) + __popc(words.y) + __popc(words.z) + __popc(words.w);
         uint32_t total;
-        const uint32_t excl = block_exclusive_scan(S, cnt, total);
+        const uint32_t excl = block_exclusive_scan(S, cnt, total, par);
 
         // ---- validation from the bitmaps: this thread's 128 bytes, line class known from the rank
         if (kAscii || kQual) {
@@ -596,85 +677,93 @@ __global__ void __launch_bounds__(kThreads, 2) k_resolve(const WinParams W, cons
 
         for (uint32_t pass = 0; pass < total; pass += kNlCap) {
             const uint32_t n = total - pass < (uint32_t)kNlCap ? total - pass : (uint32_t)kNlCap;
-            fill_newline_list(S, c, words, excl, pass);
+            if (total <= (uint32_t)kNlCap) fill_newline_list<false>(S, c, words, excl, 0u);
+            else fill_newline_list<true>(S, c, words, excl, pass);
             __syncthreads();
             const uint32_t r0 = rank + pass;  // rank of list entry 0
-            // stream bookkeeping for this pass
             const uint32_t d0_id = cum_id, d0_seq = cum_seq, d0_qual = cum_qual;
+            // first list entry of each class and the number of lines per class in this pass
             const uint32_t j_id = (0u - r0) & 3u, j_seq = (1u - r0) & 3u, j_qual = (3u - r0) & 3u;
+            const uint32_t n_id = j_id < n ? ((n - 1u - j_id) >> 2) + 1u : 0u;
+            const uint32_t n_seq = j_seq < n ? ((n - 1u - j_seq) >> 2) + 1u : 0u;
+            const uint32_t n_qual = j_qual < n ? ((n - 1u - j_qual) >> 2) + 1u : 0u;
+            // does a batch boundary fall among the records that end in this pass?  (uniform)
+            const uint32_t k_first = r0 >> 2, k_last = (r0 + n - 1u) >> 2;
+            const bool batch_edge = kPack && (P.rec_mod + k_first) / bsz != (P.rec_mod + k_last + 1u) / bsz;
 
-            for (uint32_t jb = 0; jb < n; jb += kThreads) {
-                const uint32_t j = jb + tid;
-                uint32_t v_id = 0, v_seq = 0, v_qual = 0, cls = 4, k = 0, p = 0, q1 = 0, len = 0, src = 0;
-                bool live = false;
-                if (j < n) {
-                    p = S.nlx[kHead + j];
-                    q1 = S.nlx[kHead + j - 1];
-                    const uint32_t r = r0 + j;
-                    cls = r & 3u; k = r >> 2;
-                    live = k < P.n_complete;
-                    len = p - q1 - 1u;
+            // every thread owns q consecutive list entries: [tid*q, tid*q + q)
+            const uint32_t q = (n + kThreads - 1u) / kThreads;
+            const uint32_t jb = tid * q, je = jb + q < n ? jb + q : n;
+            uint32_t v_id = 0, v_seq = 0, v_qual = 0;
+            for (uint32_t j = jb; j < je; ++j) {
+                const uint32_t p = S.nlx[kHead + j];
+                const uint32_t q1 = S.nlx[kHead + j - 1];
+                const uint32_t r = r0 + j;
+                const uint32_t cls = r & 3u, k = r >> 2;
+                const bool live = k < P.n_complete;
+                const uint32_t len = p - q1 - 1u;
+                if (kOffsets) P.line_ends[1u + r] = p;
+                if (cls == 0u) {
+                    // header line: '@' check (utils.mojo:454), id = line minus '@', stripped
+                    uint32_t a = q1 + 2u, nid = 0;
                     if (live) {
-                        if (cls == 0u) {
-                            // header line: '@' check (utils.mojo:454), id = line minus '@', stripped
-                            const uint32_t hs = q1 + 1u;
-                            if (byte_at(S, c, W, hs) != '@') report(P, k, 1u);
-                            uint32_t a = hs + 1u, nid = len > 0u ? len - 1u : 0u;
-                            if (nid > 0u && (bsq_is_space(byte_at(S, c, W, a)) || bsq_is_space(byte_at(S, c, W, p - 1u)))) {
-                                uint32_t e = p;
-                                while (a < e && bsq_is_space(byte_at(S, c, W, a))) ++a;
-                                while (e > a && bsq_is_space(byte_at(S, c, W, e - 1u))) --e;
-                                nid = e - a;
-                            }
-                            if (kOffsets || (kPack && !P.id_fast)) { P.id_spans[2u * k] = a; P.id_spans[2u * k + 1u] = nid; }
-                            v_id = nid; src = a;
-                        } else if (cls == 1u) {
-                            v_seq = len; src = q1 + 1u;
-                        } else if (cls == 2u) {
-                            if (byte_at(S, c, W, q1 + 1u) != '+') report(P, k, 2u);  // utils.mojo:456
-                        } else {
-                            const uint32_t q2 = S.nlx[kHead + j - 2], q3 = S.nlx[kHead + j - 3];
-                            if (q2 - q3 - 1u != len) report(P, k, 3u);              // utils.mojo:458-461
-                            v_qual = len; src = q1 + 1u;
+                        if (byte_at(S, c, W, q1 + 1u) != '@') report(P, k, 1u);
+                        nid = len > 0u ? len - 1u : 0u;
+                        if (nid > 0u && (bsq_is_space(byte_at(S, c, W, a)) || bsq_is_space(byte_at(S, c, W, p - 1u)))) {
+                            uint32_t e = p;
+                            while (a < e && bsq_is_space(byte_at(S, c, W, a))) ++a;
+                            while (e > a && bsq_is_space(byte_at(S, c, W, e - 1u))) --e;
+                            nid = e - a;
+                            if (kPack && P.id_fast) *P.strip_flag = 1u;   // the optimistic id packing is void
                         }
+                        if (kOffsets || (kPack && !P.id_fast)) { P.id_spans[2u * k] = a; P.id_spans[2u * k + 1u] = nid; }
                     }
-                    if (kOffsets) P.line_ends[1u + r] = p;
-                }
-                if (kPack) {
-                    uint32_t e_id, e_seq, e_qual, t_id, t_seq, t_qual;
-                    block_exclusive_scan3(S, v_id, v_seq, v_qual, e_id, e_seq, e_qual, t_id, t_seq, t_qual);
-                    if (j < n && cls != 2u && cls != 4u) {
-                        // one entry per line of the class, live or not (dead lines have length 0)
-                        if (cls == 0u) {
-                            const uint32_t i = (j - j_id) >> 2;
-                            S.sdst[0][i] = cum_id + e_id + sh_id; S.ssrc[0][i] = src;
-                            if (live && P.id_fast) {
-                                const int64_t endv = P.id_base64 + (int64_t)(cum_id + e_id + v_id);
-                                const int64_t gk = P.rec_base + (int64_t)k;
-                                P.id_ends_abs[gk] = endv;
-                                if ((gk + 1) % P.batch_size == 0) P.id_ends_base[(gk + 1) / P.batch_size] = endv;
-                            }
-                        } else if (cls == 1u) {
-                            const uint32_t i = (j - j_seq) >> 2;
-                            S.sdst[1][i] = cum_seq + e_seq + sh_seq; S.ssrc[1][i] = src;
-                        } else {
-                            const uint32_t i = (j - j_qual) >> 2;
-                            S.sdst[2][i] = cum_qual + e_qual + sh_qual; S.ssrc[2][i] = src;
-                            if (live) {
-                                const int64_t endv = P.qual_base64 + (int64_t)(cum_qual + e_qual + v_qual);
-                                const int64_t gk = P.rec_base + (int64_t)k;
-                                P.ends_abs[gk] = endv;
-                                if ((gk + 1) % P.batch_size == 0) P.ends_base[(gk + 1) / P.batch_size] = endv;
-                            }
-                        }
-                    }
-                    cum_id += t_id; cum_seq += t_seq; cum_qual += t_qual;
+                    if (kPack) { const uint32_t i = (j - j_id) >> 2; S.sdst[0][i] = nid; S.ssrc[0][i] = a; v_id += nid; }
+                } else if (cls == 1u) {
+                    const uint32_t l = live ? len : 0u;
+                    bases_acc += l;
+                    if (kPack) { const uint32_t i = (j - j_seq) >> 2; S.sdst[1][i] = l; S.ssrc[1][i] = q1 + 1u; v_seq += l; }
+                } else if (cls == 2u) {
+                    if (live && byte_at(S, c, W, q1 + 1u) != '+') report(P, k, 2u);      // utils.mojo:456
+                } else {
+                    const uint32_t q2 = S.nlx[kHead + j - 2], q3 = S.nlx[kHead + j - 3];
+                    if (live && q2 - q3 - 1u != len) report(P, k, 3u);                   // utils.mojo:458-461
+                    const uint32_t l = live ? len : 0u;
+                    if (kPack) { const uint32_t i = (j - j_qual) >> 2; S.sdst[2][i] = l; S.ssrc[2][i] = q1 + 1u; v_qual += l; }
                 }
             }
             if (kPack) {
-                const uint32_t n_id = j_id < n ? ((n - 1u - j_id) >> 2) + 1u : 0u;
-                const uint32_t n_seq = j_seq < n ? ((n - 1u - j_seq) >> 2) + 1u : 0u;
-                const uint32_t n_qual = j_qual < n ? ((n - 1u - j_qual) >> 2) + 1u : 0u;
+                uint32_t e_id, e_seq, e_qual, t_id, t_seq, t_qual;
+                block_exclusive_scan3(S, v_id, v_seq, v_qual, e_id, e_seq, e_qual, t_id, t_seq, t_qual, par);
+                // second walk: lengths -> destinations; cumulative ends of the records that finish here
+                uint32_t a_id = cum_id + e_id, a_seq = cum_seq + e_seq, a_qual = cum_qual + e_qual;
+                for (uint32_t j = jb; j < je; ++j) {
+                    const uint32_t r = r0 + j;
+                    const uint32_t cls = r & 3u, k = r >> 2;
+                    if (cls == 0u) {
+                        const uint32_t i = (j - j_id) >> 2, l = S.sdst[0][i];
+                        S.sdst[0][i] = a_id + sh_id; a_id += l;
+                        if (P.id_fast && k < P.n_complete) {
+                            const int64_t endv = P.id_base64 + (int64_t)a_id;
+                            P.id_ends_abs[P.rec_base + (int64_t)k] = endv;
+                            if (batch_edge) { const uint32_t tb1 = P.rec_mod + k + 1u;
+                                if (tb1 % bsz == 0u) P.id_ends_base[P.rec_div + (int64_t)(tb1 / bsz)] = endv; }
+                        }
+                    } else if (cls == 1u) {
+                        const uint32_t i = (j - j_seq) >> 2, l = S.sdst[1][i];
+                        S.sdst[1][i] = a_seq + sh_seq; a_seq += l;
+                    } else if (cls == 3u) {
+                        const uint32_t i = (j - j_qual) >> 2, l = S.sdst[2][i];
+                        S.sdst[2][i] = a_qual + sh_qual; a_qual += l;
+                        if (k < P.n_complete) {
+                            const int64_t endv = P.qual_base64 + (int64_t)a_qual;
+                            P.ends_abs[P.rec_base + (int64_t)k] = endv;
+                            if (batch_edge) { const uint32_t tb1 = P.rec_mod + k + 1u;
+                                if (tb1 % bsz == 0u) P.ends_base[P.rec_div + (int64_t)(tb1 / bsz)] = endv; }
+                        }
+                    }
+                }
+                cum_id += t_id; cum_seq += t_seq; cum_qual += t_qual;
                 if (tid == 0) {
                     S.sdst[0][n_id] = cum_id + sh_id; S.sdst[1][n_seq] = cum_seq + sh_seq;
                     S.sdst[2][n_qual] = cum_qual + sh_qual;
@@ -692,9 +781,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_resolve(const WinParams W, cons
             __syncthreads();
         }
         rank += total;
-        __syncthreads();
+        if (total == 0u) __syncthreads();   // (the pass loop ends with a barrier otherwise)
         if (tid == 0 && t + kStages < tb) issue_tile_load(S, W, t + kStages, c.stage);
     }
+    // one atomic per warp: the run's share of the base count
+    unsigned long long b64 = bases_acc;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) b64 += __shfl_xor_sync(0xFFFFFFFFu, b64, d);
+    if ((tid & 31u) == 0u && b64 != 0ull) atomicAdd(P.bases, b64);
 }
 
 }  // namespace bsq

@@ -126,7 +126,7 @@ BSQ_HD BsqTotals bsq_totals_from(const BsqSummary& E_end, uint32_t begin) {
 
 // is_posix_space, utils.mojo:266-289: {9,10,11,12,13,28,29,30,32}
 BSQ_HD bool bsq_is_space(uint32_t c) {
-    return c <= 32u && ((0x170003E00ull >> c) & 1ull);
+    return c == 32u || (c < 32u && ((0x70003E00u >> c) & 1u));
 }
 
 // ---- byte-lane SIMD-in-register helpers: results have 0x80 in each byte lane that matches ----

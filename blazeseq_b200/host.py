@@ -417,7 +417,7 @@ class GpuParser:
     def batch_to_host(self, index: int):
         v = self.batch_view(index)
         n = int(v.num_records)
-        seq = np.zeros(int(v.seq_len), np.uint8)
+        seq = np.zeros(int(v.sequence_bytes), np.uint8)
         qual = np.zeros(int(v.seq_len), np.uint8)
         idb = np.zeros(int(v.total_id_bytes), np.uint8)
         ends = np.zeros(n, np.int64)
@@ -528,6 +528,8 @@ class FastqParser:
                 break
             parts.append(buf[:got])
             have += got
+        if not parts:
+            return np.zeros(0, np.uint8)
         return np.concatenate(parts) if len(parts) != 1 else parts[0]
 
     def _first_fill(self):
@@ -590,11 +592,10 @@ class FastqParser:
             if n == 0:
                 continue
             base = int(v.stream_base) - reg.stream_offset
-            le = le.astype(np.int64)
             q = le.reshape(-1)[: 4 * n + 1]
-            for k in range(4):
-                cols[k].append(q[k:4 * n:4] + 1 + base)
-            cols[4].append(q[4:4 * n + 1:4] + base)
+            for k in range(4):  # u32 arithmetic: the leading sentinel is begin-1 and may wrap
+                cols[k].append((q[k:4 * n:4] + np.uint32(1)).astype(np.int64) + base)
+            cols[4].append(q[4:4 * n + 1:4].astype(np.int64) + base)
             cols[5].append(sp[0::2].astype(np.int64) + base)
             cols[6].append(sp[1::2].astype(np.int64))
         if cols[0]:

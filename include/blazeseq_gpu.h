@@ -123,6 +123,10 @@ typedef struct bsq_batch_view {
     int64_t total_id_bytes;
     uint8_t quality_offset;        /* always 33 on this path (parser.mojo:243) */
     uint8_t _pad[7];
+    int64_t sequence_bytes;        /* bytes in sequence_buffer: == seq_len, except when the batch ends
+                                      with a stream's last record that has no trailing newline -- it is
+                                      accepted without the length check, and `ends` counts QUALITY
+                                      bytes (record_batch.mojo:83-87) */
     const uint8_t* sequence_buffer;
     const uint8_t* qual_buffer;
     const uint8_t* id_buffer;
@@ -181,7 +185,8 @@ bsq_status bsq_get_batch(const bsq_parser* p, int64_t batch_index, bsq_batch_vie
 /* Whole-pass SoA (all batches back to back; ends/id_ends are the per-batch rebased values). */
 bsq_status bsq_get_soa(const bsq_parser* p, bsq_batch_view* out);
 /* DeviceFastqBatch.copy_to_host (record_batch.mojo:222-241): copies one batch into caller
- * arrays sized from bsq_batch_view (seq_len, seq_len, total_id_bytes, num_records, num_records). */
+ * arrays sized from bsq_batch_view (sequence_bytes, seq_len, total_id_bytes, num_records,
+ * num_records). */
 bsq_status bsq_batch_to_host(bsq_parser* p, int64_t batch_index, uint8_t* seq, uint8_t* qual,
                              uint8_t* id, int64_t* ends, int64_t* id_ends);
 /* Copies one window's offsets table to the host (line_ends: 4n+1, id_spans: 2n entries). */

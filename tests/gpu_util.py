@@ -23,10 +23,9 @@ def gpu_offsets(gpu: B.GpuParser, res):
         if not n:
             continue
         base = int(v.stream_base)
-        le = le.astype(np.int64)
-        for k in range(4):
-            cols[NAMES5[k]].append(le[k:4 * n:4] + 1 + base)
-        cols["record_end"].append(le[4:4 * n + 1:4] + base)
+        for k in range(4):  # u32 arithmetic: the leading sentinel is begin-1 and may wrap
+            cols[NAMES5[k]].append((le[k:4 * n:4] + np.uint32(1)).astype(np.int64) + base)
+        cols["record_end"].append(le[4:4 * n + 1:4].astype(np.int64) + base)
         cols["id_start"].append(sp[0::2].astype(np.int64) + base)
         cols["id_len"].append(sp[1::2].astype(np.int64))
     return {k: (np.concatenate(v) if v else np.zeros(0, np.int64)) for k, v in cols.items()}

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header(B):
     c = B._capi
     assert C.sizeof(c.Config) == 56 and C.sizeof(c.Error) == 1056 and C.sizeof(c.Summary) == 64
     assert C.sizeof(c.PassResult) == 48 + 1056 and C.sizeof(c.OffsetsView) == 48
-    assert C.sizeof(c.BatchView) == 72 and C.sizeof(c.ShardStart) == 32
+    assert C.sizeof(c.BatchView) == 80 and C.sizeof(c.ShardStart) == 32
 
 
 def test_no_cpu_fallback(B):
