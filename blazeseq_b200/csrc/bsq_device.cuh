@@ -33,7 +33,8 @@ constexpr int kWords = kTile / 32;        // bitmap words per tile (1024)
 constexpr int kWordsPerThread = kWords / kThreads;    // 4 -> a thread ranks 128 contiguous bytes
 constexpr int kNlCap = 2048;              // newline-list capacity per pass over a tile
 constexpr int kHead = 4;                  // carried newline positions in front of the list
-constexpr int kLinesCap = kNlCap / 4 + 2; // lines of one class per pass (+ sentinel)
+constexpr int kLinesCap = kNlCap / 4 + 3; // lines of one class per pass (+ two sentinels)
+constexpr int kVecCap = 2112;             // destination vectors of one class per pass with a line table
 constexpr int kTilePad = 32;              // readable slack after a tile for unaligned 16-byte loads
 constexpr int kMaxWindows = 64;
 
@@ -143,6 +144,7 @@ struct alignas(128) TileSmem {
                                               // nlx[kHead-1-i] = i-th newline before the list
     uint32_t sdst[3][kLinesCap];              // per class stream: destination of each line
     uint32_t ssrc[3][kLinesCap];              //                   source position of each line
+    uint16_t vline[3][kVecCap];               // line that holds the first byte of each destination vector
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -495,18 +497,12 @@ __device__ __forceinline__ void report(const ResolveParams& P, uint32_t k, uint3
 __device__ __forceinline__ uint4 load16(const TileSmem& S, const TileCursor& c, const WinParams& W, uint32_t pos) {
     const uint32_t rel = pos - c.origin;
     const uint32_t sh = (pos & 3u) * 8u;
-    uint32_t w0, w1, w2, w3, w4;
-    if (rel < (uint32_t)kTile) {
-        const uint8_t* t = S.data[c.stage];
-        const uint32_t a = rel & ~15u;
-        const uint4 lo = *reinterpret_cast<const uint4*>(t + a);
-        const uint4 hi = *reinterpret_cast<const uint4*>(t + a + 16u);
-        // five consecutive words starting at word (rel >> 2) & 3 of {lo, hi}: two select levels, no branch
-        const bool s2 = (rel & 8u) != 0u, s1 = (rel & 4u) != 0u;
-        const uint32_t v0 = s2 ? lo.z : lo.x, v1 = s2 ? lo.w : lo.y, v2 = s2 ? hi.x : lo.z,
-                       v3 = s2 ? hi.y : lo.w, v4 = s2 ? hi.z : hi.x, v5 = s2 ? hi.w : hi.y;
-        w0 = s1 ? v1 : v0; w1 = s1 ? v2 : v1; w2 = s1 ? v3 : v2; w3 = s1 ? v4 : v3; w4 = s1 ? v5 : v4;
-    } else {
+    const bool in_tile = rel < (uint32_t)kTile;
+    // five consecutive words (the tile is padded): 4-way bank conflicts, but no selects.  The read is
+    // unconditional (address clamped into the tile) so that the common path has no branch.
+    const uint32_t* t32 = reinterpret_cast<const uint32_t*>(S.data[c.stage]) + (in_tile ? (rel >> 2) : 0u);
+    uint32_t w0 = t32[0], w1 = t32[1], w2 = t32[2], w3 = t32[3], w4 = t32[4];
+    if (!in_tile) {   // the line began in an earlier tile: global memory (L2), guarded to the window
         const uint32_t* g = reinterpret_cast<const uint32_t*>(W.base);
         const uint32_t wi = pos >> 2;                       // garbage when pos wrapped: guarded
         const uint32_t wend = (W.end + 3u) >> 2;            // words that hold window bytes
@@ -525,7 +521,7 @@ __device__ __forceinline__ uint4 load16(const TileSmem& S, const TileCursor& c, 
     return r;
 }
 
-// bytes [0, a) of the result come from acc, bytes [a, 16) from x   (0 < a < 16)
+// bytes [0, a) of the result come from acc, bytes [a, 16) from x   (0 < a <= 16)
 __device__ __forceinline__ uint4 splice16(uint4 acc, uint4 x, uint32_t a) {
     // per word: the k = clamp(a - 4w, 0, 4) low bytes stay from acc; mask = 0xFFFFFFFF >> 8(4 - k),
     // with the shift clamped at 32 (funnel shift) so that k == 0 gives 0
@@ -557,50 +553,88 @@ __device__ __forceinline__ void store_partial16(uint8_t* p, uint4 v, uint32_t a,
     }
 }
 
+// Line table of one class stream: vline[u] = line that holds the first byte of destination vector
+// v0 + u.  One thread per line; every vector is written exactly once.  Requires (v1 - v0) <= kVecCap.
+__device__ __forceinline__ void build_line_table(const uint32_t* __restrict__ sdst, uint32_t n_lines, uint32_t d0,
+                                                 uint32_t d1, uint16_t* __restrict__ vline) {
+    if (d1 <= d0) return;
+    const uint32_t v0 = d0 >> 4;
+    for (uint32_t i = threadIdx.x; i < n_lines; i += kThreads) {
+        const uint32_t s0 = sdst[i], s1 = sdst[i + 1];
+        if (s1 == s0) continue;                                  // empty line: owns no byte
+        uint32_t lo = s0 == d0 ? v0 : (s0 + 15u) >> 4;           // the line holding d0 owns vector v0
+        const uint32_t hi = (s1 + 15u) >> 4;
+        for (uint32_t v = lo; v < hi; ++v) vline[v - v0] = (uint16_t)i;
+    }
+}
+
 // Copies the lines of one class stream that ended in this pass: destination range [d0, d1) of the
 // stream (virtual offsets: `out` is 16-byte aligned and d includes the sub-16 shift).  One 16-byte
-// destination vector per thread and step: the vector is assembled from the (usually one, sometimes
-// two or three) lines that intersect it and written with one aligned 16-byte store.
-__device__ __forceinline__ void copy_stream(const TileSmem& S, const TileCursor& c, const WinParams& W,
-                                            const uint32_t* __restrict__ sdst, const uint32_t* __restrict__ ssrc,
-                                            uint32_t n_lines, uint32_t d0, uint32_t d1, uint8_t* __restrict__ out,
-                                            int64_t room) {
-    // room = bytes the arena can still take from `out`.  Destinations past it only arise after
-    // a structure error (an empty header line makes the id prefix diverge); nothing there counts.
-    if (d1 <= d0 || (int64_t)d1 > room || n_lines == 0u) return;
-    const uint32_t v0 = d0 >> 4, v1 = (d1 + 15u) >> 4;
-    const float inv = (float)n_lines / (float)(d1 - d0);   // lines are of similar length: first guess
-    for (uint32_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
-        const uint32_t vs = v * 16u;
-        const uint32_t lo = vs < d0 ? d0 : vs;
-        const uint32_t hi = vs + 16u > d1 ? d1 : vs + 16u;
-        // line i with sdst[i] <= lo < sdst[i + 1]   (sdst[0] == d0, sdst[n_lines] == d1 > lo)
-        uint32_t i = (uint32_t)((float)(lo - d0) * inv);
-        if (i >= n_lines) i = n_lines - 1u;
-        int steps = 0;
-        while (sdst[i] > lo && steps < 8) { --i; ++steps; }
-        while (sdst[i + 1] <= lo && steps < 8) { ++i; ++steps; }
-        if (sdst[i] > lo || sdst[i + 1] <= lo) {   // far from the guess (very uneven lines): bisect
-            uint32_t a = 0, b = n_lines;
-            while (b - a > 1u) {
-                const uint32_t m = (a + b) >> 1;
-                if (sdst[m] <= lo) a = m; else b = m;
-            }
-            i = a;
+// destination vector per thread and step.  Source of destination byte d inside line i is
+// d + (ssrc[i] - sdst[i]), so a vector is two unaligned 16-byte reads (its first line and the next
+// one) spliced at the line boundary, and one aligned 16-byte store; a third line inside the same
+// vector (ids, very short reads) takes the loop.
+struct StreamJob {
+    const uint32_t* sdst; const uint32_t* ssrc; const uint16_t* vline;
+    uint32_t n_lines, d0, d1; uint8_t* out; bool table;
+};
+
+// the 16 bytes of destination vector v of a stream (byte k <-> destination 16 v + k)
+__device__ __forceinline__ uint4 assemble_vector(const TileSmem& S, const TileCursor& c, const WinParams& W,
+                                                 const StreamJob& J, uint32_t v, uint32_t lo, uint32_t hi) {
+    const uint32_t vs = v * 16u;
+    uint32_t i;
+    if (J.table) {
+        i = J.vline[v - (J.d0 >> 4)];
+    } else {                                   // more vectors than the table holds (long reads): bisect
+        uint32_t a = 0, b = J.n_lines;
+        while (b - a > 1u) {
+            const uint32_t m = (a + b) >> 1;
+            if (J.sdst[m] <= lo) a = m; else b = m;
         }
-        // byte k of acc <-> destination vs + k
-        uint4 acc = load16(S, c, W, ssrc[i] + (vs - sdst[i]));
-        uint32_t e = sdst[i + 1];
-        while (e < hi) {                           // the next line begins inside this vector
+        i = a;
+    }
+    uint32_t e = J.sdst[i + 1];
+    const uint32_t a1 = e - vs < 16u ? e - vs : 16u;              // bytes of this vector before line i+1
+    uint4 acc = load16(S, c, W, vs + (J.ssrc[i] - J.sdst[i]));
+    acc = splice16(acc, load16(S, c, W, J.ssrc[i + 1] - a1), a1);
+    if (e < hi) {
+        ++i;
+        e = J.sdst[i + 1];
+        while (e < hi) {                       // a third (fourth, ...) line begins inside this vector
             ++i;
-            while (sdst[i + 1] == e) ++i;          // skip empty lines (the sentinel d1 >= hi > e stops it)
             const uint32_t a = e - vs;
-            acc = splice16(acc, load16(S, c, W, ssrc[i] - a), a);
-            e = sdst[i + 1];
+            if (J.sdst[i + 1] != e) acc = splice16(acc, load16(S, c, W, J.ssrc[i] - a), a);
+            e = J.sdst[i + 1];
         }
-        uint8_t* p = out + (size_t)v * 16u;
-        if (hi - lo == 16u) *reinterpret_cast<uint4*>(p) = acc;
-        else store_partial16(p, acc, lo - vs, hi - vs);
+    }
+    return acc;
+}
+
+// Copies the lines of one class stream that ended in this pass: destination range [d0, d1) of the
+// stream (virtual offsets: `out` is 16-byte aligned and d includes the sub-16 shift).  Source of
+// destination byte d inside line i is d + (ssrc[i] - sdst[i]), so a 16-byte destination vector is
+// two unaligned 16-byte reads (its first line and the next one) spliced at the line boundary and
+// one aligned 16-byte store; a third line inside the same vector (ids, very short reads) takes a
+// loop.  Two vectors per thread are in flight.
+__device__ __noinline__ void copy_stream(const TileSmem& S, const TileCursor& c, const WinParams& W, const StreamJob J) {
+    const uint32_t v0 = J.d0 >> 4, v1 = (J.d1 + 15u) >> 4;
+    for (uint32_t v = v0 + threadIdx.x; v < v1; v += 2u * kThreads) {
+        const uint32_t u = v + kThreads;
+        const bool two = u < v1;
+        const uint32_t lo_v = v * 16u < J.d0 ? J.d0 : v * 16u, hi_v = v * 16u + 16u > J.d1 ? J.d1 : v * 16u + 16u;
+        const uint32_t lo_u = u * 16u, hi_u = u * 16u + 16u > J.d1 ? J.d1 : u * 16u + 16u;
+        const uint4 av = assemble_vector(S, c, W, J, v, lo_v, hi_v);
+        uint4 au = make_uint4(0, 0, 0, 0);
+        if (two) au = assemble_vector(S, c, W, J, u, lo_u, hi_u);
+        uint8_t* pv = J.out + (size_t)v * 16u;
+        if (hi_v - lo_v == 16u) *reinterpret_cast<uint4*>(pv) = av;
+        else store_partial16(pv, av, lo_v - v * 16u, hi_v - v * 16u);
+        if (two) {
+            uint8_t* pu = J.out + (size_t)u * 16u;
+            if (hi_u - lo_u == 16u) *reinterpret_cast<uint4*>(pu) = au;
+            else store_partial16(pu, au, 0u, hi_u - lo_u);
+        }
     }
 }
 
@@ -764,17 +798,34 @@ __global__ void __launch_bounds__(kThreads, 2) k_resolve(const WinParams W, cons
                     }
                 }
                 cum_id += t_id; cum_seq += t_seq; cum_qual += t_qual;
-                if (tid == 0) {
-                    S.sdst[0][n_id] = cum_id + sh_id; S.sdst[1][n_seq] = cum_seq + sh_seq;
-                    S.sdst[2][n_qual] = cum_qual + sh_qual;
+                if (tid < 3) {
+                    // two sentinels per stream: the end of the range, and a source for the "next line" read
+                    const uint32_t nn = tid == 0 ? n_id : (tid == 1 ? n_seq : n_qual);
+                    const uint32_t dd = tid == 0 ? cum_id + sh_id : (tid == 1 ? cum_seq + sh_seq : cum_qual + sh_qual);
+                    S.sdst[tid][nn] = dd; S.sdst[tid][nn + 1] = dd; S.sdst[tid][nn + 2] = dd;
+                    S.ssrc[tid][nn] = c.origin + 16u; S.ssrc[tid][nn + 1] = c.origin + 16u;
                 }
                 __syncthreads();
-                const int64_t big = (int64_t)1 << 40;
-                if (P.id_fast)
-                    copy_stream(S, c, W, S.sdst[0], S.ssrc[0], n_id, d0_id + sh_id, cum_id + sh_id, out_id,
-                                P.id_cap - (P.id_base64 - sh_id));
-                copy_stream(S, c, W, S.sdst[1], S.ssrc[1], n_seq, d0_seq + sh_seq, cum_seq + sh_seq, out_seq, big);
-                copy_stream(S, c, W, S.sdst[2], S.ssrc[2], n_qual, d0_qual + sh_qual, cum_qual + sh_qual, out_qual, big);
+                // room: bytes the id arena can still take.  Destinations past it only arise after a
+                // structure error (an empty header line makes the id prefix diverge); nothing there counts.
+                const uint32_t ra_id = d0_id + sh_id, rb_id = cum_id + sh_id;
+                const bool do_id = P.id_fast && rb_id > ra_id && (int64_t)rb_id <= P.id_cap - (P.id_base64 - sh_id) && n_id != 0u;
+                const uint32_t ra_seq = d0_seq + sh_seq, rb_seq = cum_seq + sh_seq;
+                const uint32_t ra_qual = d0_qual + sh_qual, rb_qual = cum_qual + sh_qual;
+                const bool tb_id = ((rb_id + 15u) >> 4) - (ra_id >> 4) <= (uint32_t)kVecCap;
+                const bool tb_seq = ((rb_seq + 15u) >> 4) - (ra_seq >> 4) <= (uint32_t)kVecCap;
+                const bool tb_qual = ((rb_qual + 15u) >> 4) - (ra_qual >> 4) <= (uint32_t)kVecCap;
+                StreamJob jobs[3];
+                jobs[0] = StreamJob{S.sdst[0], S.ssrc[0], S.vline[0], n_id, ra_id, do_id ? rb_id : ra_id, out_id, tb_id};
+                jobs[1] = StreamJob{S.sdst[1], S.ssrc[1], S.vline[1], n_seq, ra_seq, rb_seq, out_seq, tb_seq};
+                jobs[2] = StreamJob{S.sdst[2], S.ssrc[2], S.vline[2], n_qual, ra_qual, rb_qual, out_qual, tb_qual};
+#pragma unroll
+                for (int st = 0; st < 3; ++st)
+                    if (jobs[st].table) build_line_table(jobs[st].sdst, jobs[st].n_lines, jobs[st].d0, jobs[st].d1, S.vline[st]);
+                __syncthreads();
+#pragma unroll
+                for (int st = 0; st < 3; ++st)
+                    if (jobs[st].d1 > jobs[st].d0) copy_stream(S, c, W, jobs[st]);
             }
             __syncthreads();
             rotate_head(S, n);
