@@ -444,6 +444,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         P.n_complete = w.scan.totals.records;
         P.id_fast = id_fast ? 1u : 0u;
         P.strip_flag = reinterpret_cast<uint32_t*>(p->err_word.as<uint8_t>() + 8);
+        { const char* dbg = getenv("BSQ_DEBUG_SKIP"); P.debug_skip = dbg ? (uint32_t)atoi(dbg) : 0u; }
         P.bases = p->err_word.as<unsigned long long>() + 2;
         P.rec_mod = (uint32_t)(w.rec_base % m);
         P.rec_div = w.rec_base / m;

@@ -61,6 +61,7 @@ struct ResolveParams {
     uint32_t id_fast;            // 1: ids are packed here on the assumption that none needs stripping;
                                  //    *strip_flag is raised if one does and the host redoes the ids
     uint32_t* strip_flag;
+    uint32_t debug_skip;         // measurement only (BSQ_DEBUG_SKIP env): 1 = no SoA copy, 2 = no line tables
     unsigned long long* bases;   // sum of the sequence lengths of the complete records (all windows)
     uint32_t rec_mod;            // rec_base % batch_size
     int64_t rec_div;             // rec_base / batch_size
@@ -638,6 +639,40 @@ __device__ __noinline__ void copy_stream(const TileSmem& S, const TileCursor& c,
     }
 }
 
+// Line-parallel copy (the common case: no line of the pass is long).  One thread owns one line and
+// streams it: every destination vector whose first byte lies in the line is assembled with one
+// unaligned 16-byte shared read and written with one 16-byte store; the vector in which the line
+// ends also takes the first bytes of the following line(s).  Far fewer instructions per byte than
+// the vector-parallel form (no per-vector line lookup), at the price of 16-byte stores that are
+// not coalesced across the warp (adjacent stores of a thread complete each 32-byte sector in L2).
+__device__ __forceinline__ void copy_line(const TileSmem& S, const TileCursor& c, const WinParams& W,
+                                          const StreamJob& J, uint32_t i) {
+    const uint32_t s0 = J.sdst[i], s1 = J.sdst[i + 1];
+    if (s1 == s0) return;                                            // empty line owns nothing
+    const uint32_t v0 = J.d0 >> 4;
+    uint32_t v = s0 == J.d0 ? v0 : (s0 + 15u) >> 4;                  // the line holding d0 owns vector v0
+    const uint32_t vend = (s1 + 15u) >> 4;
+    const uint32_t delta = J.ssrc[i] - s0;                           // source of destination byte d is d + delta
+    for (; v < vend; ++v) {
+        const uint32_t vs = v * 16u;
+        const uint32_t lo = vs < J.d0 ? J.d0 : vs;
+        const uint32_t hi = vs + 16u > J.d1 ? J.d1 : vs + 16u;
+        uint4 acc = load16(S, c, W, vs + delta);
+        if (s1 < hi) {                                               // the line ends inside this vector
+            uint32_t k = i, e = s1;
+            while (e < hi) {
+                ++k;
+                const uint32_t a = e - vs;
+                if (J.sdst[k + 1] != e) acc = splice16(acc, load16(S, c, W, J.ssrc[k] - a), a);
+                e = J.sdst[k + 1];
+            }
+        }
+        uint8_t* p = J.out + (size_t)v * 16u;
+        if (hi - lo == 16u) *reinterpret_cast<uint4*>(p) = acc;
+        else store_partial16(p, acc, lo - vs, hi - vs);
+    }
+}
+
 template <bool kAscii, bool kQual, bool kOffsets, bool kPack>
 __global__ void __launch_bounds__(kThreads, 2) k_resolve(const WinParams W, const ResolveParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -728,7 +763,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_resolve(const WinParams W, cons
             // every thread owns q consecutive list entries: [tid*q, tid*q + q)
             const uint32_t q = (n + kThreads - 1u) / kThreads;
             const uint32_t jb = tid * q, je = jb + q < n ? jb + q : n;
-            uint32_t v_id = 0, v_seq = 0, v_qual = 0;
+            uint32_t v_id = 0, v_seq = 0, v_qual = 0, max_len = 0;
             for (uint32_t j = jb; j < je; ++j) {
                 const uint32_t p = S.nlx[kHead + j];
                 const uint32_t q1 = S.nlx[kHead + j - 1];
@@ -736,6 +771,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_resolve(const WinParams W, cons
                 const uint32_t cls = r & 3u, k = r >> 2;
                 const bool live = k < P.n_complete;
                 const uint32_t len = p - q1 - 1u;
+                if (live && cls != 2u && len > max_len) max_len = len;
                 if (kOffsets) P.line_ends[1u + r] = p;
                 if (cls == 0u) {
                     // header line: '@' check (utils.mojo:454), id = line minus '@', stripped
@@ -819,13 +855,27 @@ __global__ void __launch_bounds__(kThreads, 2) k_resolve(const WinParams W, cons
                 jobs[0] = StreamJob{S.sdst[0], S.ssrc[0], S.vline[0], n_id, ra_id, do_id ? rb_id : ra_id, out_id, tb_id};
                 jobs[1] = StreamJob{S.sdst[1], S.ssrc[1], S.vline[1], n_seq, ra_seq, rb_seq, out_seq, tb_seq};
                 jobs[2] = StreamJob{S.sdst[2], S.ssrc[2], S.vline[2], n_qual, ra_qual, rb_qual, out_qual, tb_qual};
+                // long lines (long reads, or a line that began tiles ago) are copied vector-parallel;
+                // otherwise every thread streams whole lines
+                const bool long_lines = __syncthreads_or(max_len > 1024u) != 0;
+                if (long_lines) {
 #pragma unroll
-                for (int st = 0; st < 3; ++st)
-                    if (jobs[st].table) build_line_table(jobs[st].sdst, jobs[st].n_lines, jobs[st].d0, jobs[st].d1, S.vline[st]);
-                __syncthreads();
+                    for (int st = 0; st < 3; ++st)
+                        if (jobs[st].table) build_line_table(jobs[st].sdst, jobs[st].n_lines, jobs[st].d0, jobs[st].d1, S.vline[st]);
+                    __syncthreads();
 #pragma unroll
-                for (int st = 0; st < 3; ++st)
-                    if (jobs[st].d1 > jobs[st].d0) copy_stream(S, c, W, jobs[st]);
+                    for (int st = 0; st < 3; ++st)
+                        if (jobs[st].d1 > jobs[st].d0) copy_stream(S, c, W, jobs[st]);
+                } else if (!(P.debug_skip & 1u)) {
+                    // items: sequence lines, then quality lines, then ids (warps get lines of one kind)
+                    const uint32_t n1 = jobs[1].d1 > jobs[1].d0 ? n_seq : 0u, n2 = jobs[2].d1 > jobs[2].d0 ? n_qual : 0u,
+                                   n0 = jobs[0].d1 > jobs[0].d0 ? n_id : 0u;
+                    for (uint32_t w = tid; w < n1 + n2 + n0; w += kThreads) {
+                        if (w < n1) copy_line(S, c, W, jobs[1], w);
+                        else if (w < n1 + n2) copy_line(S, c, W, jobs[2], w - n1);
+                        else copy_line(S, c, W, jobs[0], w - n1 - n2);
+                    }
+                }
             }
             __syncthreads();
             rotate_head(S, n);
