@@ -401,8 +401,10 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         consumed_total = lw->region_off + (lw->scan.totals.consumed_end - lw->wp.begin);
         rem = lw->scan.totals.newlines & 3u;
         q2 = is_last && consumed_total < n && first_record + nrec == 0 && stream_offset == 0 && !cfg.buffer_growth_enabled;
+        // (the position sums exist only in pack passes; a wrapped id total means an empty header
+        //  line earlier in the window, i.e. an error before the tail -- nothing to append then)
         have_tail_candidate = is_last && !oversize && !q2 && consumed_total < n && rem == 3u &&
-                              (int64_t)lw->scan.totals.id_bytes_unstripped <= (int64_t)lw->wp.end;
+                              (!want_pack || (int64_t)lw->scan.totals.id_bytes_unstripped <= (int64_t)lw->wp.end);
     }
     uint32_t tail_seq = 0, tail_qual = 0, tail_id_max = 0;
     TailParams T{};

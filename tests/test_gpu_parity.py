@@ -207,7 +207,9 @@ def test_random_streams_multi_tile(U, B, oracle, mutate):
         gpu = B.GpuParser(val, val, B.parse_schema("generic"), 64, buffer_growth_enabled=True)
         for trial in range(6):
             data = _rand_stream(rng, int(rng.integers(1, 3000)), mutate)
-            U.check_stream(oracle, data, check_ascii=val, check_quality=val, batch_size=64, growth=True, gpu=gpu)
+            # views only / batches only / both: the passes differ (k_summarize<false> vs <true>)
+            U.check_stream(oracle, data, check_ascii=val, check_quality=val, batch_size=64, growth=True, gpu=gpu,
+                           want=(3, 1, 2)[trial % 3])
         gpu.close()
 
 
@@ -218,6 +220,8 @@ def test_tiny_and_degenerate_streams(U, oracle):
         for growth in (False, True):
             U.check_stream(oracle, data, batch_size=1, growth=growth)
             U.check_stream(oracle, data, check_ascii=True, check_quality=True, batch_size=2, growth=growth)
+            U.check_stream(oracle, data, batch_size=3, growth=growth, want=1)
+            U.check_stream(oracle, data, check_quality=True, batch_size=3, growth=growth, want=2)
 
 
 def test_all_newlines_overflows_the_tile_list(U, oracle):
@@ -435,3 +439,71 @@ def test_shard_summaries_locate_record_starts(B, oracle):
                 assert bounds[i] + st[i].skip_bytes == starts[first_own]
             assert st[i].newline_rank == int((data[:bounds[i]] == 10).sum())
     gpu.close()
+
+
+# ------------------------------------------------------------------ FastqParser streaming (several passes)
+
+
+@pytest.mark.parametrize("region_bytes", [700, 4096, 100000])
+@pytest.mark.parametrize("mutate", ["none", "crlf", "notail", "noise"])
+def test_fastq_parser_streams_in_regions(B, oracle, region_bytes, mutate):
+    """The host mirror reads the Reader in regions and carries the unconsumed tail (BufferedReader
+    semantics); records, order and the final error must not depend on the region size."""
+    rng = np.random.default_rng(region_bytes + len(mutate))
+    data = _rand_stream(rng, 400, mutate, maxlen=120)
+    cfg = oracle.config(True, True, "generic", buffer_growth_enabled=True)
+    views, bases, err = oracle.parse_all(data, cfg)
+    arr = np.frombuffer(data, np.uint8)
+    p = B.FastqParser(B.MemoryReader(data), config=B.ParserConfig(check_ascii=True, check_quality=True,
+                                                                  buffer_growth_enabled=True),
+                      region_bytes=region_bytes)
+    got = 0
+    with pytest.raises(B.BlazeSeqError) as ei:
+        while True:
+            v = p.next_view()
+            o = views[got]
+            assert v.id() == bytes(arr[o["id_start"]:o["id_start"] + o["id_len"]])
+            assert v.sequence() == bytes(arr[o["seq_start"]:o["seq_start"] + o["seq_len"]])
+            assert v.quality() == bytes(arr[o["qual_start"]:o["qual_start"] + o["qual_len"]])
+            got += 1
+    assert got == len(views)
+    assert str(ei.value) == err.text
+    assert (ei.value.record_number, ei.value.line_number, ei.value.file_position) == \
+        (err.record_number, err.line_number, err.file_position)
+
+
+@pytest.mark.parametrize("region_bytes", [5000, 1 << 30])
+def test_fastq_parser_batches_across_regions(B, oracle, region_bytes):
+    """batches(m) over a stream that needs several passes: every batch equals the oracle's FastqBatch."""
+    data = oracle.synth(3000, 20, 90, 2, 40, "sanger")
+    views, bases, err = oracle.parse_all(data)
+    for m in (64, 1000):
+        p = B.FastqParser(B.MemoryReader(data), batch_size=m, schema="sanger", region_bytes=region_bytes)
+        first = 0
+        for batch in p.batches():
+            n = len(batch)
+            oi, os_, oq, oie, oe = oracle.build_batch(data, views[first:first + n])
+            assert np.array_equal(batch._ends, oe) and np.array_equal(batch._id_ends, oie)
+            assert np.array_equal(batch._sequence_bytes, os_) and np.array_equal(batch._quality_bytes, oq)
+            assert np.array_equal(batch._id_bytes, oi)
+            assert n == min(m, len(views) - first)
+            first += n
+        assert first == len(views) and not p.has_more()
+
+
+def test_fastq_parser_file_and_gzip_readers(B, oracle, tmp_path):
+    import gzip
+    data = oracle.synth(2000, 50, 150, 2, 40, "illumina_1.8").tobytes()
+    (tmp_path / "a.fastq").write_bytes(data)
+    with gzip.open(tmp_path / "a.fastq.gz", "wb") as f:
+        f.write(data)
+    views, bases, err = oracle.parse_all(data)
+    for path in ("a.fastq", "a.fastq.gz"):
+        p = B.parser(str(tmp_path / path), "illumina_1.8")
+        n = nb = 0
+        for rec in p.records():
+            n += 1
+            nb += len(rec)
+        assert (n, nb) == (len(views), bases)     # the "<records> <base_pairs>" cross-check of the reference
+        p = B.parser(str(tmp_path / path), "illumina_1.8")
+        assert sum(len(b) for b in p.batches(512)) == len(views)
