@@ -138,9 +138,9 @@ void set_plain_error(bsq_error* e, int code, const char* text) {
     m.str(text);
 }
 
-size_t smem_bytes() { return sizeof(TileSmem) + 128; }                      // k_resolve: 2 CTAs / SM
-size_t smem_bytes_summarize() { return offsetof(TileSmem, bm_hi) + 128; }   // k_summarize: 3 CTAs / SM
-size_t smem_bytes_scan(uint32_t n_runs) { return (size_t)n_runs * (sizeof(BsqSummary) + sizeof(BsqPrefix)); }
+size_t smem_bytes() { return sizeof(TileSmem) + 128; }                      // k_resolve: kResolveCtas / SM
+size_t smem_bytes_summarize() { return offsetof(TileSmem, bm_hi) + 128; }   // k_summarize: kSummarizeCtas / SM
+size_t smem_bytes_scan(uint32_t n_runs) { return (size_t)n_runs * (sizeof(BsqSummary) + sizeof(BsqPrefix)) + kScanThreads * sizeof(BsqSummary); }
 
 template <typename K>
 cudaError_t opt_in_smem(K kernel, size_t bytes) {
@@ -158,8 +158,9 @@ void plan_window(bsq_parser* p, Window& w, const uint8_t* first_byte, uint64_t b
     w.wp.n_tiles = (w.wp.end + kTile - 1) / kTile;
     uint32_t tiles = w.wp.n_tiles - w.wp.first_tile;
     if (tiles == 0) tiles = 1, w.wp.n_tiles = w.wp.first_tile + 1;
-    // runs per window: a whole number of waves for both kernels (2 and 3 resident CTAs per SM)
-    uint32_t max_runs = (uint32_t)std::min<int>(6 * p->sm_count, kMaxRuns);
+    // runs per window: a whole number of waves for both kernels (kResolveCtas and kSummarizeCtas
+    // resident CTAs per SM): lcm(4, 6) = 12 per SM
+    uint32_t max_runs = (uint32_t)std::min<int>(12 * p->sm_count, kMaxRuns);
     uint32_t runs = std::min(tiles, max_runs);
     w.wp.tiles_per_run = (tiles + runs - 1) / runs;
     w.wp.n_runs = (tiles + w.wp.tiles_per_run - 1) / w.wp.tiles_per_run;
@@ -197,7 +198,7 @@ bsq_status summarize_window(bsq_parser* p, Window& w, bool sums) {
     CK(p->scan_out.ensure(sizeof(ScanOut)));
     if (sums) k_summarize<true><<<w.wp.n_runs, kThreads, smem_bytes_summarize(), p->stream>>>(w.wp, p->run_sum.as<BsqSummary>());
     else k_summarize<false><<<w.wp.n_runs, kThreads, smem_bytes_summarize(), p->stream>>>(w.wp, p->run_sum.as<BsqSummary>());
-    k_scan_runs<<<1, 256, smem_bytes_scan(w.wp.n_runs), p->stream>>>(p->run_sum.as<BsqSummary>(), w.wp.n_runs, w.wp.begin,
+    k_scan_runs<<<1, kScanThreads, smem_bytes_scan(w.wp.n_runs), p->stream>>>(p->run_sum.as<BsqSummary>(), w.wp.n_runs, w.wp.begin,
                                           w.run_pre.as<BsqPrefix>(), p->scan_out.as<ScanOut>());
     p->n_launches += 2;
     CK(cudaGetLastError());

@@ -23,19 +23,22 @@
 
 namespace bsq {
 
-constexpr int kTile = 32768;              // bytes per tile
-constexpr int kThreads = 256;             // threads per CTA (8 warps)
+constexpr int kTile = 16384;              // bytes per tile
+constexpr int kThreads = 128;             // threads per CTA (4 warps): small CTAs, many per SM, cheap barriers
 constexpr int kWarps = kThreads / 32;
-constexpr int kStages = 2;                // TMA ring depth per CTA (2 CTAs/SM -> 128 KiB in flight/SM)
-constexpr int kChunks = kTile / 16;       // 16-byte chunks per tile (2048)
+constexpr int kStages = 2;                // TMA ring depth per CTA (4 CTAs/SM -> 128 KiB in flight/SM)
+constexpr int kResolveCtas = 4;           // resident CTAs per SM, k_resolve (shared memory + registers)
+constexpr int kSummarizeCtas = 6;         // resident CTAs per SM, k_summarize
+constexpr int kChunks = kTile / 16;       // 16-byte chunks per tile (1024)
 constexpr int kChunksPerThread = kChunks / kThreads;  // 8
-constexpr int kWords = kTile / 32;        // bitmap words per tile (1024)
+constexpr int kWords = kTile / 32;        // bitmap words per tile (512)
 constexpr int kWordsPerThread = kWords / kThreads;    // 4 -> a thread ranks 128 contiguous bytes
-constexpr int kNlCap = 2048;              // newline-list capacity per pass over a tile
+constexpr int kNlCap = 1024;              // newline-list capacity per pass over a tile
 constexpr int kHead = 4;                  // carried newline positions in front of the list
 constexpr int kLinesCap = kNlCap / 4 + 3; // lines of one class per pass (+ two sentinels)
-constexpr int kVecCap = 2112;             // destination vectors of one class per pass with a line table
 constexpr int kTilePad = 32;              // readable slack after a tile for unaligned 16-byte loads
+constexpr int kHalo = 1024;               // bytes before the tile kept in shared memory too: a line that began
+                                          // up to kHalo bytes before the tile is still read from shared memory
 constexpr int kMaxWindows = 64;
 
 static_assert(kThreads % 4 == 0 && kWordsPerThread == 4 && kChunksPerThread * kThreads == kChunks, "");
@@ -131,21 +134,20 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
 
 struct alignas(128) TileSmem {
     // ---- used by both kernels (k_summarize allocates only up to bm_hi) ----
-    uint8_t data[kStages][kTile + kTilePad];  // TMA destinations
-    uint64_t full_bar[kStages];
+    alignas(128) uint8_t data[kStages][kHalo + kTile + kTilePad];  // TMA destinations: [halo | tile | pad]
+    alignas(8) uint64_t full_bar[kStages];
     uint32_t warp_tot[2][kWarps][4];          // block scans, double buffered: one barrier per scan
     uint32_t carry[8];
     uint32_t k1_head[8];                      // k_summarize: [0..3] last four newlines, [4..7] first four
     uint32_t k1_red[kWarps * 4];
-    uint32_t bm_nl[kWords];                   // 1 bit per byte: '\n'
+    alignas(16) uint32_t bm_nl[kWords];       // 1 bit per byte: '\n'
     // ---- k_resolve only ----
-    uint32_t bm_hi[kWords];                   // 1 bit per byte: bit 7 set
-    uint32_t bm_bad[kWords];                  // 1 bit per byte: outside [lower, upper]
+    alignas(16) uint32_t bm_hi[kWords];       // 1 bit per byte: bit 7 set
+    alignas(16) uint32_t bm_bad[kWords];      // 1 bit per byte: outside [lower, upper]
     uint32_t nlx[kHead + kNlCap];             // nlx[kHead + j] = position of local newline j;
                                               // nlx[kHead-1-i] = i-th newline before the list
     uint32_t sdst[3][kLinesCap];              // per class stream: destination of each line
     uint32_t ssrc[3][kLinesCap];              //                   source position of each line
-    uint16_t vline[3][kVecCap];               // line that holds the first byte of each destination vector
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -166,10 +168,14 @@ __device__ __forceinline__ uint32_t tile_bytes_rounded(const WinParams& W, uint3
     return (n + 15u) & ~15u;  // stays inside the 16-byte granule that holds the last valid byte
 }
 
+template <bool kWithHalo>
 __device__ __forceinline__ void issue_tile_load(TileSmem& S, const WinParams& W, uint32_t tile, uint32_t stage) {
     const uint32_t bytes = tile_bytes_rounded(W, tile);
-    mbar_expect_tx(&S.full_bar[stage], bytes);
-    tma_load_1d(S.data[stage], W.base + (size_t)tile * kTile, bytes, &S.full_bar[stage]);
+    const size_t origin = (size_t)tile * kTile;
+    // the halo is the end of the previous tile (an L2 hit: this CTA or its neighbour just read it)
+    const uint32_t halo = (kWithHalo && origin >= (size_t)kHalo) ? (uint32_t)kHalo : 0u;
+    mbar_expect_tx(&S.full_bar[stage], bytes + halo);
+    tma_load_1d(S.data[stage] + (kHalo - halo), W.base + origin - halo, bytes + halo, &S.full_bar[stage]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -187,7 +193,7 @@ __device__ __forceinline__ uint32_t mask16(uint32_t f0, uint32_t f1, uint32_t f2
 
 template <bool kHi, bool kBad>
 __device__ __forceinline__ void build_bitmaps(TileSmem& S, const TileCursor& c, uint32_t addlo, uint32_t addup) {
-    const uint8_t* tile = S.data[c.stage];
+    const uint8_t* tile = S.data[c.stage] + kHalo;
     const uint32_t tid = threadIdx.x;
     const uint32_t vlo = c.lo - c.origin, vhi = c.hi - c.origin;  // valid offsets in the tile
 #pragma unroll
@@ -330,8 +336,8 @@ __device__ __forceinline__ void rotate_head(TileSmem& S, uint32_t n) {
 // byte of the window at offset pos: shared memory when the current tile holds it
 __device__ __forceinline__ uint32_t byte_at(const TileSmem& S, const TileCursor& c, const WinParams& W,
                                             uint32_t pos) {
-    const uint32_t rel = pos - c.origin;  // wraps to a large value for pos < origin
-    if (rel < (uint32_t)kTile) return S.data[c.stage][rel];
+    const uint32_t rel = pos - c.origin + (uint32_t)kHalo;   // offset in data[stage]; wraps for pos far before
+    if (rel < (uint32_t)(kHalo + kTile) && pos + (uint32_t)kHalo >= c.origin) return S.data[c.stage][rel];
     return __ldg(W.base + pos);
 }
 
@@ -361,7 +367,7 @@ __device__ __forceinline__ TileCursor make_cursor(const WinParams& W, uint32_t t
 // run are needed; the per-class position sums that give the SoA destinations are skipped.
 // Shared memory: the part of TileSmem before bm_hi (three CTAs per SM).
 template <bool kSums>
-__global__ void __launch_bounds__(kThreads, 3) k_summarize(const WinParams W, BsqSummary* __restrict__ run_sum) {
+__global__ void __launch_bounds__(kThreads, kSummarizeCtas) k_summarize(const WinParams W, BsqSummary* __restrict__ run_sum) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x;
@@ -375,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_summarize(const WinParams W, Bs
     if (tid < 8) S.k1_head[tid] = 0;
     __syncthreads();
     if (tid == 0)
-        for (uint32_t s = 0; s < (uint32_t)kStages && ta + s < tb; ++s) issue_tile_load(S, W, ta + s, s);
+        for (uint32_t s = 0; s < (uint32_t)kStages && ta + s < tb; ++s) issue_tile_load<false>(S, W, ta + s, s);
 
     uint32_t run_count = 0;           // newlines of the run so far (uniform)
     uint32_t acc[4] = {0, 0, 0, 0};   // position sums by (index in run) mod 4, this thread's share
@@ -418,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_summarize(const WinParams W, Bs
         }
         run_count += total;
         __syncthreads();  // every thread is done with data[stage] and the head is updated
-        if (tid == 0 && t + kStages < tb) issue_tile_load(S, W, t + kStages, c.stage);
+        if (tid == 0 && t + kStages < tb) issue_tile_load<false>(S, W, t + kStages, c.stage);
     }
 
     // block reduction of acc[4]
@@ -446,33 +452,53 @@ __global__ void __launch_bounds__(kThreads, 3) k_summarize(const WinParams W, Bs
 // k_scan_runs: one CTA; n_runs is a few hundred
 // ------------------------------------------------------------------------------------------------
 
-constexpr int kMaxRuns = 1024;
+constexpr int kMaxRuns = 2048;
+constexpr int kScanThreads = 256;
 
-// dynamic shared memory: n_runs * (sizeof(BsqSummary) + sizeof(BsqPrefix))
-__global__ void __launch_bounds__(256, 1) k_scan_runs(const BsqSummary* __restrict__ run_sum, uint32_t n_runs,
-                                                      uint32_t begin, BsqPrefix* __restrict__ run_pre,
-                                                      ScanOut* __restrict__ out) {
+// dynamic shared memory: n_runs * (sizeof(BsqSummary) + sizeof(BsqPrefix)) + kScanThreads * sizeof(BsqSummary).
+// Every thread folds a contiguous group of runs, one thread scans the kScanThreads group totals, then
+// every thread walks its group again to emit the prefixes.
+__global__ void __launch_bounds__(kScanThreads, 1) k_scan_runs(const BsqSummary* __restrict__ run_sum, uint32_t n_runs,
+                                                               uint32_t begin, BsqPrefix* __restrict__ run_pre,
+                                                               ScanOut* __restrict__ out) {
     extern __shared__ __align__(128) uint8_t scan_raw[];
     BsqSummary* s_sum = reinterpret_cast<BsqSummary*>(scan_raw);
-    BsqPrefix* s_pre = reinterpret_cast<BsqPrefix*>(scan_raw + (size_t)n_runs * sizeof(BsqSummary));
-    // stage the summaries with all threads (16-byte pieces), scan with one, write back with all
+    BsqSummary* s_grp = s_sum + n_runs;                      // exclusive state of each thread's group
+    BsqPrefix* s_pre = reinterpret_cast<BsqPrefix*>(s_grp + kScanThreads);
     {
         const uint4* src = reinterpret_cast<const uint4*>(run_sum);
         uint4* dst = reinterpret_cast<uint4*>(s_sum);
         for (uint32_t i = threadIdx.x; i < n_runs * 4u; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
+    const uint32_t per = (n_runs + kScanThreads - 1u) / kScanThreads;
+    const uint32_t r0 = threadIdx.x * per, r1 = r0 + per < n_runs ? r0 + per : n_runs;
+    {
+        BsqSummary g = bsq_summary_identity();
+        for (uint32_t r = r0; r < r1; ++r) g = bsq_combine(g, s_sum[r]);
+        s_grp[threadIdx.x] = g;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         BsqSummary E = bsq_summary_window_init(begin);
         BsqSummary R = bsq_summary_identity();
-        for (uint32_t r = 0; r < n_runs; ++r) {
-            s_pre[r] = bsq_prefix_from(E, begin);
-            E = bsq_combine(E, s_sum[r]);
-            R = bsq_combine(R, s_sum[r]);
+        for (uint32_t t = 0; t < (uint32_t)kScanThreads; ++t) {
+            const BsqSummary g = s_grp[t];
+            s_grp[t] = E;
+            E = bsq_combine(E, g);
+            R = bsq_combine(R, g);
         }
         out->totals = bsq_totals_from(E, begin);
         out->end_state = E;
         out->region = R;
+    }
+    __syncthreads();
+    {
+        BsqSummary E = s_grp[threadIdx.x];
+        for (uint32_t r = r0; r < r1; ++r) {
+            s_pre[r] = bsq_prefix_from(E, begin);
+            E = bsq_combine(E, s_sum[r]);
+        }
     }
     __syncthreads();
     {
@@ -496,14 +522,14 @@ __device__ __forceinline__ void report(const ResolveParams& P, uint32_t k, uint3
 // read from shared memory (two aligned 16-byte loads + funnel shifts); bytes of a line that began
 // in an earlier tile come from global memory (L2), word by word, guarded to the window.
 __device__ __forceinline__ uint4 load16(const TileSmem& S, const TileCursor& c, const WinParams& W, uint32_t pos) {
-    const uint32_t rel = pos - c.origin;
+    const uint32_t rel = pos - c.origin + (uint32_t)kHalo;   // offset in data[stage] = [halo | tile | pad]
     const uint32_t sh = (pos & 3u) * 8u;
-    const bool in_tile = rel < (uint32_t)kTile;
-    // five consecutive words (the tile is padded): 4-way bank conflicts, but no selects.  The read is
-    // unconditional (address clamped into the tile) so that the common path has no branch.
+    const bool in_tile = rel < (uint32_t)(kHalo + kTile) && (c.origin >= (uint32_t)kHalo || rel >= (uint32_t)kHalo - 16u);
+    // five consecutive words: bank conflicts, but no selects.  The read is unconditional (address
+    // clamped into the buffer) so that the common path has no branch.
     const uint32_t* t32 = reinterpret_cast<const uint32_t*>(S.data[c.stage]) + (in_tile ? (rel >> 2) : 0u);
     uint32_t w0 = t32[0], w1 = t32[1], w2 = t32[2], w3 = t32[3], w4 = t32[4];
-    if (!in_tile) {   // the line began in an earlier tile: global memory (L2), guarded to the window
+    if (!in_tile) {   // the line began more than kHalo before the tile: global memory (L2), guarded to the window
         const uint32_t* g = reinterpret_cast<const uint32_t*>(W.base);
         const uint32_t wi = pos >> 2;                       // garbage when pos wrapped: guarded
         const uint32_t wend = (W.end + 3u) >> 2;            // words that hold window bytes
@@ -554,30 +580,9 @@ __device__ __forceinline__ void store_partial16(uint8_t* p, uint4 v, uint32_t a,
     }
 }
 
-// Line table of one class stream: vline[u] = line that holds the first byte of destination vector
-// v0 + u.  One thread per line; every vector is written exactly once.  Requires (v1 - v0) <= kVecCap.
-__device__ __forceinline__ void build_line_table(const uint32_t* __restrict__ sdst, uint32_t n_lines, uint32_t d0,
-                                                 uint32_t d1, uint16_t* __restrict__ vline) {
-    if (d1 <= d0) return;
-    const uint32_t v0 = d0 >> 4;
-    for (uint32_t i = threadIdx.x; i < n_lines; i += kThreads) {
-        const uint32_t s0 = sdst[i], s1 = sdst[i + 1];
-        if (s1 == s0) continue;                                  // empty line: owns no byte
-        uint32_t lo = s0 == d0 ? v0 : (s0 + 15u) >> 4;           // the line holding d0 owns vector v0
-        const uint32_t hi = (s1 + 15u) >> 4;
-        for (uint32_t v = lo; v < hi; ++v) vline[v - v0] = (uint16_t)i;
-    }
-}
-
-// Copies the lines of one class stream that ended in this pass: destination range [d0, d1) of the
-// stream (virtual offsets: `out` is 16-byte aligned and d includes the sub-16 shift).  One 16-byte
-// destination vector per thread and step.  Source of destination byte d inside line i is
-// d + (ssrc[i] - sdst[i]), so a vector is two unaligned 16-byte reads (its first line and the next
-// one) spliced at the line boundary, and one aligned 16-byte store; a third line inside the same
-// vector (ids, very short reads) takes the loop.
 struct StreamJob {
-    const uint32_t* sdst; const uint32_t* ssrc; const uint16_t* vline;
-    uint32_t n_lines, d0, d1; uint8_t* out; bool table;
+    const uint32_t* sdst; const uint32_t* ssrc;
+    uint32_t n_lines, d0, d1; uint8_t* out;
 };
 
 // the 16 bytes of destination vector v of a stream (byte k <-> destination 16 v + k)
@@ -585,9 +590,7 @@ __device__ __forceinline__ uint4 assemble_vector(const TileSmem& S, const TileCu
                                                  const StreamJob& J, uint32_t v, uint32_t lo, uint32_t hi) {
     const uint32_t vs = v * 16u;
     uint32_t i;
-    if (J.table) {
-        i = J.vline[v - (J.d0 >> 4)];
-    } else {                                   // more vectors than the table holds (long reads): bisect
+    {                                          // line that holds the first byte of the vector: bisect
         uint32_t a = 0, b = J.n_lines;
         while (b - a > 1u) {
             const uint32_t m = (a + b) >> 1;
@@ -674,7 +677,7 @@ __device__ __forceinline__ void copy_line(const TileSmem& S, const TileCursor& c
 }
 
 template <bool kAscii, bool kQual, bool kOffsets, bool kPack>
-__global__ void __launch_bounds__(kThreads, 2) k_resolve(const WinParams W, const ResolveParams P) {
+__global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinParams W, const ResolveParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x;
@@ -689,7 +692,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_resolve(const WinParams W, cons
     }
     __syncthreads();
     if (tid == 0)
-        for (uint32_t s = 0; s < (uint32_t)kStages && ta + s < tb; ++s) issue_tile_load(S, W, ta + s, s);
+        for (uint32_t s = 0; s < (uint32_t)kStages && ta + s < tb; ++s) issue_tile_load<true>(S, W, ta + s, s);
     if (kOffsets && blockIdx.x == 0 && tid == 0) P.line_ends[0] = W.begin - 1u;
 
     const uint32_t addlo = (128u - P.lower) * 0x01010101u, addup = (127u - P.upper) * 0x01010101u;
@@ -848,21 +851,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_resolve(const WinParams W, cons
                 const bool do_id = P.id_fast && rb_id > ra_id && (int64_t)rb_id <= P.id_cap - (P.id_base64 - sh_id) && n_id != 0u;
                 const uint32_t ra_seq = d0_seq + sh_seq, rb_seq = cum_seq + sh_seq;
                 const uint32_t ra_qual = d0_qual + sh_qual, rb_qual = cum_qual + sh_qual;
-                const bool tb_id = ((rb_id + 15u) >> 4) - (ra_id >> 4) <= (uint32_t)kVecCap;
-                const bool tb_seq = ((rb_seq + 15u) >> 4) - (ra_seq >> 4) <= (uint32_t)kVecCap;
-                const bool tb_qual = ((rb_qual + 15u) >> 4) - (ra_qual >> 4) <= (uint32_t)kVecCap;
                 StreamJob jobs[3];
-                jobs[0] = StreamJob{S.sdst[0], S.ssrc[0], S.vline[0], n_id, ra_id, do_id ? rb_id : ra_id, out_id, tb_id};
-                jobs[1] = StreamJob{S.sdst[1], S.ssrc[1], S.vline[1], n_seq, ra_seq, rb_seq, out_seq, tb_seq};
-                jobs[2] = StreamJob{S.sdst[2], S.ssrc[2], S.vline[2], n_qual, ra_qual, rb_qual, out_qual, tb_qual};
-                // long lines (long reads, or a line that began tiles ago) are copied vector-parallel;
-                // otherwise every thread streams whole lines
-                const bool long_lines = __syncthreads_or(max_len > 1024u) != 0;
+                jobs[0] = StreamJob{S.sdst[0], S.ssrc[0], n_id, ra_id, do_id ? rb_id : ra_id, out_id};
+                jobs[1] = StreamJob{S.sdst[1], S.ssrc[1], n_seq, ra_seq, rb_seq, out_seq};
+                jobs[2] = StreamJob{S.sdst[2], S.ssrc[2], n_qual, ra_qual, rb_qual, out_qual};
+                // long lines (long reads, or a line that began far before the tile) are copied
+                // vector-parallel; otherwise every thread streams whole lines
+                const bool long_lines = __syncthreads_or(max_len > (uint32_t)kHalo - 64u) != 0;
                 if (long_lines) {
-#pragma unroll
-                    for (int st = 0; st < 3; ++st)
-                        if (jobs[st].table) build_line_table(jobs[st].sdst, jobs[st].n_lines, jobs[st].d0, jobs[st].d1, S.vline[st]);
-                    __syncthreads();
 #pragma unroll
                     for (int st = 0; st < 3; ++st)
                         if (jobs[st].d1 > jobs[st].d0) copy_stream(S, c, W, jobs[st]);
@@ -883,7 +879,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_resolve(const WinParams W, cons
         }
         rank += total;
         if (total == 0u) __syncthreads();   // (the pass loop ends with a barrier otherwise)
-        if (tid == 0 && t + kStages < tb) issue_tile_load(S, W, t + kStages, c.stage);
+        if (tid == 0 && t + kStages < tb) issue_tile_load<true>(S, W, t + kStages, c.stage);
     }
     // one atomic per warp: the run's share of the base count
     unsigned long long b64 = bases_acc;

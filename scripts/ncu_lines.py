@@ -42,7 +42,7 @@ for blk in blocks[1:]:
     tot = sum(x[2] for x in rows) or 1
     tots = sum(x[4] for x in rows) or 1
     print(name, "total warp inst", tot, "samples", tots)
-    for ln, src, inst, tinst, smp in sorted(rows, key=lambda x: -x[2])[:top]:
+    for ln, src, inst, tinst, smp in sorted(rows, key=lambda x: -(x[4] if len(sys.argv) > 4 else x[2]))[:top]:
         print(f"{ln:5d} {100 * inst / tot:5.1f}% inst  {100 * smp / tots:5.1f}% smp  thr/inst {tinst / max(inst, 1):5.1f}  {src.strip()[:110]}")
     # stall reason totals for the kernel (sampled, all samples)
     names = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]

@@ -20,12 +20,13 @@ agg = {}
 tot = 0
 for r in rd:
     if len(r) < len(hdr) or not r[0]: continue
-    try: ln = int(r[0]); inst = int(r[ci["Instructions Executed"]]); ti = int(r[ci["Thread Instructions Executed"]])
+    try: ln = int(r[0]); inst = int(r[ci["Instructions Executed"]]); ti = int(r[ci["Thread Instructions Executed"]]); smp = int(r[ci["# Samples"]])
     except ValueError: continue
     fn = "?"
     for s, n in marks:
         if s <= ln: fn = n
-    a = agg.setdefault(fn, [0, 0]); a[0] += inst; a[1] += ti; tot += inst
-for fn, (inst, ti) in sorted(agg.items(), key=lambda x: -x[1][0]):
-    print(f"{fn:28s} {100*inst/tot:5.1f}%  thr/inst {ti/max(inst,1):5.1f}")
+    a = agg.setdefault(fn, [0, 0, 0]); a[0] += inst; a[1] += ti; a[2] += smp; tot += inst
+tots = sum(a[2] for a in agg.values()) or 1
+for fn, (inst, ti, smp) in sorted(agg.items(), key=lambda x: -x[1][2]):
+    print(f"{fn:28s} inst {100*inst/tot:5.1f}%  time(samples) {100*smp/tots:5.1f}%  thr/inst {ti/max(inst,1):5.1f}")
 print("total warp inst", tot)
