@@ -203,14 +203,16 @@ def main():
         assert r.n_records == M and r.stop.code == capi.EOF, (r.n_records, r.stop.text)
         return r
 
+    # nvidia-smi needs ~100 ms to start: launch it before the warm-up so that it is sampling (every
+    # 100 ms) while the timed steps run; warm-up samples are under the same load
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         res = step()
     assert res.n_bases == M * 150
 
     # ---- timed region ------------------------------------------------------------------------------
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     ms_sum = [0.0] * 5
     launches = 0
     t0 = time.perf_counter()
