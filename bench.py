@@ -55,7 +55,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -244,7 +244,10 @@ def main():
     achieved = algo * M / (resolve_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_resolve_bytes_per_launch")
+        # measured DRAM bytes per record of k_resolve (one ncu --set full capture, profiles/traffic.json),
+        # scaled to the records one launch of this run processes
+        per_rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_resolve_bytes_per_record"]
+        traffic = per_rec * M / n_windows if args.mode == "batches" and not args.validate else None
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "k_resolve", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -479,18 +479,36 @@ __global__ void __launch_bounds__(kScanThreads, 1) k_scan_runs(const BsqSummary*
         s_grp[threadIdx.x] = g;
     }
     __syncthreads();
+    // three-level scan of the kScanThreads group totals: 16 leaders fold 16 groups each, thread 0
+    // scans the 16 leader totals, the leaders then turn their groups into exclusive states
+    __shared__ BsqSummary s_blk[kScanThreads / 16];
+    if ((threadIdx.x & 15u) == 0u) {
+        BsqSummary b = bsq_summary_identity();
+        for (uint32_t t = threadIdx.x; t < threadIdx.x + 16u; ++t) b = bsq_combine(b, s_grp[t]);
+        s_blk[threadIdx.x >> 4] = b;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         BsqSummary E = bsq_summary_window_init(begin);
         BsqSummary R = bsq_summary_identity();
-        for (uint32_t t = 0; t < (uint32_t)kScanThreads; ++t) {
-            const BsqSummary g = s_grp[t];
-            s_grp[t] = E;
-            E = bsq_combine(E, g);
-            R = bsq_combine(R, g);
+        for (uint32_t k = 0; k < (uint32_t)kScanThreads / 16u; ++k) {
+            const BsqSummary b = s_blk[k];
+            s_blk[k] = E;
+            E = bsq_combine(E, b);
+            R = bsq_combine(R, b);
         }
         out->totals = bsq_totals_from(E, begin);
         out->end_state = E;
         out->region = R;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 15u) == 0u) {
+        BsqSummary E = s_blk[threadIdx.x >> 4];
+        for (uint32_t t = threadIdx.x; t < threadIdx.x + 16u; ++t) {
+            const BsqSummary g = s_grp[t];
+            s_grp[t] = E;
+            E = bsq_combine(E, g);
+        }
     }
     __syncthreads();
     {
