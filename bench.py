@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--cpu-sample-gib", type=float, default=1.0)
     ap.add_argument("--mode", default="batches", choices=["batches", "views"])
     ap.add_argument("--validate", action="store_true", help="configs[2]: check_ascii + check_quality, sanger")
+    ap.add_argument("--mixed", action="store_true", help="configs[3]: mixed read length 75-300 bp instead of 150 bp")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -187,19 +188,35 @@ def main():
 
     # ---- input: this rank's shard of an (N * M)-record stream, generated on the device --------
     schema = B.parse_schema("sanger" if args.validate else "illumina_1.8")
-    M = capi.lib().bsq_compute_num_reads_for_size(int(args.gib * GIB), 150, 150)
+    mn, mx = (75, 300) if args.mixed else (150, 150)
+    M = capi.lib().bsq_compute_num_reads_for_size(int(args.gib * GIB), mn, mx)
     total_reads = M * world
     digits = len(str(total_reads - 1))
-    rec_bytes = 6 + digits + 1 + 2 * 150 + 4
-    size = M * rec_bytes
     gpu = B.GpuParser(args.validate, args.validate, schema, 4096, device_id=local)
+    # byte range of this rank's records inside the (world * M)-record stream (utils.mojo:753-768:
+    # len_i = mn + (31 i + 7) % (mx - mn + 1), header "@read_<i zero padded to `digits`>\n")
+    L = capi.lib()
+    period = mx - mn + 1
+    pref = [0]
+    for j in range(period):
+        pref.append(pref[-1] + (31 * j + 7) % period)
+
+    def stream_offset(i):
+        lens = i * mn + (i // period) * pref[period] + pref[i % period]
+        return i * (6 + digits + 1 + 4) + 2 * lens
+    lo_off, hi_off = stream_offset(rank * M), stream_offset((rank + 1) * M)
+    size = hi_off - lo_off
+    rec_bytes = size / M                       # average bytes per record
+    bases_expected = (size - M * (6 + digits + 1 + 4)) // 2
     buf = torch.empty(size + 256, dtype=torch.uint8, device=dev)
-    assert gpu.synth_device(buf.data_ptr(), size, total_reads, rank * M, M, 150, 150, 2, 40, schema) == size
+    assert gpu.synth_device(buf.data_ptr(), size, total_reads, rank * M, M, mn, mx, 2, 40, schema) == size
     want = capi.WANT_BATCHES if args.mode == "batches" else capi.WANT_OFFSETS
-    algo = (ALGO_BYTES_BATCHES if args.mode == "batches" else ALGO_BYTES_VIEWS) + (rec_bytes - 319)
+    # algorithmic bytes per record: R read + (2L + I + 16) written, or R + 20 for views
+    id_len = 5 + digits
+    algo = rec_bytes + (2 * (bases_expected / M) + id_len + 16 if args.mode == "batches" else 20)
 
     def step():
-        r = gpu.parse_device(buf.data_ptr(), size, rank * size, rank * M, True, want)
+        r = gpu.parse_device(buf.data_ptr(), size, lo_off, rank * M, True, want)
         assert r.n_records == M and r.stop.code == capi.EOF, (r.n_records, r.stop.text)
         return r
 
@@ -209,7 +226,7 @@ def main():
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         res = step()
-    assert res.n_bases == M * 150
+    assert res.n_bases == bases_expected
 
     # ---- timed region ------------------------------------------------------------------------------
     barrier()
@@ -230,9 +247,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     wall_max, dev_ms_max, launches = float(t[0]), float(t[1]), int(t[2])
     # the one collective of the path: total reads / bases
-    reads, bases = M, M * 150
+    reads, bases = M, bases_expected
     if dist is not None:
-        reads, bases = sharding.allreduce_counts(dist, M, M * 150, device=dev)
+        reads, bases = sharding.allreduce_counts(dist, M, bases_expected, device=dev)
     assert reads == total_reads
     ms_per_step = wall_max / args.steps * 1e3
     value = total_reads / (wall_max / args.steps)
@@ -267,12 +284,12 @@ def main():
             host = torch.empty(size, dtype=torch.uint8)
         host.copy_(buf[:size])
         harr = host.numpy()
-        r = gpu.parse_host(harr, rank * size, rank * M, True, want)   # warm: allocates the device staging copy
+        r = gpu.parse_host(harr, lo_off, rank * M, True, want)   # warm: allocates the device staging copy
         assert r.n_records == M
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            r = gpu.parse_host(harr, rank * size, rank * M, True, want)
+            r = gpu.parse_host(harr, lo_off, rank * M, True, want)
             assert r.n_records == M and r.stop.code == capi.EOF
         barrier()
         dt = (time.perf_counter() - t0) / args.e2e_steps
@@ -291,8 +308,9 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_py as O
         cores = os.cpu_count() or 1
-        sample_reads = min(M, int(args.cpu_sample_gib * GIB) // rec_bytes)
-        sample = buf[:sample_reads * rec_bytes].cpu().numpy()
+        sample_reads = min(M, int(args.cpu_sample_gib * GIB / rec_bytes))
+        sample_bytes = stream_offset(rank * M + sample_reads) - lo_off
+        sample = buf[:sample_bytes].cpu().numpy()
         cfg = O.config(args.validate, args.validate, "sanger" if args.validate else "illumina_1.8")
         mode = 1 if args.mode == "batches" else 0
 
@@ -317,7 +335,8 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "parsed_gb_per_s": size * world / (wall_max / args.steps) / 1e9,
-            "config": {"workload": ("configs[2]: 10 GiB 150 bp FASTQ, check_ascii+check_quality, sanger" if args.validate
+            "config": {"workload": ("configs[3]: 10 GiB mixed read-length (75-300 bp) FASTQ, validation OFF" if args.mixed
+                                    else "configs[2]: 10 GiB 150 bp FASTQ, check_ascii+check_quality, sanger" if args.validate
                                     else "configs[1]: 10 GiB in-memory 150 bp Illumina FASTQ, illumina_1.8, validation OFF")
                        + f", {args.mode}(4096), per GPU", "reads_per_gpu": M, "bytes_per_gpu": size,
                        "record_bytes": rec_bytes, "l2": "input (>=10 GB) is larger than L2; no flush needed",
