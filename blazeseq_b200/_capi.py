@@ -23,7 +23,8 @@ SYMBOLS = [
     "bsq_last_error_text", "bsq_set_batch_size", "bsq_parse_device", "bsq_parse_host", "bsq_get_offsets", "bsq_get_batch",
     "bsq_get_soa", "bsq_batch_to_host", "bsq_offsets_to_host", "bsq_pass_device_input",
     "bsq_last_timing", "bsq_compute_num_reads_for_size", "bsq_synth_size", "bsq_synth_device",
-    "bsq_summarize_device", "bsq_shard_prefix",
+    "bsq_summarize_device", "bsq_shard_prefix", "bsq_stream_open", "bsq_stream_next", "bsq_stream_region",
+    "bsq_stream_get_stats", "bsq_stream_close",
 ]
 
 
@@ -80,6 +81,14 @@ class Summary(C.Structure):
         return int(self.w[0])
 
 
+class StreamStats(C.Structure):
+    _fields_ = [("bytes_read", C.c_uint64), ("regions", C.c_uint64), ("reader_busy_s", C.c_double),
+                ("parse_s", C.c_double), ("wait_reader_s", C.c_double)]
+
+
+SOURCE_PLAIN, SOURCE_GZIP, SOURCE_AUTO = 0, 1, 2
+
+
 class ShardStart(C.Structure):
     _fields_ = [("newline_rank", C.c_int64), ("first_record", C.c_int64), ("skip_bytes", C.c_int64),
                 ("phase", C.c_int32), ("_pad", C.c_int32)]
@@ -128,7 +137,14 @@ def lib():
     L.bsq_synth_device.argtypes = [vp, vp, u64] + [i64] * 7 + [u8] * 3 + [C.POINTER(u64)]
     L.bsq_summarize_device.argtypes = [vp, vp, u64, C.POINTER(Summary)]
     L.bsq_shard_prefix.argtypes = [C.POINTER(Summary), C.POINTER(u64), i32, C.POINTER(ShardStart)]
-    for name in ("bsq_create", "bsq_get_offsets", "bsq_get_batch", "bsq_get_soa", "bsq_batch_to_host",
+    L.bsq_stream_open.argtypes = [vp, C.c_char_p, i32, u64, C.POINTER(vp)]
+    L.bsq_stream_next.argtypes = [vp, u32, C.POINTER(PassResult)]
+    L.bsq_stream_region.argtypes = [vp, C.POINTER(u64), C.POINTER(i64), C.POINTER(i64)]
+    L.bsq_stream_region.restype = vp
+    L.bsq_stream_get_stats.argtypes = [vp, C.POINTER(StreamStats)]
+    L.bsq_stream_close.argtypes = [vp]
+    L.bsq_stream_close.restype = None
+    for name in ("bsq_stream_open", "bsq_stream_next", "bsq_stream_get_stats", "bsq_create", "bsq_get_offsets", "bsq_get_batch", "bsq_get_soa", "bsq_batch_to_host",
                  "bsq_offsets_to_host", "bsq_last_timing", "bsq_synth_device", "bsq_summarize_device",
                  "bsq_shard_prefix"):
         getattr(L, name).restype = i32

@@ -5,8 +5,14 @@
 #include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 
+#include <zlib.h>
+
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <cstdarg>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -758,6 +764,202 @@ extern "C" bsq_status bsq_parse_host(bsq_parser* p, const uint8_t* host_bytes, u
     feed.ahead = window;
     bsq_status st = run_pass(p, feed.d, n, stream_offset, first_record, is_last, want, window, feed, out);
     return st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming from a file: reader thread -> pinned regions -> passes
+// ------------------------------------------------------------------------------------------------
+
+struct bsq_stream {
+    bsq_parser* p = nullptr;
+    int kind = BSQ_SOURCE_PLAIN;
+    FILE* fp = nullptr;
+    gzFile gz = nullptr;
+    uint64_t region_bytes = 0, carry_cap = 0;
+    struct Buf { uint8_t* mem = nullptr; uint64_t n_new = 0; bool eof = false; int state = 0; /* 0 free, 1 ready, 2 in use */ };
+    Buf buf[2];
+    std::thread reader;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool stop = false, read_error = false;
+    int next_fill = 0, next_take = 0;
+    // caller side
+    int cur = -1;                    // buffer of the region last parsed
+    const uint8_t* region_ptr = nullptr;
+    uint64_t region_n = 0;
+    std::vector<uint8_t> carry;      // unconsumed tail of the previous region
+    int64_t stream_pos = 0;          // stream offset of carry[0]
+    int64_t records_done = 0;
+    bool finished = false;
+    bsq_stream_stats st{};
+
+    void reader_main() {
+        for (;;) {
+            Buf* b;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || buf[next_fill].state == 0; });
+                if (stop) return;
+                b = &buf[next_fill];
+            }
+            const auto t0 = std::chrono::steady_clock::now();
+            uint64_t got = 0;
+            bool eof = false, err = false;
+            uint8_t* dst = b->mem + carry_cap;
+            while (got < region_bytes) {
+                const size_t ask = (size_t)std::min<uint64_t>(region_bytes - got, 1u << 30);
+                long k;
+                if (kind == BSQ_SOURCE_GZIP) k = gzread(gz, dst + got, (unsigned)std::min<size_t>(ask, 1u << 30));
+                else k = (long)fread(dst + got, 1, ask, fp);
+                if (k < 0) { err = true; break; }
+                if (k == 0) { eof = true; break; }
+                got += (uint64_t)k;
+            }
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                b->n_new = got; b->eof = eof || err; b->state = 1;
+                if (err) read_error = true;
+                st.reader_busy_s += dt; st.bytes_read += got;
+                next_fill ^= 1;
+            }
+            cv.notify_all();
+            if (eof || err) return;
+        }
+    }
+};
+
+extern "C" bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t source_kind, uint64_t region_bytes,
+                                      bsq_stream** out) {
+    if (!p || !path || !out) return BSQ_E_ARG;
+    *out = nullptr;
+    CK(cudaSetDevice(p->cfg.device_id));
+    bsq_stream* s = new (std::nothrow) bsq_stream();
+    if (!s) return BSQ_E_NOMEM;
+    s->p = p;
+    if (source_kind == BSQ_SOURCE_AUTO) {
+        const size_t n = strlen(path);
+        auto ends = [&](const char* suf) { const size_t k = strlen(suf); return n >= k && strcmp(path + n - k, suf) == 0; };
+        source_kind = (ends(".gz") || ends(".bgz")) ? BSQ_SOURCE_GZIP : BSQ_SOURCE_PLAIN;
+    }
+    s->kind = source_kind;
+    if (source_kind == BSQ_SOURCE_GZIP) {
+        s->gz = gzopen(path, "rb");
+        if (s->gz) gzbuffer(s->gz, 1 << 20);
+    } else {
+        s->fp = fopen(path, "rb");
+    }
+    if (!s->gz && !s->fp) { p->last_error = std::string("cannot open ") + path; delete s; return BSQ_E_ARG; }
+    s->region_bytes = region_bytes ? region_bytes : (256ull << 20);
+    s->carry_cap = std::max<uint64_t>(std::min<uint64_t>(s->region_bytes, 64ull << 20), 4096);
+    for (auto& b : s->buf) {
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&b.mem), s->carry_cap + s->region_bytes + 64, cudaHostAllocDefault);
+        if (e != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, e, "cudaHostAlloc(stream region)"); }
+    }
+    s->reader = std::thread([s] { s->reader_main(); });
+    *out = s;
+    return BSQ_OK;
+}
+
+extern "C" void bsq_stream_close(bsq_stream* s) {
+    if (!s) return;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        s->stop = true;
+    }
+    s->cv.notify_all();
+    if (s->reader.joinable()) s->reader.join();
+    if (s->gz) gzclose(s->gz);
+    if (s->fp) fclose(s->fp);
+    for (auto& b : s->buf) if (b.mem) cudaFreeHost(b.mem);
+    delete s;
+}
+
+extern "C" bsq_status bsq_stream_next(bsq_stream* s, uint32_t want, bsq_pass_result* out) {
+    if (!s || !out) return BSQ_E_ARG;
+    bsq_parser* p = s->p;
+    CK(cudaSetDevice(p->cfg.device_id));
+    if (s->finished) { p->last_error = "stream already finished"; return BSQ_E_STATE; }
+    // the previous region's buffer goes back to the reader
+    if (s->cur >= 0) {
+        {
+            std::lock_guard<std::mutex> lk(s->mu);
+            s->buf[s->cur].state = 0;
+        }
+        s->cv.notify_all();
+        s->cur = -1;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    bsq_stream::Buf* b;
+    {
+        std::unique_lock<std::mutex> lk(s->mu);
+        s->cv.wait(lk, [&] { return s->buf[s->next_take].state == 1; });
+        b = &s->buf[s->next_take];
+        b->state = 2;
+        s->cur = s->next_take;
+        s->next_take ^= 1;
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    s->st.wait_reader_s += std::chrono::duration<double>(t1 - t0).count();
+    if (s->read_error) { p->last_error = "read / inflate error"; s->finished = true; return BSQ_E_ARG; }
+    if (s->carry.size() > s->carry_cap) {
+        s->finished = true;
+        memset(out, 0, sizeof *out);
+        set_plain_error(&out->stop, BSQ_BUFFER_AT_MAX, "FASTQ record exceeds maximum buffer capacity");
+        return BSQ_OK;
+    }
+    uint8_t* region = b->mem + s->carry_cap - s->carry.size();
+    if (!s->carry.empty()) memcpy(region, s->carry.data(), s->carry.size());
+    const uint64_t n = s->carry.size() + b->n_new;
+    const bool is_last = b->eof;
+    const uint32_t m = (uint32_t)p->cfg.batch_size;
+    uint32_t w = want;
+    if (!is_last && (want & BSQ_WANT_BATCHES)) w |= BSQ_WANT_OFFSETS;   // the cut between regions needs offsets
+    bsq_status rc = bsq_parse_host(p, region, n, s->stream_pos, s->records_done, is_last ? 1 : 0, w, out);
+    if (rc != BSQ_OK) { s->finished = true; return rc; }
+    if (!is_last && out->stop.code == BSQ_OK && (want & BSQ_WANT_BATCHES) && out->n_records % m != 0 && out->n_records >= m) {
+        // keep batches whole across regions: the trailing partial batch is re-presented with the next region
+        const int64_t keep = out->n_records - out->n_records % m;
+        int wi = 0;
+        while (wi + 1 < p->res.n_windows && keep >= p->win[wi + 1].rec_base) ++wi;
+        uint32_t le = 0;
+        CK(cudaMemcpy(&le, p->win[wi].line_ends.as<uint32_t>() + 4ull * (keep - p->win[wi].rec_base), 4, cudaMemcpyDeviceToHost));
+        const int64_t cut = (int64_t)p->win[wi].region_off - (int64_t)p->win[wi].wp.begin + (int64_t)(le + 1u);
+        out->n_records = keep;
+        out->n_batches = keep / m;
+        out->bytes_consumed = cut;
+        out->n_bases = -1;
+        p->res.n_records = keep; p->res.n_batches = keep / m; p->res.bytes_consumed = cut;
+    }
+    s->region_ptr = region; s->region_n = n;
+    s->st.parse_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+    s->st.regions += 1;
+    // carry for the next region
+    const uint64_t consumed = (uint64_t)out->bytes_consumed;
+    s->carry.assign(region + consumed, region + n);
+    // (stream_pos / records_done describe the NEXT region from here on; bsq_stream_region reports this one)
+    const int64_t this_pos = s->stream_pos, this_first = s->records_done;
+    s->stream_pos += (int64_t)consumed;
+    s->records_done += out->n_records;
+    if (out->stop.code != BSQ_OK) s->finished = true;
+    s->carry.shrink_to_fit();
+    (void)this_pos; (void)this_first;
+    return BSQ_OK;
+}
+
+extern "C" const uint8_t* bsq_stream_region(const bsq_stream* s, uint64_t* n, int64_t* stream_offset, int64_t* first_record) {
+    if (!s || s->cur < 0) return nullptr;
+    if (n) *n = s->region_n;
+    if (stream_offset) *stream_offset = s->p->pass_stream_offset;
+    if (first_record) *first_record = s->records_done - s->p->res.n_records;
+    return s->region_ptr;
+}
+
+extern "C" bsq_status bsq_stream_get_stats(const bsq_stream* s, bsq_stream_stats* out) {
+    if (!s || !out) return BSQ_E_ARG;
+    std::lock_guard<std::mutex> lk(const_cast<bsq_stream*>(s)->mu);
+    *out = s->st;
+    return BSQ_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

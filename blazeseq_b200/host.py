@@ -128,7 +128,8 @@ class FileReader(Reader):
     """readers.mojo:86-137."""
 
     def __init__(self, path):
-        self._f = open(os.fspath(path), "rb", buffering=0)
+        self.path = os.fspath(path)
+        self._f = open(self.path, "rb", buffering=0)
 
     def read_to_buffer(self, buf, amt, pos=0):
         self._check(buf, amt, pos)
@@ -140,7 +141,8 @@ class GZFile(Reader):
     """readers.mojo:283-377 (zlib gzread)."""
 
     def __init__(self, path, mode: str = "rb"):
-        self._f = gzip.open(os.fspath(path), "rb")
+        self.path = os.fspath(path)
+        self._f = gzip.open(self.path, "rb")
 
     def read_to_buffer(self, buf, amt, pos=0):
         self._check(buf, amt, pos)
@@ -443,6 +445,34 @@ class GpuParser:
                                                schema.OFFSET, C.byref(w)), self._h, "bsq_synth_device")
         return int(w.value)
 
+    def stream_open(self, path: str, kind: int = capi.SOURCE_AUTO, region_bytes: int = 0):
+        h = C.c_void_p()
+        capi.check(capi.lib().bsq_stream_open(self._h, os.fspath(path).encode(), kind, region_bytes, C.byref(h)),
+                   self._h, "bsq_stream_open")
+        return h
+
+    def stream_next(self, stream, want: int):
+        """Parses the next region of a file stream; returns (PassResult, region bytes as a numpy view,
+        stream offset of the region, records before it)."""
+        r = capi.PassResult()
+        capi.check(capi.lib().bsq_stream_next(stream, want, C.byref(r)), self._h, "bsq_stream_next")
+        n, off, first = C.c_uint64(), C.c_int64(), C.c_int64()
+        ptr = capi.lib().bsq_stream_region(stream, C.byref(n), C.byref(off), C.byref(first))
+        if ptr and n.value:
+            data = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n.value,))
+        else:
+            data = np.zeros(0, np.uint8)
+        self.result = r
+        return r, data, off.value, first.value
+
+    def stream_stats(self, stream) -> capi.StreamStats:
+        st = capi.StreamStats()
+        capi.check(capi.lib().bsq_stream_get_stats(stream, C.byref(st)), self._h)
+        return st
+
+    def stream_close(self, stream):
+        capi.lib().bsq_stream_close(stream)
+
     def summarize_device(self, dev_ptr: int, n: int) -> capi.Summary:
         s = capi.Summary()
         capi.check(capi.lib().bsq_summarize_device(self._h, C.c_void_p(dev_ptr), n, C.byref(s)), self._h)
@@ -467,8 +497,10 @@ def shard_prefix(summaries, shard_bytes):
 class _Region:
     """One pass: the host bytes it covered and the tables it produced."""
 
-    def __init__(self, data: np.ndarray, stream_offset: int, first_record: int, result: capi.PassResult, want: int):
+    def __init__(self, data: np.ndarray, stream_offset: int, first_record: int, result: capi.PassResult, want: int,
+                 is_last: bool = True):
         self.data, self.stream_offset, self.first_record, self.want = data, stream_offset, first_record, want
+        self.is_last = is_last
         self.n = int(result.n_records)
         self.stop = result.stop
         self.consumed = int(result.bytes_consumed)
@@ -487,7 +519,7 @@ class FastqParser:
 
     def __init__(self, reader: Reader, quality_schema: Optional[str] = None, *, batch_size: Optional[int] = None,
                  schema: str = "generic", config: Optional[ParserConfig] = None, device_id: int = 0,
-                 region_bytes: int = 1 << 30, _force_id_slow_path: bool = False):
+                 region_bytes: int = 1 << 30, _force_id_slow_path: bool = False, native_io: bool = True):
         self.config = config or ParserConfig()
         if quality_schema is not None:                      # parser.mojo:117
             self.quality_schema = parse_schema(quality_schema)
@@ -511,7 +543,19 @@ class FastqParser:
         self._eof_seen = False                # BufferedReader._is_eof (buffered.mojo:278-279)
         self._region: Optional[_Region] = None
         self._cursor = 0                      # next record of the current region
-        self._first_fill()
+        # file-backed readers go through the library's own pipeline: a reader thread fills pinned
+        # regions (inflating .gz with zlib) while the GPU parses the previous one (bsq_stream_*)
+        self._stream = None
+        self._pending = None
+        path = getattr(reader, "path", None)
+        if native_io and path is not None and type(reader) in (FileReader, GZFile, RapidgzipReader):
+            kind = capi.SOURCE_PLAIN if type(reader) is FileReader else capi.SOURCE_GZIP
+            self._stream = self._gpu.stream_open(path, kind, self._region_bytes)
+            self._stream_done = False
+            if os.path.getsize(path) == 0:
+                self._eof_seen = True     # BufferedReader.__init__ already read 0 bytes
+        else:
+            self._first_fill()
 
     # -- input ---------------------------------------------------------------------------------
 
@@ -539,6 +583,16 @@ class FastqParser:
             self._eof_seen = True
 
     def _load_region(self, want: int):
+        if self._stream is not None:
+            self._gpu.set_batch_size(self._batch_size)
+            res, data, off, first = self._gpu.stream_next(self._stream, want)
+            is_last = res.stop.code != capi.OK
+            reg = _Region(data, off, first, res, want | (0 if is_last else (capi.WANT_OFFSETS if want & capi.WANT_BATCHES else 0)),
+                          is_last)
+            self._stream_done = is_last
+            self._region = reg
+            self._cursor = 0
+            return
         if self._pending is None:
             self._pending = self._read_upto(max(self._region_bytes, 2 * self._carry.size))
         data = self._pending
@@ -557,7 +611,7 @@ class FastqParser:
         data = np.ascontiguousarray(data)
         self._gpu.set_batch_size(self._batch_size)
         res = self._gpu.parse_host(data, self._stream_pos, self._records_done, is_last, want)
-        reg = _Region(data, self._stream_pos, self._records_done, res, want)
+        reg = _Region(data, self._stream_pos, self._records_done, res, want, is_last)
         if not is_last and reg.stop.code == capi.OK and (want & capi.WANT_BATCHES) and reg.n % self._batch_size:
             # keep batches whole across regions: the records of the trailing partial batch are
             # re-presented with the next region (their bytes go back into the carry)
@@ -571,6 +625,9 @@ class FastqParser:
 
     def _advance_region(self):
         reg = self._region
+        if self._stream is not None:      # the library carries the unconsumed tail itself
+            self._region = None
+            return
         self._carry = reg.data[reg.consumed:]
         self._stream_pos += reg.consumed
         self._records_done += reg.n
@@ -581,8 +638,8 @@ class FastqParser:
             return
         if not (reg.want & capi.WANT_OFFSETS):
             # the pass was cut for batches only; run it again for the offsets table
-            res = self._gpu.parse_host(reg.data, reg.stream_offset, reg.first_record,
-                                       self._reader_eof, reg.want | capi.WANT_OFFSETS)
+            res = self._gpu.parse_host(np.ascontiguousarray(reg.data), reg.stream_offset, reg.first_record,
+                                       reg.is_last, reg.want | capi.WANT_OFFSETS)
             reg.want |= capi.WANT_OFFSETS
             reg.n_windows = int(res.n_windows)
         cols = [[] for _ in range(7)]
@@ -616,6 +673,8 @@ class FastqParser:
                 return True
             unconsumed = self._region.data.size - self._region.consumed
             return unconsumed > 0 or not self._eof_seen
+        if self._stream is not None:
+            return not self._eof_seen
         return self._carry.size > 0 or (self._pending is not None and self._pending.size > 0) or not self._eof_seen
 
     def _raise_stop(self, stop: capi.Error):
@@ -628,7 +687,10 @@ class FastqParser:
         """Index (in the current region) of the next record, loading regions as needed."""
         while True:
             if self._region is None:
-                if self._eof_seen and self._carry.size == 0 and (self._pending is None or self._pending.size == 0):
+                if self._stream is not None:
+                    if self._stream_done or self._eof_seen and os.path.getsize(self._reader.path) == 0:
+                        raise EOFError()
+                elif self._eof_seen and self._carry.size == 0 and (self._pending is None or self._pending.size == 0):
                     raise EOFError()
                 self._load_region(want)
             reg = self._region
@@ -737,6 +799,17 @@ class FastqParser:
 
     def __iter__(self):
         return self.records()
+
+    def close(self):
+        if getattr(self, "_stream", None) is not None:
+            self._gpu.stream_close(self._stream)
+            self._stream = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _with_device(self: FastqBatch, dev: DeviceFastqBatch) -> FastqBatch:

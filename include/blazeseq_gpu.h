@@ -176,6 +176,38 @@ bsq_status bsq_parse_host(bsq_parser* p, const uint8_t* host_bytes, uint64_t n,
                           int64_t stream_offset, int64_t first_record, int32_t is_last,
                           uint32_t want, bsq_pass_result* out);
 
+/* ---- streaming from a file ----------------------------------------------------------------------
+ * FileReader / GZFile / RapidgzipReader (io/readers.mojo:86-137,283-377,380-443) + BufferedReader
+ * (io/buffered.mojo:115-327) + the parse loop, as a pipeline: a reader thread reads (or inflates,
+ * zlib) the next region into pinned memory while the GPU parses the current one; the H2D copies of
+ * a region run on the copy stream, overlapped with its first scan pass.  The unconsumed tail of a
+ * region (the partial record; with BSQ_WANT_BATCHES also the records of a trailing partial batch) is
+ * carried in front of the next region, like BufferedReader._compact_from (:239-260). */
+typedef struct bsq_stream bsq_stream;
+#define BSQ_SOURCE_PLAIN 0
+#define BSQ_SOURCE_GZIP 1          /* gzip / BGZF members, inflated with zlib (gzread) */
+#define BSQ_SOURCE_AUTO 2          /* by suffix: .gz / .bgz -> gzip (python/blazeseq_parser.mojo:100-114) */
+
+typedef struct bsq_stream_stats {
+    uint64_t bytes_read;           /* decompressed bytes delivered by the reader thread */
+    uint64_t regions;
+    double reader_busy_s;          /* reader thread: time spent reading / inflating */
+    double parse_s;                /* caller: time inside the GPU passes (incl. H2D) */
+    double wait_reader_s;          /* caller: time blocked waiting for the reader thread */
+} bsq_stream_stats;
+
+bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t source_kind, uint64_t region_bytes,
+                           bsq_stream** out);
+/* Parses the next region.  out->stop.code == BSQ_OK: more regions follow; BSQ_EOF: clean end;
+ * anything else: the first error (no further regions).  Result views (bsq_get_offsets, bsq_get_batch,
+ * ...) refer to this region until the next call.  first_record / stream offsets are global. */
+bsq_status bsq_stream_next(bsq_stream* s, uint32_t want, bsq_pass_result* out);
+/* Host bytes of the region just parsed (offset tables index these); *stream_offset = position of
+ * byte 0 in the file's (decompressed) stream; *first_record = records before it. */
+const uint8_t* bsq_stream_region(const bsq_stream* s, uint64_t* n, int64_t* stream_offset, int64_t* first_record);
+bsq_status bsq_stream_get_stats(const bsq_stream* s, bsq_stream_stats* out);
+void bsq_stream_close(bsq_stream* s);
+
 /* ---- results of the last pass -------------------------------------------------------------- */
 
 bsq_status bsq_get_offsets(const bsq_parser* p, int32_t window, bsq_offsets_view* out);

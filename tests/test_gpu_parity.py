@@ -507,3 +507,61 @@ def test_fastq_parser_file_and_gzip_readers(B, oracle, tmp_path):
         assert (n, nb) == (len(views), bases)     # the "<records> <base_pairs>" cross-check of the reference
         p = B.parser(str(tmp_path / path), "illumina_1.8")
         assert sum(len(b) for b in p.batches(512)) == len(views)
+
+
+# ------------------------------------------------------------------ native file / gzip pipeline
+
+
+@pytest.mark.parametrize("gz", [False, True])
+@pytest.mark.parametrize("region_bytes", [64 << 10, 1 << 20, 1 << 26])
+def test_stream_pipeline_regions(B, oracle, tmp_path, gz, region_bytes):
+    """bsq_stream_*: reader thread -> pinned regions -> passes.  Every region's tables must be the
+    oracle's slice, batches stay whole across regions, totals and the stop reason agree."""
+    import gzip
+    from blazeseq_b200 import _capi as capi
+    data = oracle.synth(12000, 75, 300, 2, 40, "illumina_1.8")
+    path = tmp_path / ("s.fastq.gz" if gz else "s.fastq")
+    if gz:
+        with gzip.open(path, "wb", compresslevel=1) as f:
+            f.write(data.tobytes())
+    else:
+        path.write_bytes(data.tobytes())
+    views, bases, err = oracle.parse_all(data)
+    m = 512
+    gpu = B.GpuParser(False, False, B.parse_schema("illumina_1.8"), m)
+    st = gpu.stream_open(str(path), capi.SOURCE_AUTO, region_bytes)
+    done = 0
+    while True:
+        res, region, off, first = gpu.stream_next(st, capi.WANT_OFFSETS | capi.WANT_BATCHES)
+        n = int(res.n_records)
+        assert first == done and off == (int(views[done]["header_start"]) if done < len(views) else data.size)
+        assert np.array_equal(region[:int(res.bytes_consumed)], data[off:off + int(res.bytes_consumed)])
+        if res.stop.code == capi.OK:
+            assert n % m == 0 or n < m            # batches are not split by a region boundary
+        for b in range(int(res.n_batches)):
+            got = gpu.batch_to_host(b)
+            exp = oracle.build_batch(data, views[done + b * m: done + min((b + 1) * m, n)])
+            for g, e in zip(got, (exp[1], exp[2], exp[0], exp[4], exp[3])):
+                assert np.array_equal(g, e)
+        done += n
+        if res.stop.code != capi.OK:
+            assert res.stop.code == capi.EOF
+            break
+    assert done == len(views)
+    stats = gpu.stream_stats(st)
+    assert stats.bytes_read == data.size and stats.regions >= 1
+    gpu.stream_close(st)
+    gpu.close()
+
+
+def test_native_and_python_io_paths_agree(B, oracle, tmp_path):
+    data = oracle.synth(5000, 30, 120, 2, 40, "sanger").tobytes() + b"@tail\nACGT\n+\nIIII"   # no final newline
+    (tmp_path / "t.fastq").write_bytes(data)
+    out = []
+    for native in (True, False):
+        p = B.FastqParser(B.FileReader(tmp_path / "t.fastq"), "sanger", region_bytes=50000, native_io=native,
+                          config=B.ParserConfig(check_ascii=True, check_quality=True, buffer_growth_enabled=True))
+        recs = [(r.id, r.sequence, r.quality) for r in p.records()]
+        out.append(recs)
+        assert not p.has_more()
+    assert out[0] == out[1] and len(out[0]) == 5001 and out[0][-1] == ("tail", "ACGT", "IIII")
