@@ -781,80 +781,92 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
             const uint32_t k_first = r0 >> 2, k_last = (r0 + n - 1u) >> 2;
             const bool batch_edge = kPack && (P.rec_mod + k_first) / bsz != (P.rec_mod + k_last + 1u) / bsz;
 
-            // every thread owns q consecutive list entries: [tid*q, tid*q + q)
-            const uint32_t q = (n + kThreads - 1u) / kThreads;
-            const uint32_t jb = tid * q, je = jb + q < n ? jb + q : n;
-            uint32_t v_id = 0, v_seq = 0, v_qual = 0, max_len = 0;
-            for (uint32_t j = jb; j < je; ++j) {
-                const uint32_t p = S.nlx[kHead + j];
-                const uint32_t q1 = S.nlx[kHead + j - 1];
-                const uint32_t r = r0 + j;
-                const uint32_t cls = r & 3u, k = r >> 2;
-                const bool live = k < P.n_complete;
-                const uint32_t len = p - q1 - 1u;
-                if (live && cls != 2u && len > max_len) max_len = len;
-                if (kOffsets) P.line_ends[1u + r] = p;
-                if (cls == 0u) {
-                    // header line: '@' check (utils.mojo:454), id = line minus '@', stripped
+            // views(): the line-end table, one coalesced store per newline
+            if (kOffsets)
+                for (uint32_t j = tid; j < n; j += kThreads) P.line_ends[1u + r0 + j] = S.nlx[kHead + j];
+
+            // one thread per RECORD: it handles the (up to four) lines of its record that end in this
+            // pass, so every class-specific step runs without divergence and a record's lengths and
+            // destinations stay in registers.  Record k owns list entries 4k - r0 + {0,1,2,3}.
+            const uint32_t n_rec = k_last - k_first + 1u;
+            uint32_t max_len = 0;
+            for (uint32_t tb0 = 0; tb0 < n_rec; tb0 += kThreads) {
+                const uint32_t t = tb0 + tid;
+                const uint32_t k = k_first + t;
+                const bool mine = t < n_rec;
+                const bool live = mine && k < P.n_complete;
+                const int32_t j0 = (int32_t)(4u * k - r0);                 // list index of the header's newline
+                const uint32_t* e = &S.nlx[kHead] + j0;                    // e[c] = newline of class c, e[-1] = the one before
+                const bool has0 = mine && j0 >= 0 && j0 < (int32_t)n, has1 = mine && j0 + 1 >= 0 && j0 + 1 < (int32_t)n,
+                           has2 = mine && j0 + 2 >= 0 && j0 + 2 < (int32_t)n, has3 = mine && j0 + 3 >= 0 && j0 + 3 < (int32_t)n;
+                uint32_t l_id = 0, l_seq = 0, l_qual = 0, s_id = 0, s_seq = 0, s_qual = 0;
+                if (has0) {
+                    // header line: '@' check (utils.mojo:454), id = line minus '@', stripped (utils.mojo:221-242)
+                    const uint32_t q1 = e[-1], p = e[0];
+                    const uint32_t len = p - q1 - 1u;
                     uint32_t a = q1 + 2u, nid = 0;
                     if (live) {
                         if (byte_at(S, c, W, q1 + 1u) != '@') report(P, k, 1u);
                         nid = len > 0u ? len - 1u : 0u;
                         if (nid > 0u && (bsq_is_space(byte_at(S, c, W, a)) || bsq_is_space(byte_at(S, c, W, p - 1u)))) {
-                            uint32_t e = p;
-                            while (a < e && bsq_is_space(byte_at(S, c, W, a))) ++a;
-                            while (e > a && bsq_is_space(byte_at(S, c, W, e - 1u))) --e;
-                            nid = e - a;
+                            uint32_t z = p;
+                            while (a < z && bsq_is_space(byte_at(S, c, W, a))) ++a;
+                            while (z > a && bsq_is_space(byte_at(S, c, W, z - 1u))) --z;
+                            nid = z - a;
                             if (kPack && P.id_fast) *P.strip_flag = 1u;   // the optimistic id packing is void
                         }
                         if (kOffsets || (kPack && !P.id_fast)) { P.id_spans[2u * k] = a; P.id_spans[2u * k + 1u] = nid; }
+                        if (len > max_len) max_len = len;
                     }
-                    if (kPack) { const uint32_t i = (j - j_id) >> 2; S.sdst[0][i] = nid; S.ssrc[0][i] = a; v_id += nid; }
-                } else if (cls == 1u) {
-                    const uint32_t l = live ? len : 0u;
-                    bases_acc += l;
-                    if (kPack) { const uint32_t i = (j - j_seq) >> 2; S.sdst[1][i] = l; S.ssrc[1][i] = q1 + 1u; v_seq += l; }
-                } else if (cls == 2u) {
-                    if (live && byte_at(S, c, W, q1 + 1u) != '+') report(P, k, 2u);      // utils.mojo:456
-                } else {
-                    const uint32_t q2 = S.nlx[kHead + j - 2], q3 = S.nlx[kHead + j - 3];
-                    if (live && q2 - q3 - 1u != len) report(P, k, 3u);                   // utils.mojo:458-461
-                    const uint32_t l = live ? len : 0u;
-                    if (kPack) { const uint32_t i = (j - j_qual) >> 2; S.sdst[2][i] = l; S.ssrc[2][i] = q1 + 1u; v_qual += l; }
+                    l_id = nid; s_id = a;
                 }
-            }
-            if (kPack) {
-                uint32_t e_id, e_seq, e_qual, t_id, t_seq, t_qual;
-                block_exclusive_scan3(S, v_id, v_seq, v_qual, e_id, e_seq, e_qual, t_id, t_seq, t_qual, par);
-                // second walk: lengths -> destinations; cumulative ends of the records that finish here
-                uint32_t a_id = cum_id + e_id, a_seq = cum_seq + e_seq, a_qual = cum_qual + e_qual;
-                for (uint32_t j = jb; j < je; ++j) {
-                    const uint32_t r = r0 + j;
-                    const uint32_t cls = r & 3u, k = r >> 2;
-                    if (cls == 0u) {
-                        const uint32_t i = (j - j_id) >> 2, l = S.sdst[0][i];
-                        S.sdst[0][i] = a_id + sh_id; a_id += l;
-                        if (P.id_fast && k < P.n_complete) {
-                            const int64_t endv = P.id_base64 + (int64_t)a_id;
+                if (has1) {
+                    const uint32_t q1 = e[0], len = e[1] - q1 - 1u;
+                    if (live) { l_seq = len; bases_acc += len; if (len > max_len) max_len = len; }
+                    s_seq = q1 + 1u;
+                }
+                if (has2 && live && byte_at(S, c, W, e[1] + 1u) != '+') report(P, k, 2u);      // utils.mojo:456
+                if (has3) {
+                    const uint32_t q1 = e[2], len = e[3] - q1 - 1u;
+                    if (live) {
+                        if (e[1] - e[0] - 1u != len) report(P, k, 3u);                       // utils.mojo:458-461
+                        l_qual = len;
+                        if (len > max_len) max_len = len;
+                    }
+                    s_qual = q1 + 1u;
+                }
+                if (kPack) {
+                    uint32_t e_id, e_seq, e_qual, t_id, t_seq, t_qual;
+                    block_exclusive_scan3(S, l_id, l_seq, l_qual, e_id, e_seq, e_qual, t_id, t_seq, t_qual, par);
+                    // stream-local line index of this record's lines (class c lines of the pass are consecutive records)
+                    if (has0) {
+                        const uint32_t i = (uint32_t)(j0 - (int32_t)j_id) >> 2;
+                        S.sdst[0][i] = cum_id + e_id + sh_id; S.ssrc[0][i] = s_id;
+                        if (live && P.id_fast) {
+                            const int64_t endv = P.id_base64 + (int64_t)(cum_id + e_id + l_id);
                             P.id_ends_abs[P.rec_base + (int64_t)k] = endv;
                             if (batch_edge) { const uint32_t tb1 = P.rec_mod + k + 1u;
                                 if (tb1 % bsz == 0u) P.id_ends_base[P.rec_div + (int64_t)(tb1 / bsz)] = endv; }
                         }
-                    } else if (cls == 1u) {
-                        const uint32_t i = (j - j_seq) >> 2, l = S.sdst[1][i];
-                        S.sdst[1][i] = a_seq + sh_seq; a_seq += l;
-                    } else if (cls == 3u) {
-                        const uint32_t i = (j - j_qual) >> 2, l = S.sdst[2][i];
-                        S.sdst[2][i] = a_qual + sh_qual; a_qual += l;
-                        if (k < P.n_complete) {
-                            const int64_t endv = P.qual_base64 + (int64_t)a_qual;
+                    }
+                    if (has1) {
+                        const uint32_t i = (uint32_t)(j0 + 1 - (int32_t)j_seq) >> 2;
+                        S.sdst[1][i] = cum_seq + e_seq + sh_seq; S.ssrc[1][i] = s_seq;
+                    }
+                    if (has3) {
+                        const uint32_t i = (uint32_t)(j0 + 3 - (int32_t)j_qual) >> 2;
+                        S.sdst[2][i] = cum_qual + e_qual + sh_qual; S.ssrc[2][i] = s_qual;
+                        if (live) {
+                            const int64_t endv = P.qual_base64 + (int64_t)(cum_qual + e_qual + l_qual);
                             P.ends_abs[P.rec_base + (int64_t)k] = endv;
                             if (batch_edge) { const uint32_t tb1 = P.rec_mod + k + 1u;
                                 if (tb1 % bsz == 0u) P.ends_base[P.rec_div + (int64_t)(tb1 / bsz)] = endv; }
                         }
                     }
+                    cum_id += t_id; cum_seq += t_seq; cum_qual += t_qual;
                 }
-                cum_id += t_id; cum_seq += t_seq; cum_qual += t_qual;
+            }
+            if (kPack) {
                 if (tid < 3) {
                     // two sentinels per stream: the end of the range, and a source for the "next line" read
                     const uint32_t nn = tid == 0 ? n_id : (tid == 1 ? n_seq : n_qual);
