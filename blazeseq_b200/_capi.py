@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libblazeseq_gpu.so")
+# BSQ_LIB: development override to A/B a differently tuned build of the same library (scripts/build_variants.sh)
+LIB_PATH = os.environ.get("BSQ_LIB") or os.path.join(HERE, "lib", "libblazeseq_gpu.so")
 
 # FastxErrorCode (blazeseq/errors.mojo:43-56) + library failures
 OK, ID_NO_AT, SEP_NO_PLUS, SEQ_QUAL_LEN_MISMATCH, ASCII_INVALID, QUALITY_OUT_OF_RANGE = range(6)

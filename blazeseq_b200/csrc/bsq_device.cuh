@@ -26,8 +26,14 @@ namespace bsq {
 constexpr int kTile = 16384;              // bytes per tile
 constexpr int kThreads = 128;             // threads per CTA (4 warps): small CTAs, many per SM, cheap barriers
 constexpr int kWarps = kThreads / 32;
-constexpr int kStages = 2;                // TMA ring depth per CTA (4 CTAs/SM -> 128 KiB in flight/SM)
-constexpr int kResolveCtas = 4;           // resident CTAs per SM, k_resolve (shared memory + registers)
+#ifndef BSQ_STAGES
+#define BSQ_STAGES 2
+#endif
+#ifndef BSQ_RESOLVE_CTAS
+#define BSQ_RESOLVE_CTAS 3
+#endif
+constexpr int kStages = BSQ_STAGES;       // TMA ring depth per CTA
+constexpr int kResolveCtas = BSQ_RESOLVE_CTAS;  // resident CTAs per SM, k_resolve (shared memory + registers)
 constexpr int kSummarizeCtas = 6;         // resident CTAs per SM, k_summarize
 constexpr int kChunks = kTile / 16;       // 16-byte chunks per tile (1024)
 constexpr int kChunksPerThread = kChunks / kThreads;  // 8
@@ -39,6 +45,7 @@ constexpr int kLinesCap = kNlCap / 4 + 3; // lines of one class per pass (+ two 
 constexpr int kTilePad = 32;              // readable slack after a tile for unaligned 16-byte loads
 constexpr int kHalo = 1024;               // bytes before the tile kept in shared memory too: a line that began
                                           // up to kHalo bytes before the tile is still read from shared memory
+constexpr int kStage = kHalo + kTile + 128;  // SoA staging: the lines that END in a tile lie in [halo | tile]; + 3 x 32 alignment slack
 constexpr int kMaxWindows = 64;
 
 static_assert(kThreads % 4 == 0 && kWordsPerThread == 4 && kChunksPerThread * kThreads == kChunks, "");
@@ -128,6 +135,22 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
         : "memory");
 }
 
+// shared -> global bulk copy (bulk async-group); bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the bulk stores issued by this thread have finished READING shared memory (the source may be reused)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // shared-memory layout of one CTA
 // ------------------------------------------------------------------------------------------------
@@ -148,6 +171,8 @@ struct alignas(128) TileSmem {
                                               // nlx[kHead-1-i] = i-th newline before the list
     uint32_t sdst[3][kLinesCap];              // per class stream: destination of each line
     uint32_t ssrc[3][kLinesCap];              //                   source position of each line
+    alignas(128) uint8_t stage[kStage];       // SoA bytes of the pass, laid out like the destination (mod 16):
+                                              // [id | seq | qual], written back with TMA bulk stores
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -694,6 +719,62 @@ __device__ __forceinline__ void copy_line(const TileSmem& S, const TileCursor& c
     }
 }
 
+// Staged copy (the common case: every line of the pass lies in [halo | tile]).  One thread moves one
+// line from the tile to `stage`, which is laid out like the destination modulo 16: a byte loop up to
+// the first 4-byte boundary of the destination, then one funnel shift per word (each source word is
+// read once), then the last 0-3 bytes.  The staged range leaves through TMA bulk stores, so the
+// global writes cost no instructions and are full 16-byte vectors.
+__device__ __forceinline__ void stage_line(const uint8_t* __restrict__ data, uint8_t* __restrict__ stage,
+                                           uint32_t src, uint32_t dst, uint32_t len) {
+    if (len == 0u) return;   // (the source of an empty line may lie outside [halo | tile])
+    uint32_t h = (0u - dst) & 3u;
+    if (h > len) h = len;
+    for (uint32_t i = 0; i < h; ++i) stage[dst + i] = data[src + i];
+    src += h; dst += h; len -= h;
+    const uint32_t nw = len >> 2;
+    const uint32_t sh = (src & 3u) * 8u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(data + (src & ~3u));
+    uint32_t* dw = reinterpret_cast<uint32_t*>(stage + dst);
+    uint32_t w0 = sw[0];
+    uint32_t i = 0;
+    for (; i + 4u <= nw; i += 4u) {
+        const uint32_t w1 = sw[i + 1], w2 = sw[i + 2], w3 = sw[i + 3], w4 = sw[i + 4];
+        dw[i] = __funnelshift_r(w0, w1, sh);
+        dw[i + 1] = __funnelshift_r(w1, w2, sh);
+        dw[i + 2] = __funnelshift_r(w2, w3, sh);
+        dw[i + 3] = __funnelshift_r(w3, w4, sh);
+        w0 = w4;
+    }
+    for (; i < nw; ++i) {
+        const uint32_t w1 = sw[i + 1];
+        dw[i] = __funnelshift_r(w0, w1, sh);
+        w0 = w1;
+    }
+    const uint32_t t = len & 3u;
+    src += nw * 4u; dst += nw * 4u;
+    for (uint32_t k = 0; k < t; ++k) stage[dst + k] = data[src + k];
+}
+
+// One stream's staged range -> global: [ra, rb) are virtual destination offsets (out + offset, out
+// 16-byte aligned), stage[so + (d - (ra & ~15))] holds destination byte d.  The 16-byte aligned
+// interior leaves as one TMA bulk store (thread `issuer`); the <= 15 bytes on either side, which
+// share their vector with a neighbouring tile, are byte stores by lanes 0..31 of warp `wsel`.
+__device__ __forceinline__ void flush_stream(const uint8_t* stage, uint32_t so, uint32_t ra, uint32_t rb, uint8_t* out,
+                                             bool issuer, bool edge_warp) {
+    if (rb <= ra) return;
+    const uint32_t A = ra & ~15u;
+    const uint32_t i0 = (ra + 15u) & ~15u, i1 = rb & ~15u;
+    if (issuer && i1 > i0) tma_store_1d(out + i0, stage + so + (i0 - A), i1 - i0);
+    if (edge_warp) {
+        const uint32_t j = threadIdx.x & 31u;
+        const uint32_t head_end = i0 < rb ? i0 : rb;                 // head = [ra, head_end)
+        const uint32_t tail_beg = i1 > head_end ? i1 : head_end;     // tail = [tail_beg, rb)
+        const uint32_t d = j < 16u ? ra + j : tail_beg + (j - 16u);
+        const bool on = j < 16u ? d < head_end : d < rb;
+        if (on) out[d] = stage[so + (d - A)];
+    }
+}
+
 template <bool kAscii, bool kQual, bool kOffsets, bool kPack>
 __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinParams W, const ResolveParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -730,6 +811,8 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
         const uint32_t it = t - ta;
         const TileCursor c = make_cursor(W, t, it % kStages);
         mbar_wait(&S.full_bar[c.stage], (it / kStages) & 1u);
+        if (kStages == 1 && tid == 0 && t + 1u < tb)   // single buffer: the next tile waits in L2
+            prefetch_l2(W.base + (size_t)(t + 1u) * kTile, tile_bytes_rounded(W, t + 1u));
         build_bitmaps<kAscii, kQual>(S, c, addlo, addup);
         __syncthreads();
         const uint4 words = *reinterpret_cast<const uint4*>(&S.bm_nl[tid * 4]);
@@ -874,6 +957,7 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
                     S.sdst[tid][nn] = dd; S.sdst[tid][nn + 1] = dd; S.sdst[tid][nn + 2] = dd;
                     S.ssrc[tid][nn] = c.origin + 16u; S.ssrc[tid][nn + 1] = c.origin + 16u;
                 }
+                if (tid == 0) tma_store_wait_read();   // the previous pass's bulk stores have read `stage`
                 __syncthreads();
                 // room: bytes the id arena can still take.  Destinations past it only arise after a
                 // structure error (an empty header line makes the id prefix diverge); nothing there counts.
@@ -881,26 +965,54 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
                 const bool do_id = P.id_fast && rb_id > ra_id && (int64_t)rb_id <= P.id_cap - (P.id_base64 - sh_id) && n_id != 0u;
                 const uint32_t ra_seq = d0_seq + sh_seq, rb_seq = cum_seq + sh_seq;
                 const uint32_t ra_qual = d0_qual + sh_qual, rb_qual = cum_qual + sh_qual;
-                StreamJob jobs[3];
-                jobs[0] = StreamJob{S.sdst[0], S.ssrc[0], n_id, ra_id, do_id ? rb_id : ra_id, out_id};
-                jobs[1] = StreamJob{S.sdst[1], S.ssrc[1], n_seq, ra_seq, rb_seq, out_seq};
-                jobs[2] = StreamJob{S.sdst[2], S.ssrc[2], n_qual, ra_qual, rb_qual, out_qual};
                 // long lines (long reads, or a line that began far before the tile) are copied
-                // vector-parallel; otherwise every thread streams whole lines
+                // vector-parallel from wherever they lie; otherwise the pass is staged in shared memory
                 const bool long_lines = __syncthreads_or(max_len > (uint32_t)kHalo - 64u) != 0;
-                if (long_lines) {
+                const bool ok_seq = rb_seq > ra_seq, ok_qual = rb_qual > ra_qual;
+                if (long_lines || (P.debug_skip & 4u)) {
+                    StreamJob jobs[3];
+                    jobs[0] = StreamJob{S.sdst[0], S.ssrc[0], n_id, ra_id, do_id ? rb_id : ra_id, out_id};
+                    jobs[1] = StreamJob{S.sdst[1], S.ssrc[1], n_seq, ra_seq, rb_seq, out_seq};
+                    jobs[2] = StreamJob{S.sdst[2], S.ssrc[2], n_qual, ra_qual, rb_qual, out_qual};
+                    if (long_lines) {
 #pragma unroll
-                    for (int st = 0; st < 3; ++st)
-                        if (jobs[st].d1 > jobs[st].d0) copy_stream(S, c, W, jobs[st]);
-                } else if (!(P.debug_skip & 1u)) {
-                    // items: sequence lines, then quality lines, then ids (warps get lines of one kind)
-                    const uint32_t n1 = jobs[1].d1 > jobs[1].d0 ? n_seq : 0u, n2 = jobs[2].d1 > jobs[2].d0 ? n_qual : 0u,
-                                   n0 = jobs[0].d1 > jobs[0].d0 ? n_id : 0u;
-                    for (uint32_t w = tid; w < n1 + n2 + n0; w += kThreads) {
-                        if (w < n1) copy_line(S, c, W, jobs[1], w);
-                        else if (w < n1 + n2) copy_line(S, c, W, jobs[2], w - n1);
-                        else copy_line(S, c, W, jobs[0], w - n1 - n2);
+                        for (int st = 0; st < 3; ++st)
+                            if (jobs[st].d1 > jobs[st].d0) copy_stream(S, c, W, jobs[st]);
+                    } else {
+                        // (measurement / cross-check only) the line-parallel direct copy
+                        const uint32_t n1 = ok_seq ? n_seq : 0u, n2 = ok_qual ? n_qual : 0u, n0 = do_id ? n_id : 0u;
+                        for (uint32_t w = tid; w < n1 + n2 + n0; w += kThreads) {
+                            if (w < n1) copy_line(S, c, W, jobs[1], w);
+                            else if (w < n1 + n2) copy_line(S, c, W, jobs[2], w - n1);
+                            else copy_line(S, c, W, jobs[0], w - n1 - n2);
+                        }
                     }
+                } else if (!(P.debug_skip & 1u)) {
+                    // stage layout: [id | seq | qual], each region starts at the 16-byte vector of its
+                    // first destination byte; lengths are bounded by the bytes of [halo | tile]
+                    const uint32_t A_id = ra_id & ~15u, A_seq = ra_seq & ~15u, A_qual = ra_qual & ~15u;
+                    const uint32_t so_id = 0u;
+                    const uint32_t so_seq = do_id ? ((rb_id - A_id + 15u) & ~15u) : 0u;
+                    const uint32_t so_qual = so_seq + (ok_seq ? ((rb_seq - A_seq + 15u) & ~15u) : 0u);
+                    const uint32_t n1 = ok_seq ? n_seq : 0u, n2 = ok_qual ? n_qual : 0u, n0 = do_id ? n_id : 0u;
+                    const uint8_t* const data = S.data[c.stage];
+                    const uint32_t sbias = (uint32_t)kHalo - c.origin;          // window offset -> offset in data[stage]
+                    // items: sequence lines, then quality lines, then ids (one line per thread)
+                    for (uint32_t w = tid; w < n1 + n2 + n0; w += kThreads) {
+                        uint32_t st, i, so, A;
+                        if (w < n1) { st = 1u; i = w; so = so_seq; A = A_seq; }
+                        else if (w < n1 + n2) { st = 2u; i = w - n1; so = so_qual; A = A_qual; }
+                        else { st = 0u; i = w - n1 - n2; so = so_id; A = A_id; }
+                        const uint32_t d = S.sdst[st][i];
+                        stage_line(data, S.stage, S.ssrc[st][i] + sbias, so + (d - A), S.sdst[st][i + 1] - d);
+                    }
+                    fence_proxy_async_smem();
+                    __syncthreads();
+                    const uint32_t wsel = tid >> 5;
+                    if (do_id) flush_stream(S.stage, so_id, ra_id, rb_id, out_id, tid == 0, wsel == 0u);
+                    if (ok_seq) flush_stream(S.stage, so_seq, ra_seq, rb_seq, out_seq, tid == 0, wsel == 1u);
+                    if (ok_qual) flush_stream(S.stage, so_qual, ra_qual, rb_qual, out_qual, tid == 0, wsel == 2u);
+                    if (tid == 0) tma_store_commit();
                 }
             }
             __syncthreads();
@@ -911,6 +1023,7 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
         if (total == 0u) __syncthreads();   // (the pass loop ends with a barrier otherwise)
         if (tid == 0 && t + kStages < tb) issue_tile_load<true>(S, W, t + kStages, c.stage);
     }
+    if (kPack && tid == 0) tma_store_wait_all();   // shared memory must outlive the bulk stores
     // one atomic per warp: the run's share of the base count
     unsigned long long b64 = bases_acc;
 #pragma unroll
