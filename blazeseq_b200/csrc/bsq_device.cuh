@@ -23,18 +23,24 @@
 
 namespace bsq {
 
-constexpr int kTile = 16384;              // bytes per tile
-constexpr int kThreads = 128;             // threads per CTA (4 warps): small CTAs, many per SM, cheap barriers
+#ifndef BSQ_TILE
+#define BSQ_TILE 16384
+#endif
+constexpr int kTile = BSQ_TILE;           // bytes per tile
+#ifndef BSQ_THREADS
+#define BSQ_THREADS 128
+#endif
+constexpr int kThreads = BSQ_THREADS;     // threads per CTA
 constexpr int kWarps = kThreads / 32;
 #ifndef BSQ_STAGES
-#define BSQ_STAGES 2
+#define BSQ_STAGES 1
 #endif
 #ifndef BSQ_RESOLVE_CTAS
-#define BSQ_RESOLVE_CTAS 3
+#define BSQ_RESOLVE_CTAS 4
 #endif
 constexpr int kStages = BSQ_STAGES;       // TMA ring depth per CTA
 constexpr int kResolveCtas = BSQ_RESOLVE_CTAS;  // resident CTAs per SM, k_resolve (shared memory + registers)
-constexpr int kSummarizeCtas = 6;         // resident CTAs per SM, k_summarize
+constexpr int kSummarizeCtas = 768 / kThreads;  // resident CTAs per SM, k_summarize (24 warps)
 constexpr int kChunks = kTile / 16;       // 16-byte chunks per tile (1024)
 constexpr int kChunksPerThread = kChunks / kThreads;  // 8
 constexpr int kWords = kTile / 32;        // bitmap words per tile (512)
@@ -48,7 +54,10 @@ constexpr int kHalo = 1024;               // bytes before the tile kept in share
 constexpr int kStage = kHalo + kTile + 128;  // SoA staging: the lines that END in a tile lie in [halo | tile]; + 3 x 32 alignment slack
 constexpr int kMaxWindows = 64;
 
-static_assert(kThreads % 4 == 0 && kWordsPerThread == 4 && kChunksPerThread * kThreads == kChunks, "");
+static_assert(kThreads % 4 == 0 && (kWordsPerThread == 4 || kWordsPerThread == 2) && kChunksPerThread * kThreads == kChunks, "");
+constexpr uint32_t kBytesPerThread = 32u * kWordsPerThread;   // contiguous bytes a thread ranks
+
+struct NlWords { uint32_t w[kWordsPerThread]; };              // a thread's share of the newline bitmap
 
 struct WinParams {
     const uint8_t* base;     // window base, 16-byte aligned
@@ -89,6 +98,15 @@ struct ResolveParams {
     int32_t batch_size;
     uint32_t lower, upper;       // quality bounds
     unsigned long long* err;     // min over ((global record << 8) | code)
+    // ---- single-pass (fused) launches only ----
+    uint32_t* tile_status;       // kStatusWords words per tile of the window (decoupled look-back)
+    uint32_t* ticket;            // next tile to claim, window-relative; zeroed before the launch
+    uint32_t epoch;              // tags the status words of this launch (never 0, never reused)
+    uint32_t line_cap;           // entries of line_ends
+    ScanOut* scan_out;           // written by the CTA that owns the window's last tile
+    uint32_t* overflow;          // raised when an output would not fit its (estimated) capacity
+    int64_t seq_cap, qual_cap;   // bytes allocated for seq_out / qual_out
+    int64_t rec_cap;             // entries of ends_abs / id_ends_abs / id_spans pairs
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -171,8 +189,26 @@ struct alignas(128) TileSmem {
                                               // nlx[kHead-1-i] = i-th newline before the list
     uint32_t sdst[3][kLinesCap];              // per class stream: destination of each line
     uint32_t ssrc[3][kLinesCap];              //                   source position of each line
+    // ---- single-pass (fused) launches ----
+    BsqPrefix pre;                            // this tile's prefix, from the look-back
+    uint32_t next_tile;                       // the tile this CTA claimed for its next iteration
+    uint32_t first_claim;                     // the tile it claimed at start
+    uint32_t agg_p[4];                        // aggregate of a tile with more than kNlCap newlines
     alignas(128) uint8_t stage[kStage];       // SoA bytes of the pass, laid out like the destination (mod 16):
                                               // [id | seq | qual], written back with TMA bulk stores
+};
+
+// k_summarize: the same front end on its own (double-buffered) ring
+constexpr int kSumStages = 2;
+struct alignas(128) SumSmem {
+    alignas(128) uint8_t data[kSumStages][kHalo + kTile + kTilePad];
+    alignas(8) uint64_t full_bar[kSumStages];
+    uint32_t warp_tot[2][kWarps][4];
+    uint32_t carry[8];
+    uint32_t k1_head[8];                      // [0..3] last four newlines, [4..7] first four
+    uint32_t k1_red[kWarps * 4];
+    alignas(16) uint32_t bm_nl[kWords];
+    uint32_t bm_hi[1], bm_bad[1];             // (never written: build_bitmaps<false, false>)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -193,8 +229,8 @@ __device__ __forceinline__ uint32_t tile_bytes_rounded(const WinParams& W, uint3
     return (n + 15u) & ~15u;  // stays inside the 16-byte granule that holds the last valid byte
 }
 
-template <bool kWithHalo>
-__device__ __forceinline__ void issue_tile_load(TileSmem& S, const WinParams& W, uint32_t tile, uint32_t stage) {
+template <bool kWithHalo, typename SM>
+__device__ __forceinline__ void issue_tile_load(SM& S, const WinParams& W, uint32_t tile, uint32_t stage) {
     const uint32_t bytes = tile_bytes_rounded(W, tile);
     const size_t origin = (size_t)tile * kTile;
     // the halo is the end of the previous tile (an L2 hit: this CTA or its neighbour just read it)
@@ -216,8 +252,8 @@ __device__ __forceinline__ uint32_t mask16(uint32_t f0, uint32_t f1, uint32_t f2
     return m;
 }
 
-template <bool kHi, bool kBad>
-__device__ __forceinline__ void build_bitmaps(TileSmem& S, const TileCursor& c, uint32_t addlo, uint32_t addup) {
+template <bool kHi, bool kBad, typename SM>
+__device__ __forceinline__ void build_bitmaps(SM& S, const TileCursor& c, uint32_t addlo, uint32_t addup) {
     const uint8_t* tile = S.data[c.stage] + kHalo;
     const uint32_t tid = threadIdx.x;
     const uint32_t vlo = c.lo - c.origin, vhi = c.hi - c.origin;  // valid offsets in the tile
@@ -256,7 +292,8 @@ __device__ __forceinline__ void build_bitmaps(TileSmem& S, const TileCursor& c, 
 
 // Exclusive prefix of `v` over the block (in thread order) and the block total.  One barrier:
 // the warp totals are double buffered (`par` alternates between consecutive scans of a CTA).
-__device__ __forceinline__ uint32_t block_exclusive_scan(TileSmem& S, uint32_t v, uint32_t& total, uint32_t& par) {
+template <typename SM>
+__device__ __forceinline__ uint32_t block_exclusive_scan(SM& S, uint32_t v, uint32_t& total, uint32_t& par) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t inc = v;
 #pragma unroll
@@ -305,16 +342,34 @@ __device__ __forceinline__ void block_exclusive_scan3(TileSmem& S, uint32_t v0, 
     t0 = s0; t1 = s1; t2 = s2;
 }
 
-// Visits the newlines of this thread's 128 bytes in order: f(rank, position).  Most 32-byte words
-// hold none, one or two newlines ("\n+\n"): the first and the last set bit are found without a
-// loop; only words with three or more take the loop.
-template <typename F>
-__device__ __forceinline__ void for_each_newline(const uint4& words, uint32_t pos0, uint32_t excl, F&& f) {
-    uint32_t r = excl;
-    const uint32_t w[4] = {words.x, words.y, words.z, words.w};
+template <typename SM>
+__device__ __forceinline__ NlWords load_nl_words(const SM& S, uint32_t tid) {
+    NlWords r;
+    if (kWordsPerThread == 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(&S.bm_nl[tid * 4]);
+        r.w[0] = v.x; r.w[1] = v.y; r.w[kWordsPerThread - 2] = v.z; r.w[kWordsPerThread - 1] = v.w;
+    } else {
+        const uint2 v = *reinterpret_cast<const uint2*>(&S.bm_nl[tid * 2]);
+        r.w[0] = v.x; r.w[1] = v.y;
+    }
+    return r;
+}
+__device__ __forceinline__ uint32_t popc_words(const NlWords& x) {
+    uint32_t n = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint32_t m = w[i];
+    for (int i = 0; i < kWordsPerThread; ++i) n += __popc(x.w[i]);
+    return n;
+}
+
+// Visits the newlines of this thread's bytes in order: f(rank, position).  Most 32-byte words
+// hold none, one or two newlines ("\n+\n"): the first and the last set bit are found without a
+// loop; only words with three or more take the loop.  (k_resolve: the body is one shared store.)
+template <typename F>
+__device__ __forceinline__ void for_each_newline(const NlWords& words, uint32_t pos0, uint32_t excl, F&& f) {
+    uint32_t r = excl;
+#pragma unroll
+    for (int i = 0; i < kWordsPerThread; ++i) {
+        uint32_t m = words.w[i];
         if (m) {
             const uint32_t lsb = m & (0u - m);
             f(r++, pos0 + (31u - __clz(lsb)));
@@ -333,15 +388,29 @@ __device__ __forceinline__ void for_each_newline(const uint4& words, uint32_t po
         pos0 += 32u;
     }
 }
+// The same visit as one plain loop per word (k_summarize: a heavier body, instantiated once).
+template <typename F>
+__device__ __forceinline__ void for_each_newline_loop(const NlWords& words, uint32_t pos0, uint32_t excl, F&& f) {
+    uint32_t r = excl;
+#pragma unroll
+    for (int i = 0; i < kWordsPerThread; ++i) {
+        uint32_t m = words.w[i];
+        while (m) {
+            f(r++, pos0 + (uint32_t)__ffs((int)m) - 1u);
+            m &= m - 1u;
+        }
+        pos0 += 32u;
+    }
+}
 
 // Writes the positions of the local newlines with rank in [pass_base, pass_base + kNlCap) to
 // nlx[kHead + rank - pass_base].  `excl` = rank of the first newline of this thread's 128 bytes.
 // kChecked = false when the whole tile fits one pass (the common case): no bound check per entry.
 template <bool kChecked>
-__device__ __forceinline__ void fill_newline_list(TileSmem& S, const TileCursor& c, const uint4& words,
+__device__ __forceinline__ void fill_newline_list(TileSmem& S, const TileCursor& c, const NlWords& words,
                                                   uint32_t excl, uint32_t pass_base) {
     uint32_t* const list = &S.nlx[kHead];
-    for_each_newline(words, c.origin + threadIdx.x * 128u, excl - pass_base, [&](uint32_t rel, uint32_t p) {
+    for_each_newline(words, c.origin + threadIdx.x * kBytesPerThread, excl - pass_base, [&](uint32_t rel, uint32_t p) {
         if (!kChecked || rel < (uint32_t)kNlCap) list[rel] = p;
     });
 }
@@ -390,23 +459,23 @@ __device__ __forceinline__ TileCursor make_cursor(const WinParams& W, uint32_t t
 
 // kSums = false (views-only passes): only the newline count and the first/last positions of the
 // run are needed; the per-class position sums that give the SoA destinations are skipped.
-// Shared memory: the part of TileSmem before bm_hi (three CTAs per SM).
+// Shared memory: SumSmem.
 template <bool kSums>
 __global__ void __launch_bounds__(kThreads, kSummarizeCtas) k_summarize(const WinParams W, BsqSummary* __restrict__ run_sum) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
+    SumSmem& S = *reinterpret_cast<SumSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x;
     uint32_t ta, tb;
     run_tiles(W, blockIdx.x, ta, tb);
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&S.full_bar[s], 1);
+        for (int s = 0; s < kSumStages; ++s) mbar_init(&S.full_bar[s], 1);
         mbar_fence_init();
     }
     if (tid < 8) S.k1_head[tid] = 0;
     __syncthreads();
     if (tid == 0)
-        for (uint32_t s = 0; s < (uint32_t)kStages && ta + s < tb; ++s) issue_tile_load<false>(S, W, ta + s, s);
+        for (uint32_t s = 0; s < (uint32_t)kSumStages && ta + s < tb; ++s) issue_tile_load<false>(S, W, ta + s, s);
 
     uint32_t run_count = 0;           // newlines of the run so far (uniform)
     uint32_t acc[4] = {0, 0, 0, 0};   // position sums by (index in run) mod 4, this thread's share
@@ -414,18 +483,18 @@ __global__ void __launch_bounds__(kThreads, kSummarizeCtas) k_summarize(const Wi
 
     for (uint32_t t = ta; t < tb; ++t) {
         const uint32_t it = t - ta;
-        const TileCursor c = make_cursor(W, t, it % kStages);
-        mbar_wait(&S.full_bar[c.stage], (it / kStages) & 1u);
+        const TileCursor c = make_cursor(W, t, it % kSumStages);
+        mbar_wait(&S.full_bar[c.stage], (it / kSumStages) & 1u);
         build_bitmaps<false, false>(S, c, 0, 0);
         __syncthreads();
-        const uint4 words = *reinterpret_cast<const uint4*>(&S.bm_nl[tid * 4]);
-        const uint32_t cnt = __popc(words.x) + __popc(words.y) + __popc(words.z) + __popc(words.w);
+        const NlWords words = load_nl_words(S, tid);
+        const uint32_t cnt = popc_words(words);
         uint32_t total;
         const uint32_t excl = block_exclusive_scan(S, cnt, total, par);
         // this thread's newlines: index in the run = run_count + excl + k
         const bool edge = run_count + excl < 4u || excl + cnt + 4u > total;   // among the first / last four
         if (cnt != 0u && (kSums || edge)) {
-            for_each_newline(words, c.origin + tid * 128u, excl, [&](uint32_t r, uint32_t p) {
+            for_each_newline_loop(words, c.origin + tid * kBytesPerThread, excl, [&](uint32_t r, uint32_t p) {
                 if (kSums) {
                     const uint32_t cls = (run_count + r) & 3u;
                     acc[0] += cls == 0u ? p : 0u;
@@ -449,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, kSummarizeCtas) k_summarize(const Wi
         }
         run_count += total;
         __syncthreads();  // every thread is done with data[stage] and the head is updated
-        if (tid == 0 && t + kStages < tb) issue_tile_load<false>(S, W, t + kStages, c.stage);
+        if (tid == 0 && t + kSumStages < tb) issue_tile_load<false>(S, W, t + kSumStages, c.stage);
     }
 
     // block reduction of acc[4]
@@ -549,6 +618,120 @@ __global__ void __launch_bounds__(kScanThreads, 1) k_scan_runs(const BsqSummary*
         uint4* dst = reinterpret_cast<uint4*>(run_pre);
         for (uint32_t i = threadIdx.x; i < n_runs * 2u; i += blockDim.x) dst[i] = src[i];
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// single pass: per-tile status words + decoupled look-back over the rank algebra
+// ------------------------------------------------------------------------------------------------
+//
+// A fused launch reads every tile ONCE: the CTA that claims a tile (in order, through a ticket)
+// publishes the tile's aggregate -- the part of a BsqSummary that bsq_prefix_from / bsq_totals_from
+// read: newline count, last four newline positions, position sums by index mod 4 -- then combines
+// the aggregates of its predecessors back to the nearest tile whose INCLUSIVE state is already
+// published (32 predecessors per round, one per lane), publishes its own inclusive state and
+// resolves the tile in place.  A tile waits only for tiles with smaller tickets, all of which are
+// owned by running CTAs, so the scheme cannot deadlock whatever the residency.
+
+constexpr int kStatusWords = 32;   // 128 bytes per tile: [flag, -, -, -][aggregate: 12 words][inclusive: 12 words][pad]
+constexpr uint32_t kLbAgg = 1u, kLbInc = 2u;
+
+__device__ __forceinline__ LbState lb_shfl_down(const LbState& v, uint32_t d) {
+    LbState o;
+    o.count = __shfl_down_sync(0xFFFFFFFFu, v.count, d);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        o.last[i] = __shfl_down_sync(0xFFFFFFFFu, v.last[i], d);
+        o.P[i] = __shfl_down_sync(0xFFFFFFFFu, v.P[i], d);
+    }
+    return o;
+}
+__device__ __forceinline__ LbState lb_bcast0(const LbState& v) {
+    LbState o;
+    o.count = __shfl_sync(0xFFFFFFFFu, v.count, 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        o.last[i] = __shfl_sync(0xFFFFFFFFu, v.last[i], 0);
+        o.P[i] = __shfl_sync(0xFFFFFFFFu, v.P[i], 0);
+    }
+    return o;
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint32_t* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_v4(uint32_t* p, uint4 v) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// one thread: payload, fence, flag
+__device__ __forceinline__ void lb_publish(uint32_t* status, uint32_t slot, const LbState& v, uint32_t epoch) {
+    uint32_t* pay = status + 4u + (slot == kLbInc ? 12u : 0u);
+    st_relaxed_v4(pay, make_uint4(v.count, v.last[0], v.last[1], v.last[2]));
+    st_relaxed_v4(pay + 4, make_uint4(v.last[3], v.P[0], v.P[1], v.P[2]));
+    st_relaxed_v4(pay + 8, make_uint4(v.P[3], 0u, 0u, 0u));
+    __threadfence();
+    st_release_u32(status, (epoch << 2) | slot);
+}
+__device__ __forceinline__ LbState lb_load(const uint32_t* status, uint32_t slot) {
+    const uint32_t* pay = status + 4u + (slot == kLbInc ? 12u : 0u);
+    const uint4 a = ld_relaxed_v4(pay), b = ld_relaxed_v4(pay + 4), c = ld_relaxed_v4(pay + 8);
+    LbState v;
+    v.count = a.x; v.last[0] = a.y; v.last[1] = a.z; v.last[2] = a.w;
+    v.last[3] = b.x; v.P[0] = b.y; v.P[1] = b.z; v.P[2] = b.w; v.P[3] = c.x;
+    return v;
+}
+
+// Warp-wide: the state before window tile `ti` (0-based within the window) = window init (+) tiles
+// [0, ti).  Lane l looks at tile ti-1-l; tiles before the window are the (inclusive) init state.
+__device__ __forceinline__ LbState lb_look_back(const uint32_t* tile_status, uint32_t ti, uint32_t begin, uint32_t epoch) {
+    const uint32_t lane = threadIdx.x & 31u;
+    LbState E = lb_identity();
+    bool have = false;                              // E holds at least one tile (it is the later operand)
+    int32_t base = (int32_t)ti - 1;
+    while (true) {
+        const int32_t t = base - (int32_t)lane;
+        uint32_t slot = kLbInc;
+        LbState v = lb_identity();
+        if (t < 0) {
+            if (t == -1) v.last[0] = begin - 1u;    // bsq_summary_window_init
+        } else {
+            const uint32_t* st = tile_status + (size_t)t * kStatusWords;
+            uint32_t f, spins = 0;
+            while (((f = ld_acquire_u32(st)) >> 2) != epoch) {
+                if (++spins > (1u << 22)) __trap();  // a predecessor that never publishes must fault, not hang
+                __nanosleep(32);
+            }
+            slot = f & 3u;
+            v = lb_load(st, slot);
+        }
+        const uint32_t inc = __ballot_sync(0xFFFFFFFFu, slot == kLbInc);
+        // lanes 0..nearest take part.  (The window-init state is not a unit of lb_combine on the
+        // right -- its virtual newline would be lost -- so the lanes beyond are left out, not zeroed.)
+        const uint32_t nearest = inc ? (uint32_t)__ffs((int)inc) - 1u : 31u;
+        // ordered reduction: a higher lane is an EARLIER tile
+#pragma unroll
+        for (uint32_t d = 1; d < 32u; d <<= 1) {
+            const LbState o = lb_shfl_down(v, d);
+            if (lane + d <= nearest) v = lb_combine(o, v);
+        }
+        const LbState R = lb_bcast0(v);
+        E = have ? lb_combine(R, E) : R;
+        have = true;
+        if (inc) break;
+        base -= 32;
+    }
+    return E;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -775,24 +958,38 @@ __device__ __forceinline__ void flush_stream(const uint8_t* stage, uint32_t so, 
     }
 }
 
-template <bool kAscii, bool kQual, bool kOffsets, bool kPack>
+// kFused = false: the second pass of the two-pass path (run prefixes from k_summarize + k_scan_runs,
+//                 one CTA per run).
+// kFused = true:  the single pass.  Persistent CTAs claim tiles in order; every tile gets its prefix
+//                 from the decoupled look-back above, so the input is read once.  The number of
+//                 complete records is not known in advance: the window's trailing incomplete record is
+//                 treated like any other (its bytes land past the counted totals, its error reports
+//                 carry a record index that the host ignores, its bases are taken back at the end).
+template <bool kAscii, bool kQual, bool kOffsets, bool kPack, bool kFused>
 __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinParams W, const ResolveParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x;
-    uint32_t ta, tb;
-    run_tiles(W, blockIdx.x, ta, tb);
-    const BsqPrefix pre = P.run_pre[blockIdx.x];
+    uint32_t ta = 0, tb = 0;
+    BsqPrefix pre;
+    if (kFused) {
+        pre.rank = 0; pre.prev[0] = pre.prev[1] = pre.prev[2] = 0; pre.cum_seq = pre.cum_qual = pre.cum_id = 0; pre._pad = 0;
+    } else {
+        run_tiles(W, blockIdx.x, ta, tb);
+        pre = P.run_pre[blockIdx.x];
+    }
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&S.full_bar[s], 1);
         mbar_fence_init();
         S.nlx[0] = 0; S.nlx[1] = pre.prev[2]; S.nlx[2] = pre.prev[1]; S.nlx[3] = pre.prev[0];
+        if (kFused) S.first_claim = W.first_tile + atomicAdd(P.ticket, 1u);
     }
     __syncthreads();
+    if (kFused) { ta = S.first_claim; tb = W.n_tiles; }
     if (tid == 0)
         for (uint32_t s = 0; s < (uint32_t)kStages && ta + s < tb; ++s) issue_tile_load<true>(S, W, ta + s, s);
-    if (kOffsets && blockIdx.x == 0 && tid == 0) P.line_ends[0] = W.begin - 1u;
+    if (kOffsets && tid == 0 && (kFused ? ta == W.first_tile : blockIdx.x == 0)) P.line_ends[0] = W.begin - 1u;
 
     const uint32_t addlo = (128u - P.lower) * 0x01010101u, addup = (127u - P.upper) * 0x01010101u;
     uint32_t bases_acc = 0;                                              // this thread's share of sum(seq_len)
@@ -806,29 +1003,103 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
     uint8_t* const out_seq = kPack ? P.seq_out + (P.seq_base64 - sh_seq) : nullptr;
     uint8_t* const out_qual = kPack ? P.qual_out + (P.qual_base64 - sh_qual) : nullptr;
     const uint32_t bsz = (uint32_t)P.batch_size;
+    // window-local index of the next record that closes a batch (uniform; advanced as the run proceeds)
+    uint32_t edge_k = (pre.rank >> 2) + (bsz - 1u - (P.rec_mod + (pre.rank >> 2)) % bsz);
+    const uint32_t n_complete = kFused ? 0xFFFFFFFFu : P.n_complete;
 
-    for (uint32_t t = ta; t < tb; ++t) {
-        const uint32_t it = t - ta;
+    for (uint32_t t = ta, it = 0; t < tb; ++it) {
         const TileCursor c = make_cursor(W, t, it % kStages);
         mbar_wait(&S.full_bar[c.stage], (it / kStages) & 1u);
-        if (kStages == 1 && tid == 0 && t + 1u < tb)   // single buffer: the next tile waits in L2
+        if (kFused) {
+            if (tid == 0) {                            // claim the next tile now: it waits in L2 when this one is done
+                const uint32_t nt = W.first_tile + atomicAdd(P.ticket, 1u);
+                S.next_tile = nt;
+                if (nt < tb) prefetch_l2(W.base + (size_t)nt * kTile, tile_bytes_rounded(W, nt));
+            }
+            if (tid < 4) S.agg_p[tid] = 0;
+        } else if (kStages == 1 && tid == 0 && t + 1u < tb) {   // single buffer: the next tile waits in L2
             prefetch_l2(W.base + (size_t)(t + 1u) * kTile, tile_bytes_rounded(W, t + 1u));
+        }
         build_bitmaps<kAscii, kQual>(S, c, addlo, addup);
         __syncthreads();
-        const uint4 words = *reinterpret_cast<const uint4*>(&S.bm_nl[tid * 4]);
-        const uint32_t cnt = __popc(words.x) + __popc(words.y) + __popc(words.z) + __popc(words.w);
+        const uint32_t t_next = kFused ? S.next_tile : t + 1u;
+        const NlWords words = load_nl_words(S, tid);
+        const uint32_t cnt = popc_words(words);
         uint32_t total;
         const uint32_t excl = block_exclusive_scan(S, cnt, total, par);
+
+        if (kFused) {
+            // ---- the tile's aggregate, the look-back, the tile's prefix --------------------------
+            const bool one_pass = total <= (uint32_t)kNlCap;
+            if (one_pass) {
+                fill_newline_list<false>(S, c, words, excl, 0u);
+            } else {                                   // rare: position sums straight from the bitmap
+                uint32_t acc[4] = {0, 0, 0, 0};
+                for_each_newline_loop(words, c.origin + tid * kBytesPerThread, excl, [&](uint32_t r, uint32_t p) {
+                    const uint32_t cls = r & 3u;
+                    acc[0] += cls == 0u ? p : 0u; acc[1] += cls == 1u ? p : 0u;
+                    acc[2] += cls == 2u ? p : 0u; acc[3] += cls == 3u ? p : 0u;
+                    if (r + 4u >= total) S.carry[total - 1u - r] = p;      // carry[i] = i-th most recent
+                });
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (acc[k] != 0u) atomicAdd(&S.agg_p[k], acc[k]);
+            }
+            __syncthreads();
+            if (tid < 32u) {
+                const uint32_t lane = tid;
+                LbState mine = lb_identity();
+                mine.count = total;
+                if (one_pass) {
+                    uint32_t a = 0;
+                    for (uint32_t j = lane; j < total; j += 32u) a += S.nlx[kHead + j];   // index mod 4 == lane mod 4
+                    a += __shfl_xor_sync(0xFFFFFFFFu, a, 4);
+                    a += __shfl_xor_sync(0xFFFFFFFFu, a, 8);
+                    a += __shfl_xor_sync(0xFFFFFFFFu, a, 16);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        mine.P[k] = __shfl_sync(0xFFFFFFFFu, a, k);
+                        mine.last[k] = (uint32_t)k < total ? S.nlx[kHead + total - 1u - (uint32_t)k] : 0u;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { mine.P[k] = S.agg_p[k]; mine.last[k] = S.carry[k]; }
+                }
+                const uint32_t ti = t - W.first_tile;
+                uint32_t* const my_status = P.tile_status + (size_t)ti * kStatusWords;
+                if (lane == 0 && ti != 0u) lb_publish(my_status, kLbAgg, mine, P.epoch);
+                const LbState E = lb_look_back(P.tile_status, ti, W.begin, P.epoch);
+                const LbState I = lb_combine(E, mine);
+                if (lane == 0) {
+                    lb_publish(my_status, kLbInc, I, P.epoch);
+                    const BsqPrefix q = bsq_prefix_from(lb_to_summary(E), W.begin);
+                    S.pre = q;
+                    S.nlx[0] = 0; S.nlx[1] = q.prev[2]; S.nlx[2] = q.prev[1]; S.nlx[3] = q.prev[0];
+                    if (t + 1u == tb) {                // the window's last tile: totals for the host
+                        const BsqSummary end = lb_to_summary(I);
+                        P.scan_out->totals = bsq_totals_from(end, W.begin);
+                        P.scan_out->end_state = end;
+                        P.scan_out->region = bsq_summary_identity();
+                        // the sequence line of the trailing incomplete record was counted: take it back
+                        const uint32_t rem = I.count & 3u;
+                        if (rem >= 2u) atomicAdd(P.bases, 0ull - (unsigned long long)(I.last[rem - 2u] - I.last[rem - 1u] - 1u));
+                    }
+                }
+            }
+            __syncthreads();
+            const BsqPrefix q = S.pre;
+            rank = q.rank; cum_id = q.cum_id; cum_seq = q.cum_seq; cum_qual = q.cum_qual;
+            edge_k = (rank >> 2) + (bsz - 1u - (P.rec_mod + (rank >> 2)) % bsz);
+        }
 
         // ---- validation from the bitmaps: this thread's 128 bytes, line class known from the rank
         if (kAscii || kQual) {
             uint32_t r = rank + excl;
-            const uint32_t nlw[4] = {words.x, words.y, words.z, words.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t nl = nlw[i];
-                const uint32_t hiw = kAscii ? S.bm_hi[tid * 4 + i] : 0u;
-                const uint32_t badw = kQual ? (S.bm_bad[tid * 4 + i] & ~nl) : 0u;
+            for (int i = 0; i < kWordsPerThread; ++i) {
+                const uint32_t nl = words.w[i];
+                const uint32_t hiw = kAscii ? S.bm_hi[tid * kWordsPerThread + i] : 0u;
+                const uint32_t badw = kQual ? (S.bm_bad[tid * kWordsPerThread + i] & ~nl) : 0u;
                 if ((hiw | badw) != 0u) {
                     uint32_t rest = 0xFFFFFFFFu, m = nl, rr = r;
                     while (rest) {
@@ -836,7 +1107,7 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
                         uint32_t seg = rest;
                         if (m) { const uint32_t b = __ffs(m) - 1u; seg = rest & (0xFFFFFFFFu >> (31u - b)); m &= m - 1u; }
                         const uint32_t cls = rr & 3u, k = rr >> 2;
-                        if (k < P.n_complete) {
+                        if (k < n_complete) {
                             if (kAscii && cls != 2u && (hiw & seg)) report(P, k, 4u);
                             if (kQual && cls == 3u && (badw & seg)) report(P, k, 5u);
                         }
@@ -850,9 +1121,14 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
 
         for (uint32_t pass = 0; pass < total; pass += kNlCap) {
             const uint32_t n = total - pass < (uint32_t)kNlCap ? total - pass : (uint32_t)kNlCap;
-            if (total <= (uint32_t)kNlCap) fill_newline_list<false>(S, c, words, excl, 0u);
-            else fill_newline_list<true>(S, c, words, excl, pass);
-            __syncthreads();
+            if (!kFused) {
+                if (total <= (uint32_t)kNlCap) fill_newline_list<false>(S, c, words, excl, 0u);
+                else fill_newline_list<true>(S, c, words, excl, pass);
+                __syncthreads();
+            } else if (total > (uint32_t)kNlCap) {     // (a one-pass tile filled its list before the look-back)
+                fill_newline_list<true>(S, c, words, excl, pass);
+                __syncthreads();
+            }
             const uint32_t r0 = rank + pass;  // rank of list entry 0
             const uint32_t d0_id = cum_id, d0_seq = cum_seq, d0_qual = cum_qual;
             // first list entry of each class and the number of lines per class in this pass
@@ -862,10 +1138,17 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
             const uint32_t n_qual = j_qual < n ? ((n - 1u - j_qual) >> 2) + 1u : 0u;
             // does a batch boundary fall among the records that end in this pass?  (uniform)
             const uint32_t k_first = r0 >> 2, k_last = (r0 + n - 1u) >> 2;
-            const bool batch_edge = kPack && (P.rec_mod + k_first) / bsz != (P.rec_mod + k_last + 1u) / bsz;
+            while (edge_k < k_first) edge_k += bsz;
+            const bool batch_edge = kPack && edge_k <= k_last;
+
+            // single pass: the outputs were sized from estimates; what does not fit is dropped and the
+            // host repeats the region with the two-pass path (exact sizes)
+            const bool rec_ok = !kFused || P.rec_base + (int64_t)k_last < P.rec_cap;
+            const bool line_ok = !kFused || 1u + r0 + n <= P.line_cap;
+            if (kFused && tid == 0 && (!rec_ok || (kOffsets && !line_ok))) *P.overflow = 1u;
 
             // views(): the line-end table, one coalesced store per newline
-            if (kOffsets)
+            if (kOffsets && line_ok)
                 for (uint32_t j = tid; j < n; j += kThreads) P.line_ends[1u + r0 + j] = S.nlx[kHead + j];
 
             // one thread per RECORD: it handles the (up to four) lines of its record that end in this
@@ -877,7 +1160,7 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
                 const uint32_t t = tb0 + tid;
                 const uint32_t k = k_first + t;
                 const bool mine = t < n_rec;
-                const bool live = mine && k < P.n_complete;
+                const bool live = mine && k < n_complete;
                 const int32_t j0 = (int32_t)(4u * k - r0);                 // list index of the header's newline
                 const uint32_t* e = &S.nlx[kHead] + j0;                    // e[c] = newline of class c, e[-1] = the one before
                 const bool has0 = mine && j0 >= 0 && j0 < (int32_t)n, has1 = mine && j0 + 1 >= 0 && j0 + 1 < (int32_t)n,
@@ -898,7 +1181,7 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
                             nid = z - a;
                             if (kPack && P.id_fast) *P.strip_flag = 1u;   // the optimistic id packing is void
                         }
-                        if (kOffsets || (kPack && !P.id_fast)) { P.id_spans[2u * k] = a; P.id_spans[2u * k + 1u] = nid; }
+                        if ((kOffsets || (kPack && !P.id_fast)) && rec_ok) { P.id_spans[2u * k] = a; P.id_spans[2u * k + 1u] = nid; }
                         if (len > max_len) max_len = len;
                     }
                     l_id = nid; s_id = a;
@@ -925,7 +1208,7 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
                     if (has0) {
                         const uint32_t i = (uint32_t)(j0 - (int32_t)j_id) >> 2;
                         S.sdst[0][i] = cum_id + e_id + sh_id; S.ssrc[0][i] = s_id;
-                        if (live && P.id_fast) {
+                        if (live && P.id_fast && rec_ok) {
                             const int64_t endv = P.id_base64 + (int64_t)(cum_id + e_id + l_id);
                             P.id_ends_abs[P.rec_base + (int64_t)k] = endv;
                             if (batch_edge) { const uint32_t tb1 = P.rec_mod + k + 1u;
@@ -939,7 +1222,7 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
                     if (has3) {
                         const uint32_t i = (uint32_t)(j0 + 3 - (int32_t)j_qual) >> 2;
                         S.sdst[2][i] = cum_qual + e_qual + sh_qual; S.ssrc[2][i] = s_qual;
-                        if (live) {
+                        if (live && rec_ok) {
                             const int64_t endv = P.qual_base64 + (int64_t)(cum_qual + e_qual + l_qual);
                             P.ends_abs[P.rec_base + (int64_t)k] = endv;
                             if (batch_edge) { const uint32_t tb1 = P.rec_mod + k + 1u;
@@ -958,17 +1241,25 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
                     S.ssrc[tid][nn] = c.origin + 16u; S.ssrc[tid][nn + 1] = c.origin + 16u;
                 }
                 if (tid == 0) tma_store_wait_read();   // the previous pass's bulk stores have read `stage`
-                __syncthreads();
+                // one barrier: the line tables are complete, every reader of the newline list is done;
+                // long lines (long reads, or a line that began far before the tile) are copied
+                // vector-parallel from wherever they lie, otherwise the pass is staged in shared memory
+                const bool long_lines = __syncthreads_or(max_len > (uint32_t)kHalo - 64u) != 0;
+                rotate_head(S, n);                     // (thread 0; next read after the barrier that ends the copy)
                 // room: bytes the id arena can still take.  Destinations past it only arise after a
                 // structure error (an empty header line makes the id prefix diverge); nothing there counts.
                 const uint32_t ra_id = d0_id + sh_id, rb_id = cum_id + sh_id;
                 const bool do_id = P.id_fast && rb_id > ra_id && (int64_t)rb_id <= P.id_cap - (P.id_base64 - sh_id) && n_id != 0u;
                 const uint32_t ra_seq = d0_seq + sh_seq, rb_seq = cum_seq + sh_seq;
                 const uint32_t ra_qual = d0_qual + sh_qual, rb_qual = cum_qual + sh_qual;
-                // long lines (long reads, or a line that began far before the tile) are copied
-                // vector-parallel from wherever they lie; otherwise the pass is staged in shared memory
-                const bool long_lines = __syncthreads_or(max_len > (uint32_t)kHalo - 64u) != 0;
-                const bool ok_seq = rb_seq > ra_seq, ok_qual = rb_qual > ra_qual;
+                bool ok_seq = rb_seq > ra_seq, ok_qual = rb_qual > ra_qual;
+                if (kFused) {
+                    const bool fit_seq = (int64_t)rb_seq <= P.seq_cap - (P.seq_base64 - sh_seq);
+                    const bool fit_qual = (int64_t)rb_qual <= P.qual_cap - (P.qual_base64 - sh_qual);
+                    const bool fit_id = !P.id_fast || n_id == 0u || rb_id <= ra_id || do_id;
+                    if (tid == 0 && !(fit_seq && fit_qual && fit_id)) *P.overflow = 1u;
+                    ok_seq = ok_seq && fit_seq; ok_qual = ok_qual && fit_qual;
+                }
                 if (long_lines || (P.debug_skip & 4u)) {
                     StreamJob jobs[3];
                     jobs[0] = StreamJob{S.sdst[0], S.ssrc[0], n_id, ra_id, do_id ? rb_id : ra_id, out_id};
@@ -987,7 +1278,10 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
                             else copy_line(S, c, W, jobs[0], w - n1 - n2);
                         }
                     }
-                } else if (!(P.debug_skip & 1u)) {
+                    __syncthreads();
+                } else if (P.debug_skip & 1u) {
+                    __syncthreads();
+                } else {
                     // stage layout: [id | seq | qual], each region starts at the 16-byte vector of its
                     // first destination byte; lengths are bounded by the bytes of [halo | tile]
                     const uint32_t A_id = ra_id & ~15u, A_seq = ra_seq & ~15u, A_qual = ra_qual & ~15u;
@@ -1014,14 +1308,21 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
                     if (ok_qual) flush_stream(S.stage, so_qual, ra_qual, rb_qual, out_qual, tid == 0, wsel == 2u);
                     if (tid == 0) tma_store_commit();
                 }
+            } else {
+                __syncthreads();
+                rotate_head(S, n);
+                if (pass + (uint32_t)kNlCap < total) __syncthreads();   // the next pass refills the list
             }
-            __syncthreads();
-            rotate_head(S, n);
-            __syncthreads();
         }
         rank += total;
         if (total == 0u) __syncthreads();   // (the pass loop ends with a barrier otherwise)
-        if (tid == 0 && t + kStages < tb) issue_tile_load<true>(S, W, t + kStages, c.stage);
+        if (kFused) {
+            if (tid == 0 && t_next < tb) issue_tile_load<true>(S, W, t_next, c.stage);
+            t = t_next;
+        } else {
+            if (tid == 0 && t + kStages < tb) issue_tile_load<true>(S, W, t + kStages, c.stage);
+            ++t;
+        }
     }
     if (kPack && tid == 0) tma_store_wait_all();   // shared memory must outlive the bulk stores
     // one atomic per warp: the run's share of the base count

@@ -124,6 +124,41 @@ BSQ_HD BsqTotals bsq_totals_from(const BsqSummary& E_end, uint32_t begin) {
     return t;
 }
 
+// ---- the part of a BsqSummary that crosses tiles in the single-pass kernel (decoupled look-back) ----
+// count, the last four newline positions and the position sums: what bsq_prefix_from and
+// bsq_totals_from read.  lb_combine is bsq_combine restricted to those fields, branch-free.
+// NOTE: the window-init state (count 0, last[0] = begin-1) is only valid as the LEFTMOST operand.
+struct LbState { uint32_t count, last[4], P[4]; };
+
+BSQ_HD LbState lb_identity() {
+    LbState s;
+    s.count = 0;
+    for (int i = 0; i < 4; ++i) { s.last[i] = 0; s.P[i] = 0; }
+    return s;
+}
+// a followed by b
+BSQ_HD LbState lb_combine(const LbState& a, const LbState& b) {
+    LbState r;
+    r.count = a.count + b.count;
+    const uint32_t cb = b.count < 4u ? b.count : 4u;
+    r.last[0] = cb > 0u ? b.last[0] : a.last[0];
+    r.last[1] = cb > 1u ? b.last[1] : (cb == 1u ? a.last[0] : a.last[1]);
+    r.last[2] = cb > 2u ? b.last[2] : (cb == 2u ? a.last[0] : (cb == 1u ? a.last[1] : a.last[2]));
+    r.last[3] = cb > 3u ? b.last[3] : (cb == 3u ? a.last[0] : (cb == 2u ? a.last[1] : (cb == 1u ? a.last[2] : a.last[3])));
+    // r.P[k] = a.P[k] + b.P[(k - a.count) mod 4]: rotate b.P right by (a.count & 3)
+    uint32_t q0 = b.P[0], q1 = b.P[1], q2 = b.P[2], q3 = b.P[3];
+    if (a.count & 1u) { const uint32_t t = q3; q3 = q2; q2 = q1; q1 = q0; q0 = t; }
+    if (a.count & 2u) { uint32_t t = q0; q0 = q2; q2 = t; t = q1; q1 = q3; q3 = t; }
+    r.P[0] = a.P[0] + q0; r.P[1] = a.P[1] + q1; r.P[2] = a.P[2] + q2; r.P[3] = a.P[3] + q3;
+    return r;
+}
+BSQ_HD BsqSummary lb_to_summary(const LbState& v) {
+    BsqSummary s = bsq_summary_identity();
+    s.count = v.count;
+    for (int i = 0; i < 4; ++i) { s.last[i] = v.last[i]; s.P[i] = v.P[i]; }
+    return s;
+}
+
 // is_posix_space, utils.mojo:266-289: {9,10,11,12,13,28,29,30,32}
 BSQ_HD bool bsq_is_space(uint32_t c) {
     return c == 32u || (c < 32u && ((0x70003E00u >> c) & 1u));

@@ -93,6 +93,76 @@ int64_t tm_parse(const uint8_t* d, uint32_t begin, uint32_t end, uint32_t run_by
     return tot.records;
 }
 
+// The single-pass kernel's decoupled look-back (bsq_device.cuh: lb_look_back), lane by lane: tile
+// `ti` combines 32 predecessors per round, nearest first, up to the nearest one whose INCLUSIVE state
+// is published (`inc_every`: every n-th tile counts as published-inclusive; 0 = none, so that the
+// walk reaches the window-init state).  Returns the number of tiles whose prefix or whose inclusive
+// state differs from the sequential scan (0 = the algebra holds).
+int64_t tm_lookback_check(const uint8_t* d, uint32_t begin, uint32_t end, uint32_t tile_bytes, uint32_t inc_every) {
+    if (tile_bytes == 0) tile_bytes = 1;
+    std::vector<LbState> agg, inc;
+    std::vector<BsqPrefix> want;
+    BsqSummary E = bsq_summary_window_init(begin);
+    for (uint64_t a = (begin / tile_bytes) * (uint64_t)tile_bytes; a < end; a += tile_bytes) {
+        const uint32_t l = a < begin ? begin : (uint32_t)a;
+        const uint32_t h = a + tile_bytes < end ? (uint32_t)(a + tile_bytes) : end;
+        const BsqSummary s = summarize(d, l, h);
+        LbState v = lb_identity();
+        v.count = s.count;
+        for (int i = 0; i < 4; ++i) { v.last[i] = s.last[i]; v.P[i] = s.P[i]; }
+        agg.push_back(v);
+        want.push_back(bsq_prefix_from(E, begin));
+        E = bsq_combine(E, s);
+        LbState w = lb_identity();
+        w.count = E.count;
+        for (int i = 0; i < 4; ++i) { w.last[i] = E.last[i]; w.P[i] = E.P[i]; }
+        inc.push_back(w);
+    }
+    int64_t bad = 0;
+    for (size_t ti = 0; ti < agg.size(); ++ti) {
+        LbState acc = lb_identity();
+        bool have = false;
+        int64_t base = (int64_t)ti - 1;
+        while (true) {
+            LbState v[32];
+            uint32_t incmask = 0;
+            for (int lane = 0; lane < 32; ++lane) {
+                const int64_t t = base - lane;
+                v[lane] = lb_identity();
+                if (t < 0) {
+                    incmask |= 1u << lane;
+                    if (t == -1) v[lane].last[0] = begin - 1u;
+                } else if (inc_every != 0 && (uint64_t)t % inc_every == 0) {
+                    incmask |= 1u << lane;
+                    v[lane] = inc[(size_t)t];
+                } else {
+                    v[lane] = agg[(size_t)t];
+                }
+            }
+            const uint32_t nearest = incmask ? (uint32_t)__builtin_ctz(incmask) : 31u;
+            for (uint32_t dd = 1; dd < 32u; dd <<= 1) {
+                LbState nv[32];
+                for (uint32_t lane = 0; lane < 32u; ++lane)
+                    nv[lane] = (lane + dd <= nearest) ? lb_combine(v[lane + dd], v[lane]) : v[lane];
+                for (uint32_t lane = 0; lane < 32u; ++lane) v[lane] = nv[lane];
+            }
+            acc = have ? lb_combine(v[0], acc) : v[0];
+            have = true;
+            if (incmask) break;
+            base -= 32;
+        }
+        const BsqPrefix got = bsq_prefix_from(lb_to_summary(acc), begin);
+        const LbState I = lb_combine(acc, agg[ti]);
+        bool ok = memcmp(&got, &want[ti], sizeof got) == 0 && I.count == inc[ti].count;
+        for (int i = 0; i < 4; ++i) {
+            ok = ok && I.P[i] == inc[ti].P[i];
+            if ((uint32_t)i < I.count + 1u) ok = ok && I.last[i] == inc[ti].last[i];   // +1: the virtual newline
+        }
+        if (!ok) ++bad;
+    }
+    return bad;
+}
+
 // 64-byte BsqSummary of d[lo, hi) with shard-relative positions (what bsq_summarize_device returns)
 void tm_summarize(const uint8_t* d, uint32_t lo, uint32_t hi, uint32_t* out16) {
     BsqSummary s = summarize(d + lo, 0, hi - lo);

@@ -248,6 +248,29 @@ def test_long_reads_span_tiles(U, oracle):
     U.check_stream(oracle, bytes(bad), batch_size=4, check_ascii=True)
 
 
+@pytest.mark.parametrize("mutate", ["none", "crlf", "noise", "notail"])
+def test_single_pass_lookback_kernel(U, B, oracle, mutate, monkeypatch):
+    """BSQ_SINGLE_PASS=1 selects k_resolve<..., kFused>: tiles claimed in order, prefixes from the
+    decoupled look-back, outputs sized from estimates (with the two-pass path as the overflow
+    fallback).  Same bit-exact bar as the default two-pass path."""
+    monkeypatch.setenv("BSQ_SINGLE_PASS", "1")
+    rng = np.random.default_rng(abs(hash("sp" + mutate)) % 2**32)
+    for val in (False, True):
+        gpu = B.GpuParser(val, val, B.parse_schema("generic"), 64, buffer_growth_enabled=True)
+        for trial in range(3):
+            data = _rand_stream(rng, int(rng.integers(1, 3000)), mutate)
+            U.check_stream(oracle, data, check_ascii=val, check_quality=val, batch_size=64, growth=True, gpu=gpu,
+                           want=(3, 1, 2)[trial % 3])
+        gpu.close()
+    if mutate == "none":
+        U.check_stream(oracle, oracle.synth(20000, 75, 300, 2, 40, "sanger"), batch_size=4096, check_ascii=True,
+                       check_quality=True)
+        U.check_stream(oracle, b"@ab\nA\n+\nI\n" * 40000, batch_size=1000)      # > kNlCap newlines per tile
+        U.check_stream(oracle, b"\n" * 100000, batch_size=16)                     # estimates overflow -> two-pass fallback
+        seq = bytes(rng.choice(list(b"ACGT"), 70000).astype(np.uint8))
+        U.check_stream(oracle, b"@long\n" + seq + b"\n+\n" + b"I" * 70000 + b"\n@s\nAC\n+\nII\n", batch_size=3)
+
+
 def test_id_strip_paths_agree(U, oracle):
     """CRLF and padded ids take the strip pipeline; forcing it on clean input changes nothing."""
     rng = np.random.default_rng(5)

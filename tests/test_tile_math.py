@@ -125,3 +125,25 @@ def test_is_space_and_byte_lane_flags(tm):
                         int(sel.sum()))
     for lo, up in ((33, 126), (59, 126), (64, 126), (66, 126)):
         assert tm.tm_check_flags(words.ctypes.data, words.size, lo, up) == 0
+
+
+@pytest.mark.parametrize("mutate", ["none", "noise", "blank", "notail"])
+def test_decoupled_lookback_algebra(tm, mutate):
+    """The single-pass kernel's look-back (tile aggregates combined 32 per round back to the nearest
+    published inclusive state, or to the window-init state) gives every tile the prefix of the
+    sequential scan, whatever the tile size and whichever predecessors are already inclusive."""
+    tm.tm_lookback_check.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    tm.tm_lookback_check.restype = C.c_int64
+    rng = np.random.default_rng(abs(hash("lb" + mutate)) % 2**32)
+    for trial in range(30):
+        data = _rand_stream(rng, int(rng.integers(0, 60)), mutate)
+        pad = int(rng.integers(0, 40))
+        buf = np.frombuffer(b"\xaa" * pad + data, np.uint8)
+        for tile in (1, 3, 16, 61, 4096):
+            for inc_every in (0, 1, 2, 5, 33, 40):
+                assert tm.tm_lookback_check(buf.ctypes.data, pad, buf.size, tile, inc_every) == 0, (trial, tile, inc_every)
+    for data in (b"\n" * 300, b"A" * 300, b"@\n\n+\n\n" * 50):
+        buf = np.frombuffer(data, np.uint8)
+        for tile in (1, 2, 7, 64):
+            for inc_every in (0, 3, 32):
+                assert tm.tm_lookback_check(buf.ctypes.data, 0, buf.size, tile, inc_every) == 0
