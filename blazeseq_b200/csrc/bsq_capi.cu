@@ -147,16 +147,19 @@ void set_plain_error(bsq_error* e, int code, const char* text) {
     m.str(text);
 }
 
-size_t smem_bytes() { return sizeof(TileSmem) + 128; }                      // k_resolve: kResolveCtas / SM
+// k_resolve: kResolveCtas / SM when it packs; without the SoA stage (views, count/validate-only) kViewCtas / SM
+size_t smem_bytes(bool pack = true, bool validate = true) {
+    if (pack) return sizeof(TileSmem) + 128;
+    return offsetof(TileSmem, stage) + (validate ? 2 * kWords * 4 : 0) + 128;
+}
 size_t smem_bytes_summarize() { return sizeof(SumSmem) + 128; }   // k_summarize: kSummarizeCtas / SM
-size_t smem_bytes_scan(uint32_t n_runs) { return (size_t)n_runs * (sizeof(BsqSummary) + sizeof(BsqPrefix)) + kScanThreads * sizeof(BsqSummary); }
 
 template <typename K>
 cudaError_t opt_in_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-void plan_window(bsq_parser* p, Window& w, const uint8_t* first_byte, uint64_t bytes) {
+void plan_window(bsq_parser* p, Window& w, const uint8_t* first_byte, uint64_t bytes, bool pack) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(first_byte);
     const uintptr_t al = a & ~uintptr_t(15);
     w.base = reinterpret_cast<const uint8_t*>(al);
@@ -167,9 +170,8 @@ void plan_window(bsq_parser* p, Window& w, const uint8_t* first_byte, uint64_t b
     w.wp.n_tiles = (w.wp.end + kTile - 1) / kTile;
     uint32_t tiles = w.wp.n_tiles - w.wp.first_tile;
     if (tiles == 0) tiles = 1, w.wp.n_tiles = w.wp.first_tile + 1;
-    // runs per window: a whole number of waves for both kernels (kResolveCtas and kSummarizeCtas
-    // resident CTAs per SM): lcm(4, 6) = 12 per SM
-    uint32_t max_runs = (uint32_t)std::min<int>(12 * p->sm_count, kMaxRuns);
+    // runs per window: a whole number of waves for the dominant kernel of the pass
+    uint32_t max_runs = (uint32_t)std::min<int>((pack ? kRunsPerSmPack : kRunsPerSmView) * p->sm_count, kMaxRuns);
     uint32_t runs = std::min(tiles, max_runs);
     w.wp.tiles_per_run = (tiles + runs - 1) / runs;
     w.wp.n_runs = (tiles + w.wp.tiles_per_run - 1) / w.wp.tiles_per_run;
@@ -203,7 +205,6 @@ ResolveKernel pick_resolve(bool ascii, bool qual, bool offs, bool pack, bool fus
 bsq_status setup_kernels(bsq_parser* p) {
     CK(opt_in_smem(k_summarize<true>, smem_bytes_summarize()));
     CK(opt_in_smem(k_summarize<false>, smem_bytes_summarize()));
-    CK(opt_in_smem(k_scan_runs, smem_bytes_scan(kMaxRuns)));
     for (int i = 0; i < 16; ++i) {
         CK(opt_in_smem(pick_resolve(i & 8, i & 4, i & 2, i & 1), smem_bytes()));
         if (kStages == 1) CK(opt_in_smem(pick_resolve(i & 8, i & 4, i & 2, i & 1, true), smem_bytes()));
@@ -218,7 +219,7 @@ bsq_status summarize_window(bsq_parser* p, Window& w, bool sums) {
     CK(p->scan_out.ensure(sizeof(ScanOut)));
     if (sums) k_summarize<true><<<w.wp.n_runs, kThreads, smem_bytes_summarize(), p->stream>>>(w.wp, p->run_sum.as<BsqSummary>());
     else k_summarize<false><<<w.wp.n_runs, kThreads, smem_bytes_summarize(), p->stream>>>(w.wp, p->run_sum.as<BsqSummary>());
-    k_scan_runs<<<1, kScanThreads, smem_bytes_scan(w.wp.n_runs), p->stream>>>(p->run_sum.as<BsqSummary>(), w.wp.n_runs, w.wp.begin,
+    k_scan_runs<<<1, kScanThreads, 0, p->stream>>>(p->run_sum.as<BsqSummary>(), w.wp.n_runs, w.wp.begin,
                                           w.run_pre.as<BsqPrefix>(), p->scan_out.as<ScanOut>());
     p->n_launches += 2;
     CK(cudaGetLastError());
@@ -378,6 +379,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     }
     const bool fused = fused_kern != nullptr;
     p->last_pass_fused = fused;
+    const size_t smem_res = smem_bytes(want_pack, cfg.check_ascii || cfg.check_quality);
     CK(cudaEventRecord(p->ev[0], p->stream));
 
     bool id_fast = cfg.force_id_slow_path == 0;   // optimistic: k_resolve raises the strip flag when an id needs stripping
@@ -455,8 +457,8 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         }
         if (want_offs) CK(w.line_ends.ensure(4ull * ((size_t)(w.wp.end - w.wp.begin) / 12 + 1024), 1 << 16));
         ResolveParams P = make_params(w);
-        const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)(kResolveCtas * p->sm_count));
-        fused_kern<<<grid, kThreads, smem_bytes(), p->stream>>>(w.wp, P);
+        const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)((want_pack ? kResolveCtas : kViewCtas) * p->sm_count));
+        fused_kern<<<grid, kThreads, smem_res, p->stream>>>(w.wp, P);
         p->n_launches += 1;
         CK(cudaGetLastError());
         return BSQ_OK;
@@ -482,7 +484,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
             const uint64_t bytes = std::min<uint64_t>(n - pos, window_bytes);
             bsq_status st = feed.ready_upto(pos + bytes);
             if (st != BSQ_OK) return st;
-            plan_window(p, w, d + pos, bytes);
+            plan_window(p, w, d + pos, bytes, want_pack);
             w.region_off = pos;
             w.rec_base = nrec0; w.seq_base = nseq0; w.qual_base = nqual0; w.id_base = nid0;
             st = launch_fused(w);
@@ -515,7 +517,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         const uint64_t bytes = std::min<uint64_t>(n - pos, window_bytes);
         bsq_status st = feed.ready_upto(pos + bytes);
         if (st != BSQ_OK) return st;
-        plan_window(p, w, d + pos, bytes);
+        plan_window(p, w, d + pos, bytes, want_pack);
         w.region_off = pos;
         st = summarize_window(p, w, want_pack);
         if (st != BSQ_OK) return st;
@@ -615,7 +617,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         Window& w = p->win[i];
         if (want_offs) CK(w.line_ends.ensure(4ull * ((size_t)w.scan.totals.newlines + 2), 1 << 16));
         ResolveParams P = make_params(w);
-        kern<<<w.wp.n_runs, kThreads, smem_bytes(), p->stream>>>(w.wp, P);
+        kern<<<w.wp.n_runs, kThreads, smem_res, p->stream>>>(w.wp, P);
         p->n_launches += 1;
     }
     CK(cudaGetLastError());
@@ -631,7 +633,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
             for (size_t i = 0; i < nw; ++i) {
                 Window& w = p->win[i];
                 ResolveParams P = make_params(w);
-                kern<<<w.wp.n_runs, kThreads, smem_bytes(), p->stream>>>(w.wp, P);
+                kern<<<w.wp.n_runs, kThreads, smem_res, p->stream>>>(w.wp, P);
                 p->n_launches += 1;
             }
             CK(cudaGetLastError());
@@ -743,7 +745,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
                 CK(scratch.ensure(8));
                 CK(cudaMemset(scratch.p, 0xFF, 8));
                 P.err = scratch.as<unsigned long long>();
-                k_resolve<false, false, true, false, false><<<w.wp.n_runs, kThreads, smem_bytes(), p->stream>>>(w.wp, P);
+                k_resolve<false, false, true, false, false><<<w.wp.n_runs, kThreads, smem_bytes(false, false), p->stream>>>(w.wp, P);
                 p->n_launches += 1;
                 CK(cudaStreamSynchronize(p->stream));
                 scratch.release();
@@ -1317,7 +1319,7 @@ extern "C" bsq_status bsq_summarize_device(bsq_parser* p, const uint8_t* dev_byt
     Window w;
     while (pos < n) {
         const uint64_t bytes = std::min<uint64_t>(n - pos, kWindowMax);
-        plan_window(p, w, dev_bytes + pos, bytes);
+        plan_window(p, w, dev_bytes + pos, bytes, false);
         bsq_status st = summarize_window(p, w, true);
         if (st != BSQ_OK) { w.run_pre.release(); return st; }
         BsqSummary s = w.scan.region;

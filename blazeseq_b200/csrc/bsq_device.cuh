@@ -36,16 +36,32 @@ constexpr int kWarps = kThreads / 32;
 #define BSQ_STAGES 1
 #endif
 #ifndef BSQ_RESOLVE_CTAS
-#define BSQ_RESOLVE_CTAS 4
+#define BSQ_RESOLVE_CTAS 5
 #endif
 constexpr int kStages = BSQ_STAGES;       // TMA ring depth per CTA
 constexpr int kResolveCtas = BSQ_RESOLVE_CTAS;  // resident CTAs per SM, k_resolve (shared memory + registers)
-constexpr int kSummarizeCtas = 768 / kThreads;  // resident CTAs per SM, k_summarize (24 warps)
+#ifndef BSQ_VIEW_CTAS
+#define BSQ_VIEW_CTAS 6
+#endif
+constexpr int kViewCtas = BSQ_VIEW_CTAS;  // ... of the instantiations that do not pack (no stage buffer)
+#ifndef BSQ_SUMMARIZE_CTAS
+#define BSQ_SUMMARIZE_CTAS (768 / BSQ_THREADS)
+#endif
+constexpr int kSummarizeCtas = BSQ_SUMMARIZE_CTAS;  // resident CTAs per SM, k_summarize
+// runs per SM and window: a whole number of waves for the kernel that dominates the pass (a run is a
+// CTA's static share, so a partial last wave costs a full one): packing passes follow k_resolve (pack),
+// the others k_summarize / k_resolve (views)
+constexpr int kRunsPerSmPack = 2 * kResolveCtas;
+constexpr int kRunsPerSmView = 2 * kViewCtas;
 constexpr int kChunks = kTile / 16;       // 16-byte chunks per tile (1024)
 constexpr int kChunksPerThread = kChunks / kThreads;  // 8
 constexpr int kWords = kTile / 32;        // bitmap words per tile (512)
 constexpr int kWordsPerThread = kWords / kThreads;    // 4 -> a thread ranks 128 contiguous bytes
-constexpr int kNlCap = 1024;              // newline-list capacity per pass over a tile
+#ifndef BSQ_NLCAP
+#define BSQ_NLCAP 512
+#endif
+constexpr int kNlCap = BSQ_NLCAP;         // newline-list capacity per pass over a tile (reads shorter than
+                                          // ~60 bp fill a 16 KiB tile with more newlines: several passes)
 constexpr int kHead = 4;                  // carried newline positions in front of the list
 constexpr int kLinesCap = kNlCap / 4 + 3; // lines of one class per pass (+ two sentinels)
 constexpr int kTilePad = 32;              // readable slack after a tile for unaligned 16-byte loads
@@ -174,7 +190,6 @@ __device__ __forceinline__ void prefetch_l2(const void* gsrc, uint32_t bytes) {
 // ------------------------------------------------------------------------------------------------
 
 struct alignas(128) TileSmem {
-    // ---- used by both kernels (k_summarize allocates only up to bm_hi) ----
     alignas(128) uint8_t data[kStages][kHalo + kTile + kTilePad];  // TMA destinations: [halo | tile | pad]
     alignas(8) uint64_t full_bar[kStages];
     uint32_t warp_tot[2][kWarps][4];          // block scans, double buffered: one barrier per scan
@@ -183,8 +198,8 @@ struct alignas(128) TileSmem {
     uint32_t k1_red[kWarps * 4];
     alignas(16) uint32_t bm_nl[kWords];       // 1 bit per byte: '\n'
     // ---- k_resolve only ----
-    alignas(16) uint32_t bm_hi[kWords];       // 1 bit per byte: bit 7 set
-    alignas(16) uint32_t bm_bad[kWords];      // 1 bit per byte: outside [lower, upper]
+    // (the HI / BAD validation bitmaps live at the start of `stage`: they are consumed before the SoA
+    //  bytes of the tile are staged)
     uint32_t nlx[kHead + kNlCap];             // nlx[kHead + j] = position of local newline j;
                                               // nlx[kHead-1-i] = i-th newline before the list
     uint32_t sdst[3][kLinesCap];              // per class stream: destination of each line
@@ -196,7 +211,10 @@ struct alignas(128) TileSmem {
     uint32_t agg_p[4];                        // aggregate of a tile with more than kNlCap newlines
     alignas(128) uint8_t stage[kStage];       // SoA bytes of the pass, laid out like the destination (mod 16):
                                               // [id | seq | qual], written back with TMA bulk stores
+    __device__ __forceinline__ uint32_t* bm_hi() { return reinterpret_cast<uint32_t*>(stage); }            // 1 bit per byte: bit 7 set
+    __device__ __forceinline__ uint32_t* bm_bad() { return reinterpret_cast<uint32_t*>(stage) + kWords; }  // outside [lower, upper]
 };
+static_assert(2 * kWords * 4 <= kStage, "the validation bitmaps fit the stage buffer");
 
 // k_summarize: the same front end on its own (double-buffered) ring
 constexpr int kSumStages = 2;
@@ -208,7 +226,8 @@ struct alignas(128) SumSmem {
     uint32_t k1_head[8];                      // [0..3] last four newlines, [4..7] first four
     uint32_t k1_red[kWarps * 4];
     alignas(16) uint32_t bm_nl[kWords];
-    uint32_t bm_hi[1], bm_bad[1];             // (never written: build_bitmaps<false, false>)
+    __device__ __forceinline__ uint32_t* bm_hi() { return nullptr; }    // (never used: build_bitmaps<false, false>)
+    __device__ __forceinline__ uint32_t* bm_bad() { return nullptr; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -284,8 +303,8 @@ __device__ __forceinline__ void build_bitmaps(SM& S, const TileCursor& c, uint32
         if ((tid & 1u) == 0u) {
             const uint32_t w = chunk >> 1;
             S.bm_nl[w] = (x & 0xFFFFu) | (xo << 16);
-            if (kHi) S.bm_hi[w] = (x >> 16) | (xo & 0xFFFF0000u);
-            if (kBad) S.bm_bad[w] = m_bad | (bo << 16);
+            if (kHi) S.bm_hi()[w] = (x >> 16) | (xo & 0xFFFF0000u);
+            if (kBad) S.bm_bad()[w] = m_bad | (bo << 16);
         }
     }
 }
@@ -547,76 +566,80 @@ __global__ void __launch_bounds__(kThreads, kSummarizeCtas) k_summarize(const Wi
 // ------------------------------------------------------------------------------------------------
 
 constexpr int kMaxRuns = 2048;
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 1024;
 
-// dynamic shared memory: n_runs * (sizeof(BsqSummary) + sizeof(BsqPrefix)) + kScanThreads * sizeof(BsqSummary).
-// Every thread folds a contiguous group of runs, one thread scans the kScanThreads group totals, then
-// every thread walks its group again to emit the prefixes.
+__device__ __forceinline__ LbState lb_from_summary(const BsqSummary& s) {
+    LbState v;
+    v.count = s.count;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v.last[i] = s.last[i]; v.P[i] = s.P[i]; }
+    return v;
+}
+__device__ __forceinline__ LbState lb_shfl_up(const LbState& v, uint32_t d) {
+    LbState o;
+    o.count = __shfl_up_sync(0xFFFFFFFFu, v.count, d);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        o.last[i] = __shfl_up_sync(0xFFFFFFFFu, v.last[i], d);
+        o.P[i] = __shfl_up_sync(0xFFFFFFFFu, v.P[i], d);
+    }
+    return o;
+}
+// inclusive scan over the lanes of a warp (lane order = stream order)
+__device__ __forceinline__ LbState lb_warp_inclusive(LbState v) {
+    const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+    for (uint32_t d = 1; d < 32u; d <<= 1) {
+        const LbState o = lb_shfl_up(v, d);
+        if (lane >= d) v = lb_combine(o, v);
+    }
+    return v;
+}
+
+// One CTA of 1024 threads: every thread folds its (<= 2) runs, a shuffle scan per warp, a shuffle scan of
+// the 32 warp totals, then every thread emits the prefixes of its runs.  Works on the nine words of a
+// summary that cross runs (LbState); the window-init state is always the leftmost operand.
 __global__ void __launch_bounds__(kScanThreads, 1) k_scan_runs(const BsqSummary* __restrict__ run_sum, uint32_t n_runs,
                                                                uint32_t begin, BsqPrefix* __restrict__ run_pre,
                                                                ScanOut* __restrict__ out) {
-    extern __shared__ __align__(128) uint8_t scan_raw[];
-    BsqSummary* s_sum = reinterpret_cast<BsqSummary*>(scan_raw);
-    BsqSummary* s_grp = s_sum + n_runs;                      // exclusive state of each thread's group
-    BsqPrefix* s_pre = reinterpret_cast<BsqPrefix*>(s_grp + kScanThreads);
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(run_sum);
-        uint4* dst = reinterpret_cast<uint4*>(s_sum);
-        for (uint32_t i = threadIdx.x; i < n_runs * 4u; i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
+    __shared__ LbState s_warp[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t per = (n_runs + kScanThreads - 1u) / kScanThreads;
-    const uint32_t r0 = threadIdx.x * per, r1 = r0 + per < n_runs ? r0 + per : n_runs;
-    {
-        BsqSummary g = bsq_summary_identity();
-        for (uint32_t r = r0; r < r1; ++r) g = bsq_combine(g, s_sum[r]);
-        s_grp[threadIdx.x] = g;
-    }
+    const uint32_t r0 = tid * per < n_runs ? tid * per : n_runs, r1 = r0 + per < n_runs ? r0 + per : n_runs;
+    LbState g = lb_identity();
+    for (uint32_t r = r0; r < r1; ++r) g = lb_combine(g, lb_from_summary(run_sum[r]));
+    const LbState inc = lb_warp_inclusive(g);
+    if (lane == 31u) s_warp[warp] = inc;
     __syncthreads();
-    // three-level scan of the kScanThreads group totals: 16 leaders fold 16 groups each, thread 0
-    // scans the 16 leader totals, the leaders then turn their groups into exclusive states
-    __shared__ BsqSummary s_blk[kScanThreads / 16];
-    if ((threadIdx.x & 15u) == 0u) {
-        BsqSummary b = bsq_summary_identity();
-        for (uint32_t t = threadIdx.x; t < threadIdx.x + 16u; ++t) b = bsq_combine(b, s_grp[t]);
-        s_blk[threadIdx.x >> 4] = b;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        BsqSummary E = bsq_summary_window_init(begin);
-        BsqSummary R = bsq_summary_identity();
-        for (uint32_t k = 0; k < (uint32_t)kScanThreads / 16u; ++k) {
-            const BsqSummary b = s_blk[k];
-            s_blk[k] = E;
-            E = bsq_combine(E, b);
-            R = bsq_combine(R, b);
-        }
-        out->totals = bsq_totals_from(E, begin);
-        out->end_state = E;
-        out->region = R;
-    }
-    __syncthreads();
-    if ((threadIdx.x & 15u) == 0u) {
-        BsqSummary E = s_blk[threadIdx.x >> 4];
-        for (uint32_t t = threadIdx.x; t < threadIdx.x + 16u; ++t) {
-            const BsqSummary g = s_grp[t];
-            s_grp[t] = E;
-            E = bsq_combine(E, g);
+    if (warp == 0) {
+        const LbState w = lb_warp_inclusive(s_warp[lane]);
+        LbState ex = lb_shfl_up(w, 1);
+        if (lane == 0) ex = lb_identity();
+        s_warp[lane] = ex;                         // runs of the warps before this one
+        if (lane == 31u) {
+            // totals of the window
+            LbState init = lb_identity();
+            init.last[0] = begin - 1u;             // bsq_summary_window_init
+            const BsqSummary E = lb_to_summary(lb_combine(init, w));
+            out->totals = bsq_totals_from(E, begin);
+            out->end_state = E;
+            // the region without the window init (shard stitching); first[] from the leading runs
+            BsqSummary R = bsq_summary_identity();
+            for (uint32_t r = 0; r < n_runs && R.count < 4u; ++r) R = bsq_combine(R, run_sum[r]);
+            BsqSummary reg = lb_to_summary(w);
+            for (int i = 0; i < 4; ++i) reg.first[i] = R.first[i];
+            out->region = reg;
         }
     }
     __syncthreads();
-    {
-        BsqSummary E = s_grp[threadIdx.x];
-        for (uint32_t r = r0; r < r1; ++r) {
-            s_pre[r] = bsq_prefix_from(E, begin);
-            E = bsq_combine(E, s_sum[r]);
-        }
-    }
-    __syncthreads();
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(s_pre);
-        uint4* dst = reinterpret_cast<uint4*>(run_pre);
-        for (uint32_t i = threadIdx.x; i < n_runs * 2u; i += blockDim.x) dst[i] = src[i];
+    LbState before = lb_shfl_up(inc, 1);           // runs of the lower lanes of this warp
+    if (lane == 0) before = lb_identity();
+    LbState init = lb_identity();
+    init.last[0] = begin - 1u;
+    LbState E = lb_combine(lb_combine(init, s_warp[warp]), before);
+    for (uint32_t r = r0; r < r1; ++r) {
+        run_pre[r] = bsq_prefix_from(lb_to_summary(E), begin);
+        E = lb_combine(E, lb_from_summary(run_sum[r]));
     }
 }
 
@@ -966,7 +989,7 @@ __device__ __forceinline__ void flush_stream(const uint8_t* stage, uint32_t so, 
 //                 treated like any other (its bytes land past the counted totals, its error reports
 //                 carry a record index that the host ignores, its bases are taken back at the end).
 template <bool kAscii, bool kQual, bool kOffsets, bool kPack, bool kFused>
-__global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinParams W, const ResolveParams P) {
+__global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_resolve(const WinParams W, const ResolveParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x;
@@ -1019,6 +1042,10 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
             if (tid < 4) S.agg_p[tid] = 0;
         } else if (kStages == 1 && tid == 0 && t + 1u < tb) {   // single buffer: the next tile waits in L2
             prefetch_l2(W.base + (size_t)(t + 1u) * kTile, tile_bytes_rounded(W, t + 1u));
+        }
+        if (kPack && (kAscii || kQual)) {              // the validation bitmaps reuse `stage`: the previous
+            if (tid == 0) tma_store_wait_read();       // tile's bulk stores and edge stores must be through with it
+            __syncthreads();
         }
         build_bitmaps<kAscii, kQual>(S, c, addlo, addup);
         __syncthreads();
@@ -1098,8 +1125,8 @@ __global__ void __launch_bounds__(kThreads, kResolveCtas) k_resolve(const WinPar
 #pragma unroll
             for (int i = 0; i < kWordsPerThread; ++i) {
                 const uint32_t nl = words.w[i];
-                const uint32_t hiw = kAscii ? S.bm_hi[tid * kWordsPerThread + i] : 0u;
-                const uint32_t badw = kQual ? (S.bm_bad[tid * kWordsPerThread + i] & ~nl) : 0u;
+                const uint32_t hiw = kAscii ? S.bm_hi()[tid * kWordsPerThread + i] : 0u;
+                const uint32_t badw = kQual ? (S.bm_bad()[tid * kWordsPerThread + i] & ~nl) : 0u;
                 if ((hiw | badw) != 0u) {
                     uint32_t rest = 0xFFFFFFFFu, m = nl, rr = r;
                     while (rest) {
