@@ -129,6 +129,12 @@ def reference_arm(args):
         assert n == sample_reads and code == 0
     dt = (time.perf_counter() - t0) / args.steps
     value = sample_reads / dt
+    # the reference's FastqParser is a sequential object (one parser = one thread, record.mojo:439): the same
+    # sample through ONE thread is what a single BlazeSeq parser delivers; `value` shards the sample by
+    # newline rank over every host thread, which the reference itself does not do
+    t1 = time.perf_counter()
+    O.baseline_mt(data, cfg, 1, 4096, 1)
+    one_thread = sample_reads / (time.perf_counter() - t1)
     sample = f"first {sample_reads} reads ({data.size / GIB:.2f} GiB) of the 10 GiB 150 bp stream, batches(4096)"
     print(json.dumps({
         "impl": "reference", "metric": "fastq_reads_per_s", "value": value, "unit": "reads/s",
@@ -137,7 +143,8 @@ def reference_arm(args):
         "parsed_gb_per_s": data.size / dt / 1e9,
         "config": {"workload": "configs[1]: 10 GiB in-memory 150 bp Illumina FASTQ, illumina_1.8, validation OFF, "
                                "batches(4096)", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port", "sample": sample,
+                         "value_1core": one_thread},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -267,7 +274,9 @@ def main():
         traffic = per_rec * M / n_windows if args.mode == "batches" and not args.validate else None
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_resolve", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    single = os.environ.get("BSQ_SINGLE_PASS", "0") not in ("", "0")
+    roofline = {"bound": "hbm", "kernel": "k_resolve", "pass": "single-pass (look-back)" if single else
+                "two-pass (k_summarize + k_scan_runs, then k_resolve)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_record": algo, "records_per_launch": M / n_windows,
                 "launches_per_step": n_windows, "avg_launch_ms": resolve_ms / n_windows,
