@@ -2,19 +2,21 @@
 //
 // Two streaming passes over a window (<= 2 GiB of the byte stream, 16-byte aligned base):
 //
-//   k_summarize   every CTA owns a contiguous RUN of 32 KiB tiles.  Tiles arrive in shared memory
-//                 through a ring of TMA bulk copies (cp.async.bulk + mbarrier).  Per tile: 16-byte
-//                 shared loads -> byte-lane compare -> per-warp newline bitmap -> block prefix scan
-//                 -> ordered newline list.  The run is reduced to a 64-byte BsqSummary.
+//   k_summarize   every CTA owns a contiguous RUN of 16 KiB tiles.  Tiles arrive in shared memory
+//                 as TMA bulk copies (cp.async.bulk + mbarrier).  Per tile: 16-byte shared loads ->
+//                 byte-lane compare -> newline bitmap -> block prefix scan.  The run is reduced to
+//                 a 64-byte BsqSummary.
 //   k_scan_runs   one CTA scans the run summaries (tile_math.h) and gives every run the state it
 //                 starts from (newline rank, previous newline positions, SoA destinations).
 //   k_resolve     same tiling; with the prefix known every line that ENDS in a tile is resolved
 //                 in place: '@' / '+' / length checks (utils.mojo:448-462), id strip
 //                 (utils.mojo:221-242), ASCII and quality-range validation from the HI/BAD bitmaps
-//                 (record.mojo:76-116), the line-end table for views() and the FastqBatch SoA copy
-//                 (record_batch.mojo:77-87) as aligned 16-byte stores assembled from shared memory.
+//                 (record.mojo:76-116), the line-end table for views() and the FastqBatch SoA
+//                 (record_batch.mojo:77-87): the lines are staged in shared memory in destination
+//                 layout and written back with TMA bulk stores.
 //
-// No CTA ever waits on another CTA: the only cross-CTA dependency is the kernel boundary.
+// In the two-pass path no CTA ever waits on another CTA: the only cross-CTA dependency is the
+// kernel boundary.  k_resolve<..., kFused> is the single-pass alternative (decoupled look-back).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

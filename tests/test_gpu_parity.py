@@ -225,14 +225,14 @@ def test_tiny_and_degenerate_streams(U, oracle):
 
 
 def test_all_newlines_overflows_the_tile_list(U, oracle):
-    """> 2048 newlines in one 32 KiB tile: the resolve kernel walks the tile in several passes."""
+    """More newlines in one 16 KiB tile than the newline list holds (512): the resolve kernel walks the tile in several passes."""
     U.check_stream(oracle, b"\n" * 100000, batch_size=16)
     U.check_stream(oracle, b"@\n\n+\n\n" * 30000, batch_size=4096, check_ascii=True, check_quality=True)
     U.check_stream(oracle, b"@ab\nA\n+\nI\n" * 40000, batch_size=1000)
 
 
 def test_long_reads_span_tiles(U, oracle):
-    """Records far longer than a 32 KiB tile (and than a CTA's run)."""
+    """Records far longer than a 16 KiB tile (and than a CTA's run)."""
     rng = np.random.default_rng(11)
     recs = []
     for L in (100000, 5, 70000, 32768, 32767, 32769, 1, 250000, 0, 65536):
