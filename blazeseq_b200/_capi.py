@@ -35,7 +35,7 @@ class Config(C.Structure):
         ("q_lower", C.c_uint8), ("q_upper", C.c_uint8), ("q_offset", C.c_uint8), ("_pad0", C.c_uint8),
         ("buffer_capacity", C.c_int64), ("buffer_max_capacity", C.c_int64),
         ("buffer_growth_enabled", C.c_int32), ("batch_size", C.c_int32),
-        ("h2d_chunk_bytes", C.c_int64), ("force_id_slow_path", C.c_int32), ("_pad1", C.c_int32),
+        ("h2d_chunk_bytes", C.c_int64), ("force_id_slow_path", C.c_int32), ("inflate_threads", C.c_int32),
     ]
 
 

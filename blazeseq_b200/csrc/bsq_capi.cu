@@ -8,6 +8,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdarg>
@@ -428,6 +429,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         P.err = p->err_word.as<unsigned long long>();
         // single pass
         P.tile_status = p->tile_status.as<uint32_t>();
+        P.group_status = p->tile_status.as<uint32_t>() + ((size_t)(kWindowMax / kTile) + 2) * kStatusWords;
         P.ticket = p->ticket.as<uint32_t>();
         P.epoch = p->epoch;
         P.line_cap = (uint32_t)std::min<size_t>(w.line_ends.cap / 4, 0xFFFFFFFFu);
@@ -442,7 +444,9 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     // one single-pass launch over window w (bases already in w)
     auto launch_fused = [&](Window& w) -> bsq_status {
         const uint32_t tiles = w.wp.n_tiles - w.wp.first_tile;
-        const size_t need = (size_t)tiles * kStatusWords * 4;
+        // [tile states | group states]; sized for the largest window so that it is cleared once
+        const size_t max_tiles = (size_t)(kWindowMax / kTile) + 2;
+        const size_t need = max_tiles * kStatusWords * 4 + (max_tiles / kLbGroup + 2) * kGroupWords * 4;
         if (need > p->tile_status.cap) {
             CK(p->tile_status.ensure(need, 1 << 20));
             CK(cudaMemsetAsync(p->tile_status.p, 0, p->tile_status.cap, p->stream));
@@ -451,7 +455,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         CK(p->ticket.ensure(16));
         CK(cudaMemsetAsync(p->ticket.p, 0, 16, p->stream));
         p->epoch += 1;
-        if (p->epoch >= (1u << 30)) {   // tags are 30 bits: start over on clean status words
+        if (p->epoch == 0xFFFFFFFFu) {   // start over on clean status words
             CK(cudaMemsetAsync(p->tile_status.p, 0, p->tile_status.cap, p->stream));
             p->epoch = 1;
         }
@@ -941,6 +945,96 @@ struct bsq_stream {
     bool finished = false;
     bsq_stream_stats st{};
 
+    // ---- BGZF (blocked gzip, SAM spec 4.1): every member is <= 64 KiB, carries its compressed size in
+    // the 'BC' extra field and its uncompressed size in ISIZE, so members inflate independently.  The
+    // reader thread walks the member headers and `inflate_threads` workers inflate a region's members in
+    // parallel, each straight into its place in the pinned region (the parallel-decoder role of
+    // RapidgzipReader(parallelism), readers.mojo:380-443; plain gzip members still go through gzread).
+    bool bgzf = false;
+    int inflate_threads = 1;
+    FILE* zfp = nullptr;                 // the compressed file, read raw
+    std::vector<uint8_t> zbuf;           // compressed members of the region being filled
+    std::vector<uint8_t> zpend;          // a member read for the previous region that did not fit it
+    struct Member { size_t coff; uint32_t clen; uint64_t ooff; uint32_t isize; };
+    std::vector<Member> members;
+
+    // next member (header + payload) appended to `to`; returns 1 ok, 0 clean EOF, -1 malformed
+    int read_member(std::vector<uint8_t>& to, uint32_t* clen, uint32_t* isize) {
+        uint8_t h[18];
+        const size_t k = fread(h, 1, 18, zfp);
+        if (k == 0) return 0;
+        if (k != 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4) || h[10] != 6 || h[11] != 0 ||
+            h[12] != 'B' || h[13] != 'C' || h[14] != 2 || h[15] != 0)
+            return -1;
+        const uint32_t total = ((uint32_t)h[16] | ((uint32_t)h[17] << 8)) + 1u;
+        if (total < 18u + 8u) return -1;
+        const size_t at = to.size();
+        to.resize(at + total);
+        memcpy(to.data() + at, h, 18);
+        if (fread(to.data() + at + 18, 1, total - 18u, zfp) != total - 18u) return -1;
+        const uint8_t* t = to.data() + at + total - 4;
+        *isize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        *clen = total;
+        return 1;
+    }
+    // fills dst[0, region_bytes) with whole members; false on a malformed / corrupt member
+    bool fill_bgzf(uint8_t* dst, uint64_t* got, bool* eof) {
+        zbuf.clear(); members.clear();
+        uint64_t out = 0;
+        if (!zpend.empty()) {
+            const uint8_t* t = zpend.data() + zpend.size() - 4;
+            const uint32_t isz = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+            if (isz > region_bytes) return false;
+            zbuf = zpend; zpend.clear();
+            members.push_back(Member{0, (uint32_t)zbuf.size(), 0, isz});
+            out = isz;
+        }
+        for (;;) {
+            const size_t at = zbuf.size();
+            uint32_t clen = 0, isz = 0;
+            const int r = read_member(zbuf, &clen, &isz);
+            if (r == 0) { *eof = true; break; }
+            if (r < 0 || isz > (1u << 16)) return false;
+            if (out + isz > region_bytes) {            // belongs to the next region
+                zpend.assign(zbuf.begin() + (ptrdiff_t)at, zbuf.end());
+                zbuf.resize(at);
+                break;
+            }
+            members.push_back(Member{at, clen, out, isz});
+            out += isz;
+        }
+        std::atomic<size_t> next{0};
+        std::atomic<bool> bad{false};
+        auto work = [&]() {
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) { bad = true; return; }
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= members.size() || bad.load()) break;
+                const Member& m = members[i];
+                const uint8_t* c = zbuf.data() + m.coff;
+                inflateReset(&zs);
+                zs.next_in = const_cast<Bytef*>(c + 18); zs.avail_in = m.clen - 18u - 8u;
+                zs.next_out = dst + m.ooff; zs.avail_out = m.isize;
+                const int rc = m.isize ? inflate(&zs, Z_FINISH) : (inflate(&zs, Z_FINISH), Z_STREAM_END);
+                const uint8_t* t = c + m.clen - 8;
+                const uint32_t want_crc = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+                if (rc != Z_STREAM_END || zs.total_out != m.isize ||
+                    (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst + m.ooff, m.isize) != want_crc)
+                    bad = true;
+            }
+            inflateEnd(&zs);
+        };
+        const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)inflate_threads, members.size() / 4 + 1));
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+        *got = out;
+        return !bad.load();
+    }
+
     void reader_main() {
         for (;;) {
             Buf* b;
@@ -954,6 +1048,9 @@ struct bsq_stream {
             uint64_t got = 0;
             bool eof = false, err = false;
             uint8_t* dst = b->mem + carry_cap;
+            if (bgzf) {
+                if (!fill_bgzf(dst, &got, &eof)) err = true;
+            } else
             while (got < region_bytes) {
                 const size_t ask = (size_t)std::min<uint64_t>(region_bytes - got, 1u << 30);
                 long k;
@@ -992,12 +1089,27 @@ extern "C" bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t s
     }
     s->kind = source_kind;
     if (source_kind == BSQ_SOURCE_GZIP) {
-        s->gz = gzopen(path, "rb");
-        if (s->gz) gzbuffer(s->gz, 1 << 20);
+        // BGZF?  (first member: FEXTRA with the 'BC' subfield in the canonical position)
+        FILE* f = fopen(path, "rb");
+        uint8_t h[18];
+        if (f && fread(h, 1, 18, f) == 18 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) && h[10] == 6 &&
+            h[11] == 0 && h[12] == 'B' && h[13] == 'C' && h[14] == 2 && h[15] == 0) {
+            rewind(f);
+            s->bgzf = true;
+            s->zfp = f;
+            int nt = p->cfg.inflate_threads;
+            if (const char* e = getenv("BSQ_INFLATE_THREADS")) nt = atoi(e);
+            if (nt <= 0) nt = (int)std::max(1u, std::thread::hardware_concurrency());
+            s->inflate_threads = std::min(nt, 64);
+        } else {
+            if (f) fclose(f);
+            s->gz = gzopen(path, "rb");
+            if (s->gz) gzbuffer(s->gz, 1 << 20);
+        }
     } else {
         s->fp = fopen(path, "rb");
     }
-    if (!s->gz && !s->fp) { p->last_error = std::string("cannot open ") + path; delete s; return BSQ_E_ARG; }
+    if (!s->gz && !s->fp && !s->zfp) { p->last_error = std::string("cannot open ") + path; delete s; return BSQ_E_ARG; }
     s->region_bytes = region_bytes ? region_bytes : (256ull << 20);
     s->carry_cap = std::max<uint64_t>(std::min<uint64_t>(s->region_bytes, 64ull << 20), 4096);
     for (auto& b : s->buf) {
@@ -1019,6 +1131,7 @@ extern "C" void bsq_stream_close(bsq_stream* s) {
     if (s->reader.joinable()) s->reader.join();
     if (s->gz) gzclose(s->gz);
     if (s->fp) fclose(s->fp);
+    if (s->zfp) fclose(s->zfp);
     for (auto& b : s->buf) if (b.mem) cudaFreeHost(b.mem);
     delete s;
 }

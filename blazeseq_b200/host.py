@@ -154,7 +154,9 @@ class GZFile(Reader):
 
 
 class RapidgzipReader(GZFile):
-    """readers.mojo:380-443.  rapidgzip is not in this image; zlib inflates the same bytes."""
+    """readers.mojo:380-443.  rapidgzip is not in this image; zlib inflates the same bytes.  Through the
+    native pipeline (FastqParser with native_io) `parallelism` host threads inflate the members of a BGZF
+    file block-parallel (0 = all cores); any other gzip stream is inflated sequentially."""
 
     def __init__(self, path, parallelism: int = 0):
         super().__init__(path)
@@ -344,7 +346,7 @@ class GpuParser:
     def __init__(self, check_ascii=False, check_quality=False, schema: QualitySchema | None = None,
                  batch_size=DEFAULT_BATCH_SIZE, device_id=0, buffer_capacity=DEFAULT_CAPACITY,
                  buffer_max_capacity=MAX_CAPACITY, buffer_growth_enabled=False, h2d_chunk_bytes=None,
-                 force_id_slow_path=False):
+                 force_id_slow_path=False, inflate_threads=0):
         L = capi.lib()
         cfg = capi.default_config()
         cfg.device_id = device_id
@@ -357,6 +359,7 @@ class GpuParser:
         if h2d_chunk_bytes:
             cfg.h2d_chunk_bytes = h2d_chunk_bytes
         cfg.force_id_slow_path = int(force_id_slow_path)
+        cfg.inflate_threads = int(inflate_threads)   # BGZF members of a stream are inflated by this many host threads (0 = all)
         self.cfg = cfg
         self._h = C.c_void_p()
         capi.check(L.bsq_create(C.byref(cfg), C.byref(self._h)), None, "bsq_create")
@@ -535,7 +538,8 @@ class FastqParser:
         self._gpu = GpuParser(self.config.check_ascii, self.config.check_quality, self.quality_schema,
                               self._batch_size, device_id, self.config.buffer_capacity,
                               self.config.buffer_max_capacity, self.config.buffer_growth_enabled,
-                              force_id_slow_path=_force_id_slow_path)
+                              force_id_slow_path=_force_id_slow_path,
+                              inflate_threads=int(getattr(reader, "parallelism", 0) or 0))
         self._carry = np.zeros(0, np.uint8)   # unconsumed tail of the previous region
         self._stream_pos = 0                  # stream offset of _carry[0]
         self._records_done = 0                # records of finished regions

@@ -70,7 +70,8 @@ typedef struct bsq_config {
     int32_t batch_size;            /* FastqParser._batch_size, DEFAULT_BATCH_SIZE = 4096 */
     int64_t h2d_chunk_bytes;       /* staging chunk for bsq_parse_host (default 64 MiB) */
     int32_t force_id_slow_path;    /* tests: always take the id strip pipeline */
-    int32_t _pad1;
+    int32_t inflate_threads;       /* bsq_stream_*: host threads that inflate BGZF members (0 = all cores); the
+                                      parallelism argument of RapidgzipReader, readers.mojo:380-443 */
 } bsq_config;
 
 /* The first error of a pass, with the context the reference prints
@@ -185,7 +186,8 @@ bsq_status bsq_parse_host(bsq_parser* p, const uint8_t* host_bytes, uint64_t n,
  * carried in front of the next region, like BufferedReader._compact_from (:239-260). */
 typedef struct bsq_stream bsq_stream;
 #define BSQ_SOURCE_PLAIN 0
-#define BSQ_SOURCE_GZIP 1          /* gzip / BGZF members, inflated with zlib (gzread) */
+#define BSQ_SOURCE_GZIP 1          /* gzip: BGZF members are inflated block-parallel by cfg.inflate_threads host
+                                      threads, any other gzip stream sequentially with zlib (gzread) */
 #define BSQ_SOURCE_AUTO 2          /* by suffix: .gz / .bgz -> gzip (python/blazeseq_parser.mojo:100-114) */
 
 typedef struct bsq_stream_stats {

@@ -535,7 +535,7 @@ def test_fastq_parser_file_and_gzip_readers(B, oracle, tmp_path):
 # ------------------------------------------------------------------ native file / gzip pipeline
 
 
-@pytest.mark.parametrize("gz", [False, True])
+@pytest.mark.parametrize("gz", [False, True, "bgzf"])
 @pytest.mark.parametrize("region_bytes", [64 << 10, 1 << 20, 1 << 26])
 def test_stream_pipeline_regions(B, oracle, tmp_path, gz, region_bytes):
     """bsq_stream_*: reader thread -> pinned regions -> passes.  Every region's tables must be the
@@ -544,7 +544,11 @@ def test_stream_pipeline_regions(B, oracle, tmp_path, gz, region_bytes):
     from blazeseq_b200 import _capi as capi
     data = oracle.synth(12000, 75, 300, 2, 40, "illumina_1.8")
     path = tmp_path / ("s.fastq.gz" if gz else "s.fastq")
-    if gz:
+    if gz == "bgzf":       # members of <= 64 KiB, inflated block-parallel by the reader's worker threads
+        from blazeseq_b200 import bgzf
+        path.write_bytes(bgzf.compress(data.tobytes(), level=1))
+        assert gzip.decompress(path.read_bytes()) == data.tobytes()
+    elif gz:
         with gzip.open(path, "wb", compresslevel=1) as f:
             f.write(data.tobytes())
     else:
@@ -573,6 +577,42 @@ def test_stream_pipeline_regions(B, oracle, tmp_path, gz, region_bytes):
     assert done == len(views)
     stats = gpu.stream_stats(st)
     assert stats.bytes_read == data.size and stats.regions >= 1
+    gpu.stream_close(st)
+    gpu.close()
+
+
+def test_bgzf_parallel_inflate(B, oracle, tmp_path, golden_dir):
+    """BGZF input: the reference's own .bgz fixtures and a synthetic file, 1 / 3 / all inflate threads; a
+    corrupted member is reported, not parsed."""
+    from blazeseq_b200 import _capi as capi, bgzf
+    for f in ("example.fastq.bgz", "example_dos.fastq.bgz"):
+        plain = open(os.path.join(golden_dir, "corpus", f[:-4]), "rb").read()
+        exp = [(r["id_len"], r["seq_len"]) for r in oracle.parse_all(plain)[0]]
+        p = B.FastqParser(B.RapidgzipReader(os.path.join(golden_dir, "corpus", f), 2), "generic")
+        assert [(len(r.id), len(r.sequence)) for r in p.records()] == [(int(a), int(b)) for a, b in exp]
+    data = oracle.synth(30000, 50, 250, 2, 40, "sanger")
+    views, bases, err = oracle.parse_all(data)
+    path = tmp_path / "p.fastq.gz"
+    blob = bgzf.compress(data.tobytes(), level=1)
+    path.write_bytes(blob)
+    for threads in (1, 3, 0):
+        p = B.FastqParser(B.RapidgzipReader(str(path), threads), "sanger", region_bytes=1 << 20,
+                          config=B.ParserConfig(check_ascii=True, check_quality=True))
+        n = nb = 0
+        for batch in p.batches(1000):
+            n += len(batch)
+            nb += batch.seq_len()
+        assert (n, nb) == (len(views), bases)
+    bad = bytearray(blob)
+    bad[len(bad) // 2] ^= 0x55
+    path.write_bytes(bytes(bad))
+    gpu = B.GpuParser(False, False, B.parse_schema("sanger"), 512)
+    st = gpu.stream_open(str(path), capi.SOURCE_AUTO, 1 << 20)
+    with pytest.raises(Exception):
+        while True:
+            res, region, off, first = gpu.stream_next(st, capi.WANT_OFFSETS)
+            if res.stop.code != capi.OK:
+                break
     gpu.stream_close(st)
     gpu.close()
 
