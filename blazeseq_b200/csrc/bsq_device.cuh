@@ -118,9 +118,8 @@ struct ResolveParams {
     unsigned long long* err;     // min over ((global record << 8) | code)
     // ---- single-pass (fused) launches only ----
     uint32_t* tile_status;       // kStatusWords words per tile of the window (decoupled look-back)
-    uint32_t* group_status;      // kGroupWords words per group of kLbGroup tiles
     uint32_t* ticket;            // next tile to claim, window-relative; zeroed before the launch
-    uint32_t epoch;              // tags the status chunks of this launch (never 0, never reused)
+    uint32_t epoch;              // tags the status words of this launch (never 0, never reused)
     uint32_t line_cap;           // entries of line_ends
     ScanOut* scan_out;           // written by the CTA that owns the window's last tile
     uint32_t* overflow;          // raised when an output would not fit its (estimated) capacity
@@ -658,15 +657,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) k_scan_runs(const BsqSummary*
 // resolves the tile in place.  A tile waits only for tiles with smaller tickets, all of which are
 // owned by running CTAs, so the scheme cannot deadlock whatever the residency.
 
-// Status memory of a fused launch.  Per tile 128 bytes: the tile's own aggregate at word 0, its inclusive
-// state at word 12; per GROUP of kLbGroup consecutive tiles 64 bytes: the aggregate of the whole group.
-// A state travels as three 16-byte chunks {3 payload words, tag}; every chunk is written and read with one
-// 128-bit relaxed gpu-scope access (single-copy atomic), and a state is valid when its three tags equal the
-// launch's epoch -- no fence, no separate flag, and the buffer is never cleared (epochs do not repeat).
-constexpr int kStatusWords = 32;
-constexpr int kGroupWords = 16;
-constexpr int kLbGroup = 32;
-constexpr uint32_t kLbAggOff = 0u, kLbIncOff = 12u;
+constexpr int kStatusWords = 32;   // 128 bytes per tile: [flag, -, -, -][aggregate: 12 words][inclusive: 12 words][pad]
+constexpr uint32_t kLbAgg = 1u, kLbInc = 2u;
 
 __device__ __forceinline__ LbState lb_shfl_down(const LbState& v, uint32_t d) {
     LbState o;
@@ -688,109 +680,83 @@ __device__ __forceinline__ LbState lb_bcast0(const LbState& v) {
     }
     return o;
 }
-
-__device__ __forceinline__ uint4 ld_b128(const uint32_t* p) {
-    unsigned long long lo, hi;
-    asm volatile("{\n\t.reg .b128 t;\n\tld.relaxed.gpu.global.b128 t, [%2];\n\tmov.b128 {%0, %1}, t;\n\t}"
-                 : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
-    return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
-__device__ __forceinline__ void st_b128(uint32_t* p, uint4 v) {
-    const unsigned long long lo = (unsigned long long)v.x | ((unsigned long long)v.y << 32),
-                             hi = (unsigned long long)v.z | ((unsigned long long)v.w << 32);
-    asm volatile("{\n\t.reg .b128 t;\n\tmov.b128 t, {%1, %2};\n\tst.relaxed.gpu.global.b128 [%0], t;\n\t}" ::"l"(p), "l"(lo), "l"(hi)
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint32_t* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_v4(uint32_t* p, uint4 v) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
 }
 
-// one thread publishes a state (12 words at `slot`, 16-byte aligned)
-__device__ __forceinline__ void lb_publish(uint32_t* slot, const LbState& v, uint32_t epoch) {
-    st_b128(slot, make_uint4(v.count, v.last[0], v.last[1], epoch));
-    st_b128(slot + 4, make_uint4(v.last[2], v.last[3], v.P[0], epoch));
-    st_b128(slot + 8, make_uint4(v.P[1], v.P[2], v.P[3], epoch));
+// one thread: payload, fence, flag
+__device__ __forceinline__ void lb_publish(uint32_t* status, uint32_t slot, const LbState& v, uint32_t epoch) {
+    uint32_t* pay = status + 4u + (slot == kLbInc ? 12u : 0u);
+    st_relaxed_v4(pay, make_uint4(v.count, v.last[0], v.last[1], v.last[2]));
+    st_relaxed_v4(pay + 4, make_uint4(v.last[3], v.P[0], v.P[1], v.P[2]));
+    st_relaxed_v4(pay + 8, make_uint4(v.P[3], 0u, 0u, 0u));
+    __threadfence();
+    st_release_u32(status, (epoch << 2) | slot);
 }
-__device__ __forceinline__ bool lb_try_load(const uint32_t* slot, uint32_t epoch, LbState& v) {
-    const uint4 a = ld_b128(slot), b = ld_b128(slot + 4), c = ld_b128(slot + 8);
-    if (a.w != epoch || b.w != epoch || c.w != epoch) return false;
-    v.count = a.x; v.last[0] = a.y; v.last[1] = a.z; v.last[2] = b.x; v.last[3] = b.y;
-    v.P[0] = b.z; v.P[1] = c.x; v.P[2] = c.y; v.P[3] = c.z;
-    return true;
-}
-// Polls until the inclusive state (returns true) or the aggregate (returns false) is there; the inclusive
-// one is preferred.  A state that never comes must fault, not hang.
-__device__ __forceinline__ bool lb_wait_either(const uint32_t* inc_slot, const uint32_t* agg_slot, uint32_t epoch, LbState& v) {
-    for (uint32_t spins = 0;; ++spins) {
-        if (lb_try_load(inc_slot, epoch, v)) return true;
-        if (lb_try_load(agg_slot, epoch, v)) return false;
-        if (spins > (1u << 22)) __trap();
-        __nanosleep(20);
-    }
-}
-// Ordered reduction over lanes [0, last]: a higher lane holds an EARLIER range.  Returns the combined state
-// on every lane.  (The window-init state is not a unit of lb_combine on the right, so lanes beyond `last`
-// are left out rather than zeroed.)
-__device__ __forceinline__ LbState lb_reduce_lanes(LbState v, uint32_t last) {
-    const uint32_t lane = threadIdx.x & 31u;
-#pragma unroll
-    for (uint32_t d = 1; d < 32u; d <<= 1) {
-        const LbState o = lb_shfl_down(v, d);
-        if (lane + d <= last) v = lb_combine(o, v);
-    }
-    return lb_bcast0(v);
+__device__ __forceinline__ LbState lb_load(const uint32_t* status, uint32_t slot) {
+    const uint32_t* pay = status + 4u + (slot == kLbInc ? 12u : 0u);
+    const uint4 a = ld_relaxed_v4(pay), b = ld_relaxed_v4(pay + 4), c = ld_relaxed_v4(pay + 8);
+    LbState v;
+    v.count = a.x; v.last[0] = a.y; v.last[1] = a.z; v.last[2] = a.w;
+    v.last[3] = b.x; v.P[0] = b.y; v.P[1] = b.z; v.P[2] = b.w; v.P[3] = c.x;
+    return v;
 }
 
-// Warp-wide, two levels: the state before window tile `ti` (0-based within the window) = window init (+)
-// tiles [0, ti).  Round 1 covers the tile's own group (lane l = tile ti-1-l), later rounds cover 32 earlier
-// groups each (lane l = group g-1-l: the inclusive state of the group's last tile, else the group aggregate
-// that tile published).  `mine` is this tile's aggregate; a group's last tile publishes the group aggregate.
-__device__ __forceinline__ LbState lb_look_back(uint32_t* tile_status, uint32_t* group_status, uint32_t ti, uint32_t begin,
-                                                uint32_t epoch, const LbState& mine) {
+// Warp-wide: the state before window tile `ti` (0-based within the window) = window init (+) tiles
+// [0, ti).  Lane l looks at tile ti-1-l; tiles before the window are the (inclusive) init state.
+__device__ __forceinline__ LbState lb_look_back(const uint32_t* tile_status, uint32_t ti, uint32_t begin, uint32_t epoch) {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t g = ti / (uint32_t)kLbGroup, j = ti % (uint32_t)kLbGroup;
-    LbState init = lb_identity();
-    init.last[0] = begin - 1u;                      // bsq_summary_window_init
-    // ---- round 1: the tiles of this group before ti (and the window init for group 0) ----
     LbState E = lb_identity();
-    bool have = false;
-    {
-        const uint32_t n_lanes = j + (g == 0u ? 1u : 0u);          // lanes that take part
+    bool have = false;                              // E holds at least one tile (it is the later operand)
+    int32_t base = (int32_t)ti - 1;
+    while (true) {
+        const int32_t t = base - (int32_t)lane;
+        uint32_t slot = kLbInc;
         LbState v = lb_identity();
-        bool is_inc = false;
-        if (lane < j) {
-            const uint32_t* st = tile_status + (size_t)(ti - 1u - lane) * kStatusWords;
-            is_inc = lb_wait_either(st + kLbIncOff, st + kLbAggOff, epoch, v);
-        } else if (lane == j && g == 0u) {
-            v = init; is_inc = true;
-        }
-        const uint32_t inc = __ballot_sync(0xFFFFFFFFu, is_inc);
-        if (n_lanes != 0u) {
-            const uint32_t last = inc ? (uint32_t)__ffs((int)inc) - 1u : n_lanes - 1u;
-            E = lb_reduce_lanes(v, last);
-            have = true;
-        }
-        if (inc) return E;
-    }
-    // no inclusive state inside the group: E = aggregate of the group's tiles before ti (if any)
-    if (j == (uint32_t)kLbGroup - 1u && lane == 0)
-        lb_publish(group_status + (size_t)g * kGroupWords, lb_combine(E, mine), epoch);
-    // ---- rounds 2..: earlier groups, 32 per round ----
-    for (int32_t base = (int32_t)g - 1;; base -= 32) {
-        const int32_t grp = base - (int32_t)lane;
-        LbState v = lb_identity();
-        bool is_inc = false;
-        if (grp < 0) {
-            is_inc = true;
-            if (grp == -1) v = init;
+        if (t < 0) {
+            if (t == -1) v.last[0] = begin - 1u;    // bsq_summary_window_init
         } else {
-            const uint32_t* st = tile_status + ((size_t)grp * kLbGroup + (kLbGroup - 1)) * kStatusWords;
-            is_inc = lb_wait_either(st + kLbIncOff, group_status + (size_t)grp * kGroupWords, epoch, v);
+            const uint32_t* st = tile_status + (size_t)t * kStatusWords;
+            uint32_t f, spins = 0;
+            while (((f = ld_acquire_u32(st)) >> 2) != epoch) {
+                if (++spins > (1u << 22)) __trap();  // a predecessor that never publishes must fault, not hang
+                __nanosleep(32);
+            }
+            slot = f & 3u;
+            v = lb_load(st, slot);
         }
-        const uint32_t inc = __ballot_sync(0xFFFFFFFFu, is_inc);
-        const uint32_t last = inc ? (uint32_t)__ffs((int)inc) - 1u : 31u;
-        const LbState R = lb_reduce_lanes(v, last);
+        const uint32_t inc = __ballot_sync(0xFFFFFFFFu, slot == kLbInc);
+        // lanes 0..nearest take part.  (The window-init state is not a unit of lb_combine on the
+        // right -- its virtual newline would be lost -- so the lanes beyond are left out, not zeroed.)
+        const uint32_t nearest = inc ? (uint32_t)__ffs((int)inc) - 1u : 31u;
+        // ordered reduction: a higher lane is an EARLIER tile
+#pragma unroll
+        for (uint32_t d = 1; d < 32u; d <<= 1) {
+            const LbState o = lb_shfl_down(v, d);
+            if (lane + d <= nearest) v = lb_combine(o, v);
+        }
+        const LbState R = lb_bcast0(v);
         E = have ? lb_combine(R, E) : R;
         have = true;
-        if (inc) return E;
+        if (inc) break;
+        base -= 32;
     }
+    return E;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1130,11 +1096,11 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
                 }
                 const uint32_t ti = t - W.first_tile;
                 uint32_t* const my_status = P.tile_status + (size_t)ti * kStatusWords;
-                if (lane == 0 && ti != 0u) lb_publish(my_status + kLbAggOff, mine, P.epoch);
-                const LbState E = lb_look_back(P.tile_status, P.group_status, ti, W.begin, P.epoch, mine);
+                if (lane == 0 && ti != 0u) lb_publish(my_status, kLbAgg, mine, P.epoch);
+                const LbState E = lb_look_back(P.tile_status, ti, W.begin, P.epoch);
                 const LbState I = lb_combine(E, mine);
                 if (lane == 0) {
-                    lb_publish(my_status + kLbIncOff, I, P.epoch);
+                    lb_publish(my_status, kLbInc, I, P.epoch);
                     const BsqPrefix q = bsq_prefix_from(lb_to_summary(E), W.begin);
                     S.pre = q;
                     S.nlx[0] = 0; S.nlx[1] = q.prev[2]; S.nlx[2] = q.prev[1]; S.nlx[3] = q.prev[0];

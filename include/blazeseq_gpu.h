@@ -70,7 +70,8 @@ typedef struct bsq_config {
     int32_t batch_size;            /* FastqParser._batch_size, DEFAULT_BATCH_SIZE = 4096 */
     int64_t h2d_chunk_bytes;       /* staging chunk for bsq_parse_host (default 64 MiB) */
     int32_t force_id_slow_path;    /* tests: always take the id strip pipeline */
-    int32_t inflate_threads;       /* bsq_stream_*: host threads that inflate BGZF members (0 = all cores); the
+    int32_t inflate_threads;       /* bsq_stream_*: host threads that inflate BGZF members / read slices of a plain
+                                      file (0 = all cores, at most 8 for plain reads); the
                                       parallelism argument of RapidgzipReader, readers.mojo:380-443 */
 } bsq_config;
 

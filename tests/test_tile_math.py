@@ -139,8 +139,8 @@ def test_decoupled_lookback_algebra(tm, mutate):
         data = _rand_stream(rng, int(rng.integers(0, 60)), mutate)
         pad = int(rng.integers(0, 40))
         buf = np.frombuffer(b"\xaa" * pad + data, np.uint8)
-        for tile in (1, 3, 16, 61, 4096):
-            for inc_every in (0, 1, 2, 5, 33, 40):
+        for tile in (1, 3, 16, 61, 4096):      # tile = 1: hundreds of tiles, i.e. many groups of 32
+            for inc_every in (0, 1, 2, 5, 32, 33, 40, 1000):
                 assert tm.tm_lookback_check(buf.ctypes.data, pad, buf.size, tile, inc_every) == 0, (trial, tile, inc_every)
     for data in (b"\n" * 300, b"A" * 300, b"@\n\n+\n\n" * 50):
         buf = np.frombuffer(data, np.uint8)
