@@ -25,7 +25,7 @@ SYMBOLS = [
     "bsq_get_soa", "bsq_batch_to_host", "bsq_offsets_to_host", "bsq_pass_device_input",
     "bsq_last_timing", "bsq_compute_num_reads_for_size", "bsq_synth_size", "bsq_synth_device",
     "bsq_summarize_device", "bsq_shard_prefix", "bsq_stream_open", "bsq_stream_next", "bsq_stream_region",
-    "bsq_stream_get_stats", "bsq_stream_close",
+    "bsq_stream_get_stats", "bsq_stream_close", "bsq_quality_sums",
 ]
 
 
@@ -145,6 +145,7 @@ def lib():
     L.bsq_stream_get_stats.argtypes = [vp, C.POINTER(StreamStats)]
     L.bsq_stream_close.argtypes = [vp]
     L.bsq_stream_close.restype = None
+    L.bsq_quality_sums.argtypes = [vp, i64, i64, vp, vp]
     for name in ("bsq_stream_open", "bsq_stream_next", "bsq_stream_get_stats", "bsq_create", "bsq_get_offsets", "bsq_get_batch", "bsq_get_soa", "bsq_batch_to_host",
                  "bsq_offsets_to_host", "bsq_last_timing", "bsq_synth_device", "bsq_summarize_device",
                  "bsq_shard_prefix"):

@@ -122,6 +122,40 @@ __global__ void __launch_bounds__(256) k_rebase(int64_t* __restrict__ ends, int6
 }
 
 // ------------------------------------------------------------------------------------------------
+// A consumer of the device-resident SoA (the role of examples/nw_gpu/kernels.mojo:21-89, which takes a
+// DeviceFastqBatch's qual_buffer + ends): per-record sum of Phred scores, one warp per record, straight
+// from the quality arena -- no host round trip between the parse and the consumer.
+// ends[] are per-batch rebased (record_batch.mojo:82-87); ends_base[b] is the arena offset of batch b.
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_quality_sums(const uint8_t* __restrict__ qual, const int64_t* __restrict__ ends,
+                                                      const int64_t* __restrict__ ends_base, int64_t first, int64_t count,
+                                                      int32_t batch_size, uint32_t offset, int32_t* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < count; r += warps) {
+        const int64_t k = first + r, b = k / batch_size;
+        const int64_t base = ends_base[b];
+        const int64_t lo = base + (k % batch_size == 0 ? 0 : ends[k - 1]), hi = base + ends[k];
+        // aligned 4-byte words covering [lo, hi); bytes outside the record are masked off
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(qual + (lo & ~int64_t(3)));
+        const int64_t w_lo = lo & ~int64_t(3);
+        const int64_t n_words = ((hi + 3) >> 2) - (w_lo >> 2);
+        uint32_t sum = 0;
+        for (int64_t w = lane; w < n_words; w += 32) {
+            uint32_t v = __ldg(words + w);
+            const int64_t p0 = w_lo + 4 * w;                      // arena offset of the word's first byte
+            if (p0 < lo) v &= 0xFFFFFFFFu << (8u * (uint32_t)(lo - p0));
+            if (p0 + 4 > hi) v &= 0xFFFFFFFFu >> (8u * (uint32_t)(p0 + 4 - hi));
+            sum = __dp4a(v, 0x01010101u, sum);                    // sum of the four (unsigned) bytes
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+        if (lane == 0) out[r] = (int32_t)sum - (int32_t)(offset * (uint32_t)(hi - lo));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // id strip pipeline (taken only when some header needs _strip_spaces, e.g. CRLF input)
 // ------------------------------------------------------------------------------------------------
 

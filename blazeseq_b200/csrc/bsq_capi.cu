@@ -1356,6 +1356,27 @@ extern "C" bsq_status bsq_batch_to_host(bsq_parser* p, int64_t b, uint8_t* seq, 
     return BSQ_OK;
 }
 
+extern "C" bsq_status bsq_quality_sums(bsq_parser* p, int64_t first_record, int64_t count, int32_t* out_device,
+                                       int32_t* out_host) {
+    if (!p || first_record < 0 || count < 0) return BSQ_E_ARG;
+    if (!p->have_pass || !(p->want & BSQ_WANT_BATCHES)) return BSQ_E_STATE;
+    if (first_record + count > p->total_records) return BSQ_E_ARG;
+    if (count == 0) return BSQ_OK;
+    CK(cudaSetDevice(p->cfg.device_id));
+    int32_t* dst = out_device;
+    if (!dst) {
+        CK(p->cub_tmp.ensure(4ull * (size_t)count, 1 << 16));
+        dst = p->cub_tmp.as<int32_t>();
+    }
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)p->sm_count * 8, (count + 7) / 8));
+    k_quality_sums<<<grid, 256, 0, p->stream>>>(p->qual_out.as<uint8_t>(), p->ends.as<int64_t>(), p->ends_base.as<int64_t>(),
+                                                 first_record, count, p->cfg.batch_size, (uint32_t)p->cfg.q_offset, dst);
+    CK(cudaGetLastError());
+    if (out_host) CK(cudaMemcpyAsync(out_host, dst, 4ull * (size_t)count, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return BSQ_OK;
+}
+
 extern "C" bsq_status bsq_offsets_to_host(bsq_parser* p, int32_t window, uint32_t* line_ends, uint32_t* id_spans) {
     bsq_offsets_view v;
     bsq_status st = bsq_get_offsets(p, window, &v);

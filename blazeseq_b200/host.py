@@ -434,6 +434,16 @@ class GpuParser:
                    self._h, "bsq_batch_to_host")
         return seq, qual, idb, ends, id_ends
 
+    def quality_sums(self, first_record: int = 0, count: Optional[int] = None, out_device_ptr: int = 0) -> np.ndarray:
+        """Per-record sum of Phred scores of the last batches() pass, computed on the device from the SoA
+        (bsq_quality_sums): the parse -> consumer hand-off without a host round trip."""
+        if count is None:
+            count = int(self.result.n_records) - first_record
+        out = np.zeros(max(count, 0), np.int32)
+        capi.check(capi.lib().bsq_quality_sums(self._h, first_record, count, C.c_void_p(out_device_ptr or None),
+                                               C.c_void_p(out.ctypes.data if count > 0 else None)), self._h)
+        return out
+
     def timing(self):
         ms = (C.c_float * 5)()
         n = C.c_int64()

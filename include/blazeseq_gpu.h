@@ -213,6 +213,14 @@ void bsq_stream_close(bsq_stream* s);
 
 /* ---- results of the last pass -------------------------------------------------------------- */
 
+/* A consumer of the device-resident SoA of the last batches() pass -- the hand-off BlazeSeq's GPU story is
+ * about (DeviceFastqBatch, fastq/record_batch.mojo:210-220, consumed by a kernel in
+ * examples/nw_gpu/kernels.mojo:21-89): per-record sum of Phred scores (quality byte - cfg.q_offset) for the
+ * arena records [first_record, first_record + count), computed on the device from the quality arena and the
+ * per-batch `ends`.  The int32 results go to out_device (device pointer, may be NULL: a library buffer is
+ * used) and, if out_host is not NULL, are copied there.  The parsed bytes never visit the host. */
+bsq_status bsq_quality_sums(bsq_parser* p, int64_t first_record, int64_t count, int32_t* out_device, int32_t* out_host);
+
 bsq_status bsq_get_offsets(const bsq_parser* p, int32_t window, bsq_offsets_view* out);
 /* FastqParser.next_batch(max_records) restricted to the pass: batch b holds records
  * [b*batch_size, min((b+1)*batch_size, n_records)). */

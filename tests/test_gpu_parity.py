@@ -271,6 +271,25 @@ def test_single_pass_lookback_kernel(U, B, oracle, mutate, monkeypatch):
         U.check_stream(oracle, b"@long\n" + seq + b"\n+\n" + b"I" * 70000 + b"\n@s\nAC\n+\nII\n", batch_size=3)
 
 
+def test_device_consumer_quality_sums(B, oracle):
+    """bsq_quality_sums reads the device-resident SoA of a batches() pass (quality arena + per-batch ends):
+    per-record Phred sums equal the host computation on the input bytes, across batch and window edges."""
+    from blazeseq_b200 import _capi as capi
+    rng = np.random.default_rng(21)
+    data = np.frombuffer(_rand_stream(rng, 5000, "none", maxlen=260), np.uint8)
+    views, bases, err = oracle.parse_all(data.tobytes())
+    exp = np.array([int(data[int(v["qual_start"]):int(v["qual_start"]) + int(v["qual_len"])].astype(np.int64).sum())
+                    - 33 * int(v["qual_len"]) for v in views], np.int64)
+    for m in (1, 7, 512, 4096):
+        gpu = B.GpuParser(False, False, B.parse_schema("generic"), m, buffer_growth_enabled=True)
+        res = gpu.parse_host(data, want=capi.WANT_BATCHES)
+        assert res.n_records == len(views)
+        got = gpu.quality_sums()
+        assert np.array_equal(got.astype(np.int64), exp)
+        assert np.array_equal(gpu.quality_sums(1234, 100).astype(np.int64), exp[1234:1334])
+        gpu.close()
+
+
 def test_id_strip_paths_agree(U, oracle):
     """CRLF and padded ids take the strip pipeline; forcing it on clean input changes nothing."""
     rng = np.random.default_rng(5)
