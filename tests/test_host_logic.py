@@ -218,3 +218,28 @@ def test_sharded_parse_over_gloo(oracle, world):
         assert first_record == first and code == oracle.EOF
         assert (reads, total_bases) == (len(views), bases)
         first += n
+
+
+def test_bgzf_writer_members():
+    """blazeseq_b200/bgzf.py writes what the stream pipeline's block-parallel inflater expects (SAM spec 4.1):
+    gzip members of <= 64 KiB with the 'BC' extra field holding the member size, closed by the empty member;
+    any gzip reader concatenates them back."""
+    import gzip
+    import struct
+
+    from blazeseq_b200 import bgzf
+    rng = np.random.default_rng(3)
+    data = rng.integers(0, 256, 200001, dtype=np.uint8).tobytes() + b"ACGT" * 40000
+    for threads in (1, 4):
+        blob = bgzf.compress(data, level=1, threads=threads)
+        assert gzip.decompress(blob) == data
+        pos, total, n = 0, 0, 0
+        while pos < len(blob):
+            assert blob[pos:pos + 4] == b"\x1f\x8b\x08\x04" and blob[pos + 10:pos + 16] == b"\x06\x00BC\x02\x00"
+            size = struct.unpack_from("<H", blob, pos + 16)[0] + 1
+            isize = struct.unpack_from("<I", blob, pos + size - 4)[0]
+            assert isize <= 0x10000
+            total += isize
+            pos += size
+            n += 1
+        assert pos == len(blob) and total == len(data) and isize == 0 and n == -(-len(data) // bgzf.BLOCK) + 1
