@@ -61,6 +61,7 @@ struct Window {
     int64_t seq_base = 0, qual_base = 0, id_base = 0;
     DevBuf line_ends;                // views(): newlines + 2 entries
     DevBuf run_pre;                  // BsqPrefix per run (kept for the resolve pass)
+    DevBuf nl_count, nl_list;        // per tile: newline count and ordered list (k_summarize -> k_resolve)
 };
 
 struct HostMirror {                  // pinned
@@ -216,10 +217,19 @@ bsq_status setup_kernels(bsq_parser* p) {
 }
 
 // Summarise + scan one window; leaves the ScanOut in w.scan (host) after a stream sync.
-bsq_status summarize_window(bsq_parser* p, Window& w, bool sums) {
+bsq_status summarize_window(bsq_parser* p, Window& w, bool sums, bool hand_off = false) {
     CK(p->run_sum.ensure(sizeof(BsqSummary) * kMaxRuns));
     CK(w.run_pre.ensure(sizeof(BsqPrefix) * kMaxRuns));
     CK(p->scan_out.ensure(sizeof(ScanOut)));
+    if (hand_off) {   // the per-tile newline lists k_resolve picks up (BSQ_NO_LIST_HANDOFF=1: rebuild them there)
+        const size_t tiles = w.wp.n_tiles - w.wp.first_tile;
+        CK(w.nl_count.ensure(4 * tiles, 1 << 16));
+        CK(w.nl_list.ensure(2ull * kNlCap * tiles, 1 << 20));
+        w.wp.nl_count = w.nl_count.as<uint32_t>();
+        w.wp.nl_list = w.nl_list.as<uint16_t>();
+    } else {
+        w.wp.nl_count = nullptr; w.wp.nl_list = nullptr;
+    }
     if (sums) k_summarize<true><<<w.wp.n_runs, kThreads, smem_bytes_summarize(), p->stream>>>(w.wp, p->run_sum.as<BsqSummary>());
     else k_summarize<false><<<w.wp.n_runs, kThreads, smem_bytes_summarize(), p->stream>>>(w.wp, p->run_sum.as<BsqSummary>());
     k_scan_runs<<<1, kScanThreads, 0, p->stream>>>(p->run_sum.as<BsqSummary>(), w.wp.n_runs, w.wp.begin,
@@ -320,7 +330,7 @@ extern "C" void bsq_destroy(bsq_parser* p) {
     cudaSetDevice(p->cfg.device_id);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->copy_stream) cudaStreamSynchronize(p->copy_stream);
-    for (auto& w : p->win) { w.line_ends.release(); w.run_pre.release(); }
+    for (auto& w : p->win) { w.line_ends.release(); w.run_pre.release(); w.nl_count.release(); w.nl_list.release(); }
     DevBuf* bufs[] = {&p->run_sum, &p->scan_out, &p->err_word, &p->tail_out, &p->cub_tmp, &p->len_prefix,
                       &p->seq_out, &p->qual_out, &p->id_out, &p->ends, &p->id_ends, &p->ends_base,
                       &p->id_ends_base, &p->id_spans, &p->host_input, &p->tile_status, &p->ticket};
@@ -383,6 +393,9 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     const bool fused = fused_kern != nullptr;
     p->last_pass_fused = fused;
     const size_t smem_res = smem_bytes(want_pack, cfg.check_ascii || cfg.check_quality);
+    // k_summarize hands every tile's ordered newline list to k_resolve unless the bitmaps are needed there anyway
+    bool list_hand_off = kStages == 1 && !cfg.check_ascii && !cfg.check_quality;
+    if (const char* e = getenv("BSQ_NO_LIST_HANDOFF")) list_hand_off = list_hand_off && atoi(e) == 0;
     CK(cudaEventRecord(p->ev[0], p->stream));
 
     bool id_fast = cfg.force_id_slow_path == 0;   // optimistic: k_resolve raises the strip flag when an id needs stripping
@@ -523,7 +536,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         if (st != BSQ_OK) return st;
         plan_window(p, w, d + pos, bytes, want_pack);
         w.region_off = pos;
-        st = summarize_window(p, w, want_pack);
+        st = summarize_window(p, w, want_pack, list_hand_off);
         if (st != BSQ_OK) return st;
         ++nw;
         const uint64_t consumed = w.scan.totals.consumed_end - w.wp.begin;

@@ -84,6 +84,9 @@ struct WinParams {
     uint32_t n_tiles;        // tiles [first_tile, n_tiles) cover [begin, end)
     uint32_t tiles_per_run;
     uint32_t n_runs;
+    // hand-off from k_summarize to k_resolve (may be null: nothing is written / nothing is read):
+    uint32_t* nl_count;      // [tile - first_tile] newlines of the tile
+    uint16_t* nl_list;       // [tile - first_tile][kNlCap] tile-relative newline positions, valid when count <= kNlCap
 };
 
 struct ScanOut {             // written by k_scan_runs, read by the host
@@ -206,6 +209,8 @@ struct alignas(128) TileSmem {
                                               // nlx[kHead-1-i] = i-th newline before the list
     uint32_t sdst[3][kLinesCap];              // per class stream: destination of each line
     uint32_t ssrc[3][kLinesCap];              //                   source position of each line
+    alignas(16) uint16_t nl16[kNlCap];        // the tile's newline list from k_summarize (TMA destination)
+    uint32_t tile_total[2];                   // newline count of the current / next tile (double buffered)
     // ---- single-pass (fused) launches ----
     BsqPrefix pre;                            // this tile's prefix, from the look-back
     uint32_t next_tile;                       // the tile this CTA claimed for its next iteration
@@ -220,6 +225,7 @@ static_assert(2 * kWords * 4 <= kStage, "the validation bitmaps fit the stage bu
 
 // k_summarize: the same front end on its own (double-buffered) ring
 constexpr int kSumStages = 2;
+static_assert(kNlCap * 2 <= kHalo, "k_summarize keeps the newline list in an unused halo");
 struct alignas(128) SumSmem {
     alignas(128) uint8_t data[kSumStages][kHalo + kTile + kTilePad];
     alignas(8) uint64_t full_bar[kSumStages];
@@ -228,6 +234,9 @@ struct alignas(128) SumSmem {
     uint32_t k1_head[8];                      // [0..3] last four newlines, [4..7] first four
     uint32_t k1_red[kWarps * 4];
     alignas(16) uint32_t bm_nl[kWords];
+    // tile-relative newline positions, in order (handed to k_resolve): they live in the halo bytes of ring
+    // slot 0, which k_summarize never loads
+    __device__ __forceinline__ uint16_t* list() { return reinterpret_cast<uint16_t*>(data[0]); }
     __device__ __forceinline__ uint32_t* bm_hi() { return nullptr; }    // (never used: build_bitmaps<false, false>)
     __device__ __forceinline__ uint32_t* bm_bad() { return nullptr; }
 };
@@ -250,14 +259,19 @@ __device__ __forceinline__ uint32_t tile_bytes_rounded(const WinParams& W, uint3
     return (n + 15u) & ~15u;  // stays inside the 16-byte granule that holds the last valid byte
 }
 
+// list_count: newlines of the tile when its ordered list (k_summarize's hand-off) is to arrive with it, else 0
 template <bool kWithHalo, typename SM>
-__device__ __forceinline__ void issue_tile_load(SM& S, const WinParams& W, uint32_t tile, uint32_t stage) {
+__device__ __forceinline__ void issue_tile_load(SM& S, const WinParams& W, uint32_t tile, uint32_t stage,
+                                                uint16_t* list_dst = nullptr, uint32_t list_count = 0) {
     const uint32_t bytes = tile_bytes_rounded(W, tile);
     const size_t origin = (size_t)tile * kTile;
     // the halo is the end of the previous tile (an L2 hit: this CTA or its neighbour just read it)
     const uint32_t halo = (kWithHalo && origin >= (size_t)kHalo) ? (uint32_t)kHalo : 0u;
-    mbar_expect_tx(&S.full_bar[stage], bytes + halo);
+    const uint32_t list_bytes = (list_count * 2u + 15u) & ~15u;
+    mbar_expect_tx(&S.full_bar[stage], bytes + halo + list_bytes);
     tma_load_1d(S.data[stage] + (kHalo - halo), W.base + origin - halo, bytes + halo, &S.full_bar[stage]);
+    if (list_bytes != 0u)
+        tma_load_1d(list_dst, W.nl_list + (size_t)(tile - W.first_tile) * kNlCap, list_bytes, &S.full_bar[stage]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -512,31 +526,62 @@ __global__ void __launch_bounds__(kThreads, kSummarizeCtas) k_summarize(const Wi
         const uint32_t cnt = popc_words(words);
         uint32_t total;
         const uint32_t excl = block_exclusive_scan(S, cnt, total, par);
-        // this thread's newlines: index in the run = run_count + excl + k
-        const bool edge = run_count + excl < 4u || excl + cnt + 4u > total;   // among the first / last four
-        if (cnt != 0u && (kSums || edge)) {
-            for_each_newline_loop(words, c.origin + tid * kBytesPerThread, excl, [&](uint32_t r, uint32_t p) {
-                if (kSums) {
-                    const uint32_t cls = (run_count + r) & 3u;
-                    acc[0] += cls == 0u ? p : 0u;
-                    acc[1] += cls == 1u ? p : 0u;
-                    acc[2] += cls == 2u ? p : 0u;
-                    acc[3] += cls == 3u ? p : 0u;
-                }
-                if (edge) {
-                    if (run_count + r < 4u) S.k1_head[4u + run_count + r] = p;     // first[] of the run
-                    if (r + 4u >= total) S.carry[r + 4u - total] = p;             // last four of the tile
-                }
-            });
+        if (total <= (uint32_t)kNlCap) {
+            // the ordered list of the tile's newlines (tile-relative, 16 bit): k_resolve picks it up instead of
+            // rebuilding it, and the run's position sums and edge positions are read off it here
+            uint16_t* const list = S.list();
+            if (cnt != 0u)
+                for_each_newline(words, tid * kBytesPerThread, excl, [&](uint32_t r, uint32_t p) { list[r] = (uint16_t)p; });
+            __syncthreads();
+            if (kSums) {
+                uint32_t a = 0;                        // index in the run = run_count + j: one class per thread
+                for (uint32_t j = tid; j < total; j += kThreads) a += c.origin + (uint32_t)list[j];
+                const uint32_t cls = (run_count + tid) & 3u;
+                acc[0] += cls == 0u ? a : 0u; acc[1] += cls == 1u ? a : 0u;
+                acc[2] += cls == 2u ? a : 0u; acc[3] += cls == 3u ? a : 0u;
+            }
+            if (W.nl_list != nullptr) {                // coalesced copy-out, two positions per store
+                uint32_t* g = reinterpret_cast<uint32_t*>(W.nl_list + (size_t)(t - W.first_tile) * kNlCap);
+                const uint32_t* l = reinterpret_cast<const uint32_t*>(list);
+                for (uint32_t j = tid; j < (total + 1u) >> 1; j += kThreads) g[j] = l[j];
+            }
+            if (tid == 0 && total != 0u) {
+                for (uint32_t r = 0; r < total && run_count + r < 4u; ++r)           // first[] of the run
+                    S.k1_head[4u + run_count + r] = c.origin + (uint32_t)list[r];
+                // merge the tile's last (up to four) newlines into the run's last four (oldest first)
+                const uint32_t k = total < 4u ? total : 4u;
+                uint32_t h[4];
+                for (uint32_t i = 0; i < 4u; ++i)
+                    h[i] = i + k < 4u ? S.k1_head[i + k] : c.origin + (uint32_t)list[total - 4u + i];
+                for (uint32_t i = 0; i < 4u; ++i) S.k1_head[i] = h[i];
+            }
+        } else {
+            // more newlines than the list holds: visit them from the bitmap
+            const bool edge = run_count + excl < 4u || excl + cnt + 4u > total;   // among the first / last four
+            if (cnt != 0u && (kSums || edge)) {
+                for_each_newline_loop(words, c.origin + tid * kBytesPerThread, excl, [&](uint32_t r, uint32_t p) {
+                    if (kSums) {
+                        const uint32_t cls = (run_count + r) & 3u;
+                        acc[0] += cls == 0u ? p : 0u;
+                        acc[1] += cls == 1u ? p : 0u;
+                        acc[2] += cls == 2u ? p : 0u;
+                        acc[3] += cls == 3u ? p : 0u;
+                    }
+                    if (edge) {
+                        if (run_count + r < 4u) S.k1_head[4u + run_count + r] = p;     // first[] of the run
+                        if (r + 4u >= total) S.carry[r + 4u - total] = p;             // last four of the tile
+                    }
+                });
+            }
+            __syncthreads();
+            if (tid == 0 && total != 0u) {
+                const uint32_t k = total < 4u ? total : 4u;
+                uint32_t h[4];
+                for (uint32_t i = 0; i < 4u; ++i) h[i] = i + k < 4u ? S.k1_head[i + k] : S.carry[i];
+                for (uint32_t i = 0; i < 4u; ++i) S.k1_head[i] = h[i];
+            }
         }
-        __syncthreads();
-        if (tid == 0 && total != 0u) {
-            // merge the tile's last (up to four) newlines into the run's last four (oldest first)
-            const uint32_t k = total < 4u ? total : 4u;
-            uint32_t h[4];
-            for (uint32_t i = 0; i < 4u; ++i) h[i] = i + k < 4u ? S.k1_head[i + k] : S.carry[i];
-            for (uint32_t i = 0; i < 4u; ++i) S.k1_head[i] = h[i];
-        }
+        if (W.nl_count != nullptr && tid == 0) W.nl_count[t - W.first_tile] = total;
         run_count += total;
         __syncthreads();  // every thread is done with data[stage] and the head is updated
         if (tid == 0 && t + kSumStages < tb) issue_tile_load<false>(S, W, t + kSumStages, c.stage);
@@ -1012,8 +1057,26 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
     }
     __syncthreads();
     if (kFused) { ta = S.first_claim; tb = W.n_tiles; }
-    if (tid == 0)
-        for (uint32_t s = 0; s < (uint32_t)kStages && ta + s < tb; ++s) issue_tile_load<true>(S, W, ta + s, s);
+    // kList: the ordered newline list of every tile comes from k_summarize (same TMA transaction as the tile),
+    // so the bitmap / scan / list front end runs only where the bitmaps are needed anyway (validation), in the
+    // single pass, and for tiles with more newlines than the list holds
+    constexpr bool kList = !kAscii && !kQual && !kFused && kStages == 1;
+    const bool use_list = kList && W.nl_list != nullptr;
+    auto list_count_of = [&](uint32_t tile) -> uint32_t {
+        const uint32_t n = W.nl_count[tile - W.first_tile];
+        return n;
+    };
+    uint32_t n_next = 0;                               // (thread 0) newline count of tile t + 1
+    if (tid == 0) {
+        if (use_list && ta < tb) {
+            const uint32_t n0 = list_count_of(ta);
+            S.tile_total[0] = n0;
+            issue_tile_load<true>(S, W, ta, 0, S.nl16, n0 <= (uint32_t)kNlCap ? n0 : 0u);
+            if (ta + 1u < tb) n_next = list_count_of(ta + 1u);
+        } else {
+            for (uint32_t s = 0; s < (uint32_t)kStages && ta + s < tb; ++s) issue_tile_load<true>(S, W, ta + s, s);
+        }
+    }
     if (kOffsets && tid == 0 && (kFused ? ta == W.first_tile : blockIdx.x == 0)) P.line_ends[0] = W.begin - 1u;
 
     const uint32_t addlo = (128u - P.lower) * 0x01010101u, addup = (127u - P.upper) * 0x01010101u;
@@ -1044,18 +1107,40 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
             if (tid < 4) S.agg_p[tid] = 0;
         } else if (kStages == 1 && tid == 0 && t + 1u < tb) {   // single buffer: the next tile waits in L2
             prefetch_l2(W.base + (size_t)(t + 1u) * kTile, tile_bytes_rounded(W, t + 1u));
+            if (use_list && n_next != 0u && n_next <= (uint32_t)kNlCap)
+                prefetch_l2(W.nl_list + (size_t)(t + 1u - W.first_tile) * kNlCap, (n_next * 2u + 15u) & ~15u);
         }
         if (kPack && (kAscii || kQual)) {              // the validation bitmaps reuse `stage`: the previous
             if (tid == 0) tma_store_wait_read();       // tile's bulk stores and edge stores must be through with it
             __syncthreads();
         }
-        build_bitmaps<kAscii, kQual>(S, c, addlo, addup);
-        __syncthreads();
+        // the newline counts travel ahead of the tiles: thread 0 publishes the next tile's count (loaded one
+        // tile ago) and starts loading the one after it, so that neither costs a round trip here
+        uint32_t n_next2 = 0;
+        if (use_list && tid == 0) {
+            S.tile_total[(it + 1u) & 1u] = n_next;
+            if (t + 2u < tb) n_next2 = list_count_of(t + 2u);
+        }
+        NlWords words;
+#pragma unroll
+        for (int i = 0; i < kWordsPerThread; ++i) words.w[i] = 0u;
+        uint32_t total = 0, excl = 0;
+        bool listed = false;                           // nlx already holds this tile's newline list
+        if (use_list) {
+            total = S.tile_total[it & 1u];             // written during the previous tile (or the prologue)
+            listed = total <= (uint32_t)kNlCap;
+        }
+        if (listed) {
+            for (uint32_t j = tid; j < total; j += kThreads) S.nlx[kHead + j] = c.origin + (uint32_t)S.nl16[j];
+            __syncthreads();
+        } else {
+            build_bitmaps<kAscii, kQual>(S, c, addlo, addup);
+            __syncthreads();
+            words = load_nl_words(S, tid);
+            const uint32_t cnt = popc_words(words);
+            excl = block_exclusive_scan(S, cnt, total, par);
+        }
         const uint32_t t_next = kFused ? S.next_tile : t + 1u;
-        const NlWords words = load_nl_words(S, tid);
-        const uint32_t cnt = popc_words(words);
-        uint32_t total;
-        const uint32_t excl = block_exclusive_scan(S, cnt, total, par);
 
         if (kFused) {
             // ---- the tile's aggregate, the look-back, the tile's prefix --------------------------
@@ -1150,7 +1235,9 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
 
         for (uint32_t pass = 0; pass < total; pass += kNlCap) {
             const uint32_t n = total - pass < (uint32_t)kNlCap ? total - pass : (uint32_t)kNlCap;
-            if (!kFused) {
+            if (listed) {
+                // (the list is in place)
+            } else if (!kFused) {
                 if (total <= (uint32_t)kNlCap) fill_newline_list<false>(S, c, words, excl, 0u);
                 else fill_newline_list<true>(S, c, words, excl, pass);
                 __syncthreads();
@@ -1340,7 +1427,7 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
             } else {
                 __syncthreads();
                 rotate_head(S, n);
-                if (pass + (uint32_t)kNlCap < total) __syncthreads();   // the next pass refills the list
+                if (pass + (uint32_t)kNlCap < total || use_list) __syncthreads();   // the next pass / tile refills the list
             }
         }
         rank += total;
@@ -1348,6 +1435,11 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
         if (kFused) {
             if (tid == 0 && t_next < tb) issue_tile_load<true>(S, W, t_next, c.stage);
             t = t_next;
+        } else if (use_list) {
+            if (tid == 0 && t + 1u < tb)
+                issue_tile_load<true>(S, W, t + 1u, c.stage, S.nl16, n_next <= (uint32_t)kNlCap ? n_next : 0u);
+            n_next = n_next2;
+            ++t;
         } else {
             if (tid == 0 && t + kStages < tb) issue_tile_load<true>(S, W, t + kStages, c.stage);
             ++t;
