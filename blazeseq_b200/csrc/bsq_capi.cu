@@ -206,9 +206,18 @@ ResolveKernel pick_resolve(bool ascii, bool qual, bool offs, bool pack, bool fus
     return pick_resolve_t<false>(ascii, qual, offs, pack);
 }
 
+using SummarizeKernel = void (*)(const WinParams, BsqSummary*, uint32_t, uint32_t);
+SummarizeKernel pick_summarize(bool sums, bool hi, bool bad) {
+    static const SummarizeKernel table[8] = {
+        k_summarize<false, false, false>, k_summarize<false, false, true>, k_summarize<false, true, false>,
+        k_summarize<false, true, true>,   k_summarize<true, false, false>, k_summarize<true, false, true>,
+        k_summarize<true, true, false>,   k_summarize<true, true, true>,
+    };
+    return table[(sums ? 4 : 0) | (hi ? 2 : 0) | (bad ? 1 : 0)];
+}
+
 bsq_status setup_kernels(bsq_parser* p) {
-    CK(opt_in_smem(k_summarize<true>, smem_bytes_summarize()));
-    CK(opt_in_smem(k_summarize<false>, smem_bytes_summarize()));
+    for (int i = 0; i < 8; ++i) CK(opt_in_smem(pick_summarize(i & 4, i & 2, i & 1), smem_bytes_summarize()));
     for (int i = 0; i < 16; ++i) {
         CK(opt_in_smem(pick_resolve(i & 8, i & 4, i & 2, i & 1), smem_bytes()));
         if (kStages == 1) CK(opt_in_smem(pick_resolve(i & 8, i & 4, i & 2, i & 1, true), smem_bytes()));
@@ -230,8 +239,10 @@ bsq_status summarize_window(bsq_parser* p, Window& w, bool sums, bool hand_off =
     } else {
         w.wp.nl_count = nullptr; w.wp.nl_list = nullptr;
     }
-    if (sums) k_summarize<true><<<w.wp.n_runs, kThreads, smem_bytes_summarize(), p->stream>>>(w.wp, p->run_sum.as<BsqSummary>());
-    else k_summarize<false><<<w.wp.n_runs, kThreads, smem_bytes_summarize(), p->stream>>>(w.wp, p->run_sum.as<BsqSummary>());
+    // with the hand-off, a validating pass also screens every tile for HI / BAD bytes (k_resolve skips clean tiles)
+    const bool hi = hand_off && p->cfg.check_ascii, bad = hand_off && p->cfg.check_quality;
+    pick_summarize(sums, hi, bad)<<<w.wp.n_runs, kThreads, smem_bytes_summarize(), p->stream>>>(
+        w.wp, p->run_sum.as<BsqSummary>(), (uint32_t)p->cfg.q_lower, (uint32_t)p->cfg.q_upper);
     k_scan_runs<<<1, kScanThreads, 0, p->stream>>>(p->run_sum.as<BsqSummary>(), w.wp.n_runs, w.wp.begin,
                                           w.run_pre.as<BsqPrefix>(), p->scan_out.as<ScanOut>());
     p->n_launches += 2;
@@ -393,8 +404,8 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     const bool fused = fused_kern != nullptr;
     p->last_pass_fused = fused;
     const size_t smem_res = smem_bytes(want_pack, cfg.check_ascii || cfg.check_quality);
-    // k_summarize hands every tile's ordered newline list to k_resolve unless the bitmaps are needed there anyway
-    bool list_hand_off = kStages == 1 && !cfg.check_ascii && !cfg.check_quality;
+    // k_summarize hands every tile's ordered newline list (and, when validating, its HI / BAD screen) to k_resolve
+    bool list_hand_off = kStages == 1;
     if (const char* e = getenv("BSQ_NO_LIST_HANDOFF")) list_hand_off = list_hand_off && atoi(e) == 0;
     CK(cudaEventRecord(p->ev[0], p->stream));
 

@@ -233,6 +233,7 @@ struct alignas(128) SumSmem {
     uint32_t carry[8];
     uint32_t k1_head[8];                      // [0..3] last four newlines, [4..7] first four
     uint32_t k1_red[kWarps * 4];
+    uint32_t dirty;                           // validation screen of the current tile: bit 0 HI, bit 1 BAD
     alignas(16) uint32_t bm_nl[kWords];
     // tile-relative newline positions, in order (handed to k_resolve): they live in the halo bytes of ring
     // slot 0, which k_summarize never loads
@@ -323,6 +324,43 @@ __device__ __forceinline__ void build_bitmaps(SM& S, const TileCursor& c, uint32
             if (kBad) S.bm_bad()[w] = m_bad | (bo << 16);
         }
     }
+}
+
+// k_summarize with validation configured: the newline bitmap as above, plus a SCREEN of the tile for the two
+// validators -- does any byte have bit 7 set / does any non-newline byte lie outside [lower, upper]?  Returns
+// bit 0 / bit 1 for this thread's chunks.  No gathers and no bitmap stores: a clean tile (the normal case)
+// lets k_resolve skip the validation bitmaps and the per-byte walk; a flagged tile is examined there exactly.
+template <bool kHi, bool kBad, typename SM>
+__device__ __forceinline__ uint32_t build_nl_bitmap_and_screen(SM& S, const TileCursor& c, uint32_t addlo, uint32_t addup) {
+    const uint8_t* tile = S.data[c.stage] + kHalo;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t vlo = c.lo - c.origin, vhi = c.hi - c.origin;  // valid offsets in the tile
+    uint32_t any_hi = 0, any_bad = 0;
+#pragma unroll
+    for (int j = 0; j < kChunksPerThread; ++j) {
+        const uint32_t chunk = j * kThreads + tid;
+        const uint32_t off = chunk * 16u;
+        uint32_t m_nl = 0;
+        if (off < vhi && off + 16u > vlo) {
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + off);
+            const uint32_t f0 = bsq_nl_flags(v.x), f1 = bsq_nl_flags(v.y), f2 = bsq_nl_flags(v.z), f3 = bsq_nl_flags(v.w);
+            m_nl = mask16(f0, f1, f2, f3);
+            if (kHi) any_hi |= (v.x | v.y | v.z | v.w) & 0x80808080u;
+            if (kBad)
+                any_bad |= (bsq_badq_flags(v.x, addlo, addup) & ~f0) | (bsq_badq_flags(v.y, addlo, addup) & ~f1) |
+                           (bsq_badq_flags(v.z, addlo, addup) & ~f2) | (bsq_badq_flags(v.w, addlo, addup) & ~f3);
+            if (off < vlo || off + 16u > vhi) {
+                uint32_t keep = 0xFFFFu;
+                if (off < vlo) keep &= 0xFFFFu << (vlo - off);
+                if (off + 16u > vhi) keep &= 0xFFFFu >> (off + 16u - vhi);
+                m_nl &= keep;
+            }
+        }
+        const uint32_t xo = __shfl_down_sync(0xFFFFFFFFu, m_nl, 1);
+        if ((tid & 1u) == 0u) S.bm_nl[chunk >> 1] = m_nl | (xo << 16);
+    }
+    // (bytes outside the window in the two edge tiles are not masked here: the caller flags those tiles)
+    return (any_hi != 0u ? 1u : 0u) | (any_bad != 0u ? 2u : 0u);
 }
 
 // Exclusive prefix of `v` over the block (in thread order) and the block total.  One barrier:
@@ -495,8 +533,10 @@ __device__ __forceinline__ TileCursor make_cursor(const WinParams& W, uint32_t t
 // kSums = false (views-only passes): only the newline count and the first/last positions of the
 // run are needed; the per-class position sums that give the SoA destinations are skipped.
 // Shared memory: SumSmem.
-template <bool kSums>
-__global__ void __launch_bounds__(kThreads, kSummarizeCtas) k_summarize(const WinParams W, BsqSummary* __restrict__ run_sum) {
+constexpr uint32_t kNlCountMask = 0x0FFFFFFFu;   // nl_count word: newlines | validation screen << 30
+template <bool kSums, bool kHi, bool kBad>
+__global__ void __launch_bounds__(kThreads, kSummarizeCtas) k_summarize(const WinParams W, BsqSummary* __restrict__ run_sum,
+                                                                        uint32_t lower, uint32_t upper) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SumSmem& S = *reinterpret_cast<SumSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x;
@@ -508,9 +548,11 @@ __global__ void __launch_bounds__(kThreads, kSummarizeCtas) k_summarize(const Wi
         mbar_fence_init();
     }
     if (tid < 8) S.k1_head[tid] = 0;
+    if (tid == 0) S.dirty = 0;
     __syncthreads();
     if (tid == 0)
         for (uint32_t s = 0; s < (uint32_t)kSumStages && ta + s < tb; ++s) issue_tile_load<false>(S, W, ta + s, s);
+    const uint32_t addlo = (128u - lower) * 0x01010101u, addup = (127u - upper) * 0x01010101u;
 
     uint32_t run_count = 0;           // newlines of the run so far (uniform)
     uint32_t acc[4] = {0, 0, 0, 0};   // position sums by (index in run) mod 4, this thread's share
@@ -520,7 +562,13 @@ __global__ void __launch_bounds__(kThreads, kSummarizeCtas) k_summarize(const Wi
         const uint32_t it = t - ta;
         const TileCursor c = make_cursor(W, t, it % kSumStages);
         mbar_wait(&S.full_bar[c.stage], (it / kSumStages) & 1u);
-        build_bitmaps<false, false>(S, c, 0, 0);
+        if (kHi || kBad) {
+            uint32_t d = build_nl_bitmap_and_screen<kHi, kBad>(S, c, addlo, addup);
+            d = __reduce_or_sync(0xFFFFFFFFu, d);
+            if (d != 0u && (tid & 31u) == 0u) atomicOr(&S.dirty, d);
+        } else {
+            build_bitmaps<false, false>(S, c, 0, 0);
+        }
         __syncthreads();
         const NlWords words = load_nl_words(S, tid);
         const uint32_t cnt = popc_words(words);
@@ -581,7 +629,13 @@ __global__ void __launch_bounds__(kThreads, kSummarizeCtas) k_summarize(const Wi
                 for (uint32_t i = 0; i < 4u; ++i) S.k1_head[i] = h[i];
             }
         }
-        if (W.nl_count != nullptr && tid == 0) W.nl_count[t - W.first_tile] = total;
+        if (tid == 0) {
+            // an edge tile of the window holds foreign bytes the screen did not mask: examine it in k_resolve
+            const bool edge_tile = c.lo != c.origin || c.hi != c.origin + (uint32_t)kTile;
+            const uint32_t dirty = (kHi || kBad) ? (edge_tile ? 3u : S.dirty) : 0u;
+            if (W.nl_count != nullptr) W.nl_count[t - W.first_tile] = total | (dirty << 30);
+            S.dirty = 0;                               // (read above; the next tile ORs into it after the barrier below)
+        }
         run_count += total;
         __syncthreads();  // every thread is done with data[stage] and the head is updated
         if (tid == 0 && t + kSumStages < tb) issue_tile_load<false>(S, W, t + kSumStages, c.stage);
@@ -1060,18 +1114,23 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
     // kList: the ordered newline list of every tile comes from k_summarize (same TMA transaction as the tile),
     // so the bitmap / scan / list front end runs only where the bitmaps are needed anyway (validation), in the
     // single pass, and for tiles with more newlines than the list holds
-    constexpr bool kList = !kAscii && !kQual && !kFused && kStages == 1;
+    // (with validation: k_summarize also screened the tile -- a tile without a single HI / BAD byte needs
+    //  neither the validation bitmaps nor the per-byte walk, and takes the list too)
+    constexpr bool kList = !kFused && kStages == 1;
     const bool use_list = kList && W.nl_list != nullptr;
-    auto list_count_of = [&](uint32_t tile) -> uint32_t {
-        const uint32_t n = W.nl_count[tile - W.first_tile];
-        return n;
+    auto list_count_of = [&](uint32_t tile) -> uint32_t { return W.nl_count[tile - W.first_tile]; };   // raw word
+    // newlines of a tile whose list is usable by this instantiation, else 0 (raw = count | screen << 30)
+    auto list_ok = [&](uint32_t raw) -> bool {
+        const uint32_t n = raw & kNlCountMask, dirty = raw >> 30;
+        return n <= (uint32_t)kNlCap && !((kAscii && (dirty & 1u)) || (kQual && (dirty & 2u)));
     };
+    auto listed_count = [&](uint32_t raw) -> uint32_t { return list_ok(raw) ? (raw & kNlCountMask) : 0u; };
     uint32_t n_next = 0;                               // (thread 0) newline count of tile t + 1
     if (tid == 0) {
         if (use_list && ta < tb) {
             const uint32_t n0 = list_count_of(ta);
             S.tile_total[0] = n0;
-            issue_tile_load<true>(S, W, ta, 0, S.nl16, n0 <= (uint32_t)kNlCap ? n0 : 0u);
+            issue_tile_load<true>(S, W, ta, 0, S.nl16, listed_count(n0));
             if (ta + 1u < tb) n_next = list_count_of(ta + 1u);
         } else {
             for (uint32_t s = 0; s < (uint32_t)kStages && ta + s < tb; ++s) issue_tile_load<true>(S, W, ta + s, s);
@@ -1107,12 +1166,8 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
             if (tid < 4) S.agg_p[tid] = 0;
         } else if (kStages == 1 && tid == 0 && t + 1u < tb) {   // single buffer: the next tile waits in L2
             prefetch_l2(W.base + (size_t)(t + 1u) * kTile, tile_bytes_rounded(W, t + 1u));
-            if (use_list && n_next != 0u && n_next <= (uint32_t)kNlCap)
-                prefetch_l2(W.nl_list + (size_t)(t + 1u - W.first_tile) * kNlCap, (n_next * 2u + 15u) & ~15u);
-        }
-        if (kPack && (kAscii || kQual)) {              // the validation bitmaps reuse `stage`: the previous
-            if (tid == 0) tma_store_wait_read();       // tile's bulk stores and edge stores must be through with it
-            __syncthreads();
+            if (use_list && listed_count(n_next) != 0u)
+                prefetch_l2(W.nl_list + (size_t)(t + 1u - W.first_tile) * kNlCap, (listed_count(n_next) * 2u + 15u) & ~15u);
         }
         // the newline counts travel ahead of the tiles: thread 0 publishes the next tile's count (loaded one
         // tile ago) and starts loading the one after it, so that neither costs a round trip here
@@ -1127,13 +1182,18 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
         uint32_t total = 0, excl = 0;
         bool listed = false;                           // nlx already holds this tile's newline list
         if (use_list) {
-            total = S.tile_total[it & 1u];             // written during the previous tile (or the prologue)
-            listed = total <= (uint32_t)kNlCap;
+            const uint32_t raw = S.tile_total[it & 1u];   // written during the previous tile (or the prologue)
+            total = raw & kNlCountMask;
+            listed = list_ok(raw);
         }
         if (listed) {
             for (uint32_t j = tid; j < total; j += kThreads) S.nlx[kHead + j] = c.origin + (uint32_t)S.nl16[j];
             __syncthreads();
         } else {
+            if (kPack && (kAscii || kQual)) {          // the validation bitmaps reuse `stage`: the previous
+                if (tid == 0) tma_store_wait_read();   // tile's bulk stores and edge stores must be through with it
+                __syncthreads();
+            }
             build_bitmaps<kAscii, kQual>(S, c, addlo, addup);
             __syncthreads();
             words = load_nl_words(S, tid);
@@ -1207,7 +1267,8 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
         }
 
         // ---- validation from the bitmaps: this thread's 128 bytes, line class known from the rank
-        if (kAscii || kQual) {
+        // (a listed tile was screened by k_summarize: no byte of it can fail either validator)
+        if ((kAscii || kQual) && !listed) {
             uint32_t r = rank + excl;
 #pragma unroll
             for (int i = 0; i < kWordsPerThread; ++i) {
@@ -1436,8 +1497,7 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
             if (tid == 0 && t_next < tb) issue_tile_load<true>(S, W, t_next, c.stage);
             t = t_next;
         } else if (use_list) {
-            if (tid == 0 && t + 1u < tb)
-                issue_tile_load<true>(S, W, t + 1u, c.stage, S.nl16, n_next <= (uint32_t)kNlCap ? n_next : 0u);
+            if (tid == 0 && t + 1u < tb) issue_tile_load<true>(S, W, t + 1u, c.stage, S.nl16, listed_count(n_next));
             n_next = n_next2;
             ++t;
         } else {

@@ -271,6 +271,43 @@ def test_single_pass_lookback_kernel(U, B, oracle, mutate, monkeypatch):
         U.check_stream(oracle, b"@long\n" + seq + b"\n+\n" + b"I" * 70000 + b"\n@s\nAC\n+\nII\n", batch_size=3)
 
 
+def test_validation_screen_of_clean_and_dirty_tiles(U, B, oracle):
+    """With validation on, k_summarize screens every interior tile for HI / BAD bytes and k_resolve examines
+    only the flagged ones.  One corrupted byte at a time -- in an id, a sequence, a '+' line (HI there is not
+    an error), a quality line, next to 16 KiB tile edges -- must give exactly the oracle's verdict, and the
+    clean stream none."""
+    data = oracle.synth(9000, 100, 200, 2, 40, "sanger")          # ~3 MB, ids without blanks: every tile is clean
+    views, bases, err = oracle.parse_all(data, oracle.config(True, True, "sanger"))
+    assert len(views) == 9000
+    gpu = B.GpuParser(True, True, B.parse_schema("sanger"), 1000)
+    U.check_stream(oracle, data, check_ascii=True, check_quality=True, schema="sanger", batch_size=1000, gpu=gpu)
+    rng = np.random.default_rng(17)
+    tile = 16384
+    spots = []
+    for k in (3000, 6100):
+        v = views[k]
+        spots += [(int(v["id_start"]) + 2, 0x80), (int(v["seq_start"]) + 5, 0xC3), (int(v["sep_start"]), 0x80 | ord("+")),
+                  (int(v["qual_start"]) + 7, 0xFF), (int(v["qual_start"]) + 1, ord(" ")), (int(v["seq_start"]) + 1, ord(" ")),
+                  (int(v["id_start"]) + 1, 0x7F), (int(v["qual_start"]) + 3, 0x7F)]
+    for edge in (40 * tile, 41 * tile - 1, 41 * tile, 97 * tile + 1):
+        spots += [(edge, 0x80), (edge, 0x1F)]
+    for pos, byte in spots:
+        if data[pos] == 10:
+            continue
+        bad = data.copy()
+        bad[pos] = byte
+        U.check_stream(oracle, bad, check_ascii=True, check_quality=True, schema="sanger", batch_size=1000, gpu=gpu,
+                       want=(3, 1, 2)[int(rng.integers(0, 3))])
+    for val in ((True, False), (False, True)):                     # each validator on its own
+        g2 = B.GpuParser(val[0], val[1], B.parse_schema("sanger"), 1000)
+        for pos, byte in spots[3:6]:
+            bad = data.copy()
+            bad[pos] = byte
+            U.check_stream(oracle, bad, check_ascii=val[0], check_quality=val[1], schema="sanger", batch_size=1000, gpu=g2)
+        g2.close()
+    gpu.close()
+
+
 def test_device_consumer_quality_sums(B, oracle):
     """bsq_quality_sums reads the device-resident SoA of a batches() pass (quality arena + per-batch ends):
     per-record Phred sums equal the host computation on the input bytes, across batch and window edges."""
