@@ -136,7 +136,7 @@ def reference_arm(args):
     O.baseline_mt(data, cfg, 1, 4096, 1)
     one_thread = sample_reads / (time.perf_counter() - t1)
     sample = f"first {sample_reads} reads ({data.size / GIB:.2f} GiB) of the 10 GiB 150 bp stream, batches(4096)"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "fastq_reads_per_s", "value": value, "unit": "reads/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -354,11 +354,22 @@ def main():
             "timing": "wall clock between barrier+synchronize pairs (max over ranks); kernels timed with CUDA events "
                       "on the parser's stream",
         }
-        print(json.dumps(out))
+        emit(json.dumps(out))
     gpu.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
+def emit(line: str) -> None:
+    """The one JSON line goes to the process's real stdout; everything else that lands on fd 1 while the
+    bench runs (NCCL's version banner, library chatter) was redirected to stderr in __main__."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     main()
