@@ -164,6 +164,8 @@ def main():
     ap.add_argument("--mode", default="batches", choices=["batches", "views"])
     ap.add_argument("--validate", action="store_true", help="configs[2]: check_ascii + check_quality, sanger")
     ap.add_argument("--mixed", action="store_true", help="configs[3]: mixed read length 75-300 bp instead of 150 bp")
+    ap.add_argument("--read-len", type=int, default=150, help="read length of the synthetic stream (record stride sweeps)")
+    ap.add_argument("--id-digits", type=int, default=0, help="zero-padded id width (0: that of the stream's read count)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -195,10 +197,13 @@ def main():
 
     # ---- input: this rank's shard of an (N * M)-record stream, generated on the device --------
     schema = B.parse_schema("sanger" if args.validate else "illumina_1.8")
-    mn, mx = (75, 300) if args.mixed else (150, 150)
+    mn, mx = (75, 300) if args.mixed else (args.read_len, args.read_len)
     M = capi.lib().bsq_compute_num_reads_for_size(int(args.gib * GIB), mn, mx)
     total_reads = M * world
-    digits = len(str(total_reads - 1))
+    stream_reads = total_reads              # ids are zero padded to the width of the stream's last index
+    if args.id_digits:
+        stream_reads = max(total_reads, 10 ** (args.id_digits - 1) + 1)
+    digits = len(str(stream_reads - 1))
     gpu = B.GpuParser(args.validate, args.validate, schema, 4096, device_id=local)
     # byte range of this rank's records inside the (world * M)-record stream (utils.mojo:753-768:
     # len_i = mn + (31 i + 7) % (mx - mn + 1), header "@read_<i zero padded to `digits`>\n")
@@ -216,7 +221,7 @@ def main():
     rec_bytes = size / M                       # average bytes per record
     bases_expected = (size - M * (6 + digits + 1 + 4)) // 2
     buf = torch.empty(size + 256, dtype=torch.uint8, device=dev)
-    assert gpu.synth_device(buf.data_ptr(), size, total_reads, rank * M, M, mn, mx, 2, 40, schema) == size
+    assert gpu.synth_device(buf.data_ptr(), size, stream_reads, rank * M, M, mn, mx, 2, 40, schema) == size
     want = capi.WANT_BATCHES if args.mode == "batches" else capi.WANT_OFFSETS
     # algorithmic bytes per record: R read + (2L + I + 16) written, or R + 20 for views
     id_len = 5 + digits
@@ -274,9 +279,8 @@ def main():
         traffic = per_rec * M / n_windows if args.mode == "batches" and not args.validate else None
     except Exception:
         pass
-    single = os.environ.get("BSQ_SINGLE_PASS", "0") not in ("", "0")
-    roofline = {"bound": "hbm", "kernel": "k_resolve", "pass": "single-pass (look-back)" if single else
-                "two-pass (k_summarize + k_scan_runs, then k_resolve)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_resolve", "pass": "two-pass (k_summarize + k_scan_runs, then k_resolve)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_record": algo, "records_per_launch": M / n_windows,
                 "launches_per_step": n_windows, "avg_launch_ms": resolve_ms / n_windows,

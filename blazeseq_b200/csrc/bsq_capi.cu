@@ -80,9 +80,6 @@ struct bsq_parser {
     cudaEvent_t ev_copy[2]{};
     DevBuf run_sum, scan_out, err_word, tail_out, cub_tmp, len_prefix;   // err_word: [0] error key, [1] strip flag
     DevBuf seq_out, qual_out, id_out, ends, id_ends, ends_base, id_ends_base, id_spans;
-    DevBuf tile_status, ticket;      // single-pass launches: look-back status words, tile ticket
-    uint32_t epoch = 0;              // tag of the last single-pass launch
-    bool last_pass_fused = false;
     DevBuf host_input;               // device copy of a host pass
     void* pinned_stage[2] = {nullptr, nullptr};
     size_t pinned_stage_bytes = 0;
@@ -151,10 +148,9 @@ void set_plain_error(bsq_error* e, int code, const char* text) {
     m.str(text);
 }
 
-// k_resolve: kResolveCtas / SM when it packs; without the SoA stage (views, count/validate-only) kViewCtas / SM
-size_t smem_bytes(bool pack = true, bool validate = true) {
-    if (pack) return sizeof(TileSmem) + 128;
-    return offsetof(TileSmem, stage) + (validate ? 2 * kWords * 4 : 0) + 128;
+// k_resolve: the validation bitmaps are the tail of TileSmem and only allocated by validating passes
+size_t smem_bytes(bool validate = true) {
+    return (validate ? sizeof(TileSmem) : offsetof(TileSmem, bm_hi)) + 128;
 }
 size_t smem_bytes_summarize() { return sizeof(SumSmem) + 128; }   // k_summarize: kSummarizeCtas / SM
 
@@ -183,27 +179,19 @@ void plan_window(bsq_parser* p, Window& w, const uint8_t* first_byte, uint64_t b
 
 using ResolveKernel = void (*)(const WinParams, const ResolveParams);
 
-template <bool kFused>
-ResolveKernel pick_resolve_t(bool ascii, bool qual, bool offs, bool pack) {
+ResolveKernel pick_resolve(bool ascii, bool qual, bool offs, bool pack) {
     // ParserConfig(check_ascii, check_quality) x {views, batches}: one instantiation each
     static const ResolveKernel table[16] = {
-        k_resolve<false, false, false, false, kFused>, k_resolve<false, false, false, true, kFused>,
-        k_resolve<false, false, true, false, kFused>,  k_resolve<false, false, true, true, kFused>,
-        k_resolve<false, true, false, false, kFused>,  k_resolve<false, true, false, true, kFused>,
-        k_resolve<false, true, true, false, kFused>,   k_resolve<false, true, true, true, kFused>,
-        k_resolve<true, false, false, false, kFused>,  k_resolve<true, false, false, true, kFused>,
-        k_resolve<true, false, true, false, kFused>,   k_resolve<true, false, true, true, kFused>,
-        k_resolve<true, true, false, false, kFused>,   k_resolve<true, true, false, true, kFused>,
-        k_resolve<true, true, true, false, kFused>,    k_resolve<true, true, true, true, kFused>,
+        k_resolve<false, false, false, false>, k_resolve<false, false, false, true>,
+        k_resolve<false, false, true, false>,  k_resolve<false, false, true, true>,
+        k_resolve<false, true, false, false>,  k_resolve<false, true, false, true>,
+        k_resolve<false, true, true, false>,   k_resolve<false, true, true, true>,
+        k_resolve<true, false, false, false>,  k_resolve<true, false, false, true>,
+        k_resolve<true, false, true, false>,   k_resolve<true, false, true, true>,
+        k_resolve<true, true, false, false>,   k_resolve<true, true, false, true>,
+        k_resolve<true, true, true, false>,    k_resolve<true, true, true, true>,
     };
     return table[(ascii ? 8 : 0) | (qual ? 4 : 0) | (offs ? 2 : 0) | (pack ? 1 : 0)];
-}
-ResolveKernel pick_resolve(bool ascii, bool qual, bool offs, bool pack, bool fused = false) {
-    if (fused) {
-        if constexpr (kStages == 1) return pick_resolve_t<true>(ascii, qual, offs, pack);
-        else return nullptr;   // (a build with a deeper tile ring has no single-pass kernel)
-    }
-    return pick_resolve_t<false>(ascii, qual, offs, pack);
 }
 
 using SummarizeKernel = void (*)(const WinParams, BsqSummary*, uint32_t, uint32_t);
@@ -218,10 +206,7 @@ SummarizeKernel pick_summarize(bool sums, bool hi, bool bad) {
 
 bsq_status setup_kernels(bsq_parser* p) {
     for (int i = 0; i < 8; ++i) CK(opt_in_smem(pick_summarize(i & 4, i & 2, i & 1), smem_bytes_summarize()));
-    for (int i = 0; i < 16; ++i) {
-        CK(opt_in_smem(pick_resolve(i & 8, i & 4, i & 2, i & 1), smem_bytes()));
-        if (kStages == 1) CK(opt_in_smem(pick_resolve(i & 8, i & 4, i & 2, i & 1, true), smem_bytes()));
-    }
+    for (int i = 0; i < 16; ++i) CK(opt_in_smem(pick_resolve(i & 8, i & 4, i & 2, i & 1), smem_bytes()));
     return BSQ_OK;
 }
 
@@ -230,7 +215,7 @@ bsq_status summarize_window(bsq_parser* p, Window& w, bool sums, bool hand_off =
     CK(p->run_sum.ensure(sizeof(BsqSummary) * kMaxRuns));
     CK(w.run_pre.ensure(sizeof(BsqPrefix) * kMaxRuns));
     CK(p->scan_out.ensure(sizeof(ScanOut)));
-    if (hand_off) {   // the per-tile newline lists k_resolve picks up (BSQ_NO_LIST_HANDOFF=1: rebuild them there)
+    if (hand_off) {   // the per-tile newline lists k_resolve picks up
         const size_t tiles = w.wp.n_tiles - w.wp.first_tile;
         CK(w.nl_count.ensure(4 * tiles, 1 << 16));
         CK(w.nl_list.ensure(2ull * kNlCap * tiles, 1 << 20));
@@ -344,7 +329,7 @@ extern "C" void bsq_destroy(bsq_parser* p) {
     for (auto& w : p->win) { w.line_ends.release(); w.run_pre.release(); w.nl_count.release(); w.nl_list.release(); }
     DevBuf* bufs[] = {&p->run_sum, &p->scan_out, &p->err_word, &p->tail_out, &p->cub_tmp, &p->len_prefix,
                       &p->seq_out, &p->qual_out, &p->id_out, &p->ends, &p->id_ends, &p->ends_base,
-                      &p->id_ends_base, &p->id_spans, &p->host_input, &p->tile_status, &p->ticket};
+                      &p->id_ends_base, &p->id_spans, &p->host_input};
     for (auto* b : bufs) b->release();
     for (auto& s : p->pinned_stage) if (s) cudaFreeHost(s);
     if (p->hm) cudaFreeHost(p->hm);
@@ -377,15 +362,12 @@ struct InputFeed {
     virtual ~InputFeed() {}
 };
 
-// Two passes (default) or a single pass.  The single pass (k_resolve<..., kFused = true>) reads the
-// input once but has to size its outputs before it knows the totals: it uses estimates, and a region
-// that does not fit (or a build without the single-pass kernel) takes the exact two-pass path.
+// Two passes: k_summarize + k_scan_runs over every window (the host learns where the next window starts and
+// the exact output sizes), then k_resolve.
 bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_offset, int64_t first_record,
-                    int32_t is_last, uint32_t want, uint64_t window_bytes, InputFeed& feed, bsq_pass_result* out,
-                    bool allow_fused = true) {
+                    int32_t is_last, uint32_t want, uint64_t window_bytes, InputFeed& feed, bsq_pass_result* out) {
     const bsq_config& cfg = p->cfg;
     const bool want_offs = (want & BSQ_WANT_OFFSETS) != 0, want_pack = (want & BSQ_WANT_BATCHES) != 0;
-    const uint64_t window_bytes_arg = window_bytes;
     p->have_pass = false;
     p->want = want;
     p->pass_input = d;
@@ -394,19 +376,9 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     memset(&p->res, 0, sizeof p->res);
     bsq_pass_result& R = p->res;
     const int32_t m = cfg.batch_size;
-    ResolveKernel fused_kern = nullptr;
-    if (allow_fused && n > 0) {
-        // opt-in (BSQ_SINGLE_PASS=1): bit-exact, but its one-level look-back advances only 32 tiles per
-        // round trip through L2 and is slower than the two passes on a B200
-        const char* one = getenv("BSQ_SINGLE_PASS");
-        if (one && atoi(one) != 0) fused_kern = pick_resolve(cfg.check_ascii, cfg.check_quality, want_offs, want_pack, true);
-    }
-    const bool fused = fused_kern != nullptr;
-    p->last_pass_fused = fused;
-    const size_t smem_res = smem_bytes(want_pack, cfg.check_ascii || cfg.check_quality);
+    const size_t smem_res = smem_bytes(cfg.check_ascii || cfg.check_quality);
     // k_summarize hands every tile's ordered newline list (and, when validating, its HI / BAD screen) to k_resolve
-    bool list_hand_off = kStages == 1;
-    if (const char* e = getenv("BSQ_NO_LIST_HANDOFF")) list_hand_off = list_hand_off && atoi(e) == 0;
+    const bool list_hand_off = true;
     CK(cudaEventRecord(p->ev[0], p->stream));
 
     bool id_fast = cfg.force_id_slow_path == 0;   // optimistic: k_resolve raises the strip flag when an id needs stripping
@@ -437,7 +409,6 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         P.n_complete = w.scan.totals.records;
         P.id_fast = id_fast ? 1u : 0u;
         P.strip_flag = reinterpret_cast<uint32_t*>(p->err_word.as<uint8_t>() + 8);
-        { const char* dbg = getenv("BSQ_DEBUG_SKIP"); P.debug_skip = dbg ? (uint32_t)atoi(dbg) : 0u; }
         P.bases = p->err_word.as<unsigned long long>() + 2;
         P.rec_mod = (uint32_t)(w.rec_base % m);
         P.rec_div = w.rec_base / m;
@@ -453,90 +424,11 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         P.batch_size = m;
         P.lower = cfg.q_lower; P.upper = cfg.q_upper;
         P.err = p->err_word.as<unsigned long long>();
-        // single pass
-        P.tile_status = p->tile_status.as<uint32_t>();
-        P.ticket = p->ticket.as<uint32_t>();
-        P.epoch = p->epoch;
-        P.line_cap = (uint32_t)std::min<size_t>(w.line_ends.cap / 4, 0xFFFFFFFFu);
-        P.scan_out = p->scan_out.as<ScanOut>();
-        P.overflow = reinterpret_cast<uint32_t*>(p->err_word.as<uint8_t>() + 24);
-        P.seq_cap = (int64_t)p->seq_out.cap; P.qual_cap = (int64_t)p->qual_out.cap;
-        P.rec_cap = INT64_MAX;
-        if (want_offs || want_pack) P.rec_cap = std::min<int64_t>(P.rec_cap, (int64_t)(p->id_spans.cap / 8));
-        if (want_pack) P.rec_cap = std::min<int64_t>(P.rec_cap, (int64_t)(std::min(p->ends.cap, p->id_ends.cap) / 8));
         return P;
     };
-    // one single-pass launch over window w (bases already in w)
-    auto launch_fused = [&](Window& w) -> bsq_status {
-        const uint32_t tiles = w.wp.n_tiles - w.wp.first_tile;
-        // sized for the largest window so that it is cleared once
-        const size_t need = ((size_t)(kWindowMax / kTile) + 2) * kStatusWords * 4;
-        if (need > p->tile_status.cap) {
-            CK(p->tile_status.ensure(need, 1 << 20));
-            CK(cudaMemsetAsync(p->tile_status.p, 0, p->tile_status.cap, p->stream));
-            p->epoch = 0;
-        }
-        CK(p->ticket.ensure(16));
-        CK(cudaMemsetAsync(p->ticket.p, 0, 16, p->stream));
-        p->epoch += 1;
-        if (p->epoch >= (1u << 30)) {   // tags are 30 bits: start over on clean status words
-            CK(cudaMemsetAsync(p->tile_status.p, 0, p->tile_status.cap, p->stream));
-            p->epoch = 1;
-        }
-        if (want_offs) CK(w.line_ends.ensure(4ull * ((size_t)(w.wp.end - w.wp.begin) / 12 + 1024), 1 << 16));
-        ResolveParams P = make_params(w);
-        const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)((want_pack ? kResolveCtas : kViewCtas) * p->sm_count));
-        fused_kern<<<grid, kThreads, smem_res, p->stream>>>(w.wp, P);
-        p->n_launches += 1;
-        CK(cudaGetLastError());
-        return BSQ_OK;
-    };
-
     size_t nw = 0;
     uint64_t pos = 0;
     bool oversize = false;
-    if (fused) {
-        // ---- the single pass: outputs sized from estimates, one launch + one small D2H per window ----
-        CK(cudaEventRecord(p->ev[1], p->stream));   // (no separate summarise phase)
-        CK(p->scan_out.ensure(sizeof(ScanOut)));
-        const int64_t rec_est = (int64_t)(n / 64) + 4096;
-        bsq_status st0 = prepare_outputs(rec_est, (int64_t)(n / 32 * 17) + (1 << 20), (int64_t)(n / 32 * 17) + (1 << 20),
-                                         (int64_t)(n / 5 * 2) + (1 << 20));
-        if (st0 != BSQ_OK) return st0;
-        int64_t nrec0 = 0, nseq0 = 0, nqual0 = 0, nid0 = 0;
-        bool overflow = false;
-        while (pos < n) {
-            if (nw >= (size_t)kMaxWindows) { p->last_error = "region needs more than kMaxWindows windows"; return BSQ_E_ARG; }
-            if (p->win.size() <= nw) p->win.emplace_back();
-            Window& w = p->win[nw];
-            const uint64_t bytes = std::min<uint64_t>(n - pos, window_bytes);
-            bsq_status st = feed.ready_upto(pos + bytes);
-            if (st != BSQ_OK) return st;
-            plan_window(p, w, d + pos, bytes, want_pack);
-            w.region_off = pos;
-            w.rec_base = nrec0; w.seq_base = nseq0; w.qual_base = nqual0; w.id_base = nid0;
-            st = launch_fused(w);
-            if (st != BSQ_OK) return st;
-            CK(cudaMemcpyAsync(&p->hm->scan, p->scan_out.p, sizeof(ScanOut), cudaMemcpyDeviceToHost, p->stream));
-            CK(cudaMemcpyAsync(p->hm->err, p->err_word.p, 32, cudaMemcpyDeviceToHost, p->stream));
-            CK(cudaStreamSynchronize(p->stream));
-            w.scan = p->hm->scan;
-            if ((uint32_t)p->hm->err[3] != 0u) { overflow = true; break; }
-            ++nw;
-            const uint64_t consumed = w.scan.totals.consumed_end - w.wp.begin;
-            const bool reaches_end = pos + bytes == n;
-            if (reaches_end) break;
-            if (consumed == 0) {
-                if (window_bytes < kWindowMax) { window_bytes = std::min<uint64_t>(window_bytes * 4, kWindowMax); --nw; continue; }
-                oversize = true;  // a single record larger than a window
-                break;
-            }
-            nrec0 += w.scan.totals.records; nseq0 += w.scan.totals.seq_bytes; nqual0 += w.scan.totals.qual_bytes;
-            nid0 += w.scan.totals.id_bytes_unstripped;
-            pos += consumed;
-        }
-        if (overflow) return run_pass(p, d, n, stream_offset, first_record, is_last, want, window_bytes_arg, feed, out, false);
-    } else {
     // ---- pass 1: summarise every window (host learns where the next window starts) ----------
     while (pos < n) {
         if (nw >= (size_t)kMaxWindows) { p->last_error = "region needs more than kMaxWindows windows"; return BSQ_E_ARG; }
@@ -561,7 +453,6 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         pos += consumed;
     }
     CK(cudaEventRecord(p->ev[1], p->stream));
-    }
 
     // ---- totals, tail classification ----------------------------------------------------------
     int64_t nrec = 0, nseq = 0, nqual = 0, nid = 0, nnl = 0;
@@ -611,32 +502,6 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     // ---- outputs -------------------------------------------------------------------------------
     const int64_t arena_rec = nrec + (have_tail_candidate ? 1 : 0);
     ResolveKernel kern = pick_resolve(cfg.check_ascii, cfg.check_quality, want_offs, want_pack);
-    if (fused) {
-        // what the estimates must have covered (the kernel checked the windows; this adds the tail record)
-        bool fits = (!(want_offs || want_pack) || 8ull * (arena_rec + 1) <= p->id_spans.cap);
-        if (want_pack)
-            fits = fits && (size_t)nseq + tail_seq + 64 <= p->seq_out.cap && (size_t)nqual + tail_qual + 64 <= p->qual_out.cap &&
-                   (size_t)id_room + tail_id_max <= p->id_out.cap && 8ull * (arena_rec + 1) <= p->ends.cap &&
-                   8ull * (arena_rec + 1) <= p->id_ends.cap && 8ull * (arena_rec / m + 2) <= p->ends_base.cap &&
-                   8ull * (arena_rec / m + 2) <= p->id_ends_base.cap;
-        if (!fits) return run_pass(p, d, n, stream_offset, first_record, is_last, want, window_bytes_arg, feed, out, false);
-        CK(cudaEventRecord(p->ev[2], p->stream));
-        if (want_pack && id_fast && p->hm->err[1] != 0) {
-            // an id needed _strip_spaces (CRLF input, padded ids): repeat with the id spans materialised
-            id_fast = false;
-            CK(cudaMemsetAsync(p->err_word.p, 0xFF, 8, p->stream));
-            CK(cudaMemsetAsync(p->err_word.as<uint8_t>() + 16, 0, 16, p->stream));
-            for (size_t i = 0; i < nw; ++i) {
-                bsq_status st = launch_fused(p->win[i]);
-                if (st != BSQ_OK) return st;
-            }
-            CK(cudaMemcpyAsync(p->hm->err, p->err_word.p, 32, cudaMemcpyDeviceToHost, p->stream));
-            CK(cudaStreamSynchronize(p->stream));
-        }
-        // a report against the trailing incomplete record is not an error of this pass
-        if (p->hm->err[0] != ~0ull && (int64_t)(p->hm->err[0] >> 8) - first_record >= nrec)
-            CK(cudaMemsetAsync(p->err_word.p, 0xFF, 8, p->stream));
-    } else {
     bsq_status stp = prepare_outputs(arena_rec, nseq + tail_seq, nqual + tail_qual, id_room + tail_id_max);
     if (stp != BSQ_OK) return stp;
 
@@ -666,7 +531,6 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
             }
             CK(cudaGetLastError());
         }
-    }
     }
 
     if (have_tail_candidate) {
@@ -762,18 +626,12 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
             if (!want_offs) {  // cold path: materialise this window's line-end table
                 CK(w.line_ends.ensure(4ull * ((size_t)w.scan.totals.newlines + 2), 1 << 16));
                 CK(p->id_spans.ensure(8ull * (arena_rec + 1), 1 << 20));
-                if (fused) {   // the two-pass kernel needs the run prefixes of this window
-                    const ScanOut keep = w.scan;
-                    bsq_status st = summarize_window(p, w, false);
-                    if (st != BSQ_OK) return st;
-                    w.scan = keep;
-                }
                 ResolveParams P = make_params(w);
                 DevBuf scratch;
                 CK(scratch.ensure(8));
                 CK(cudaMemset(scratch.p, 0xFF, 8));
                 P.err = scratch.as<unsigned long long>();
-                k_resolve<false, false, true, false, false><<<w.wp.n_runs, kThreads, smem_bytes(false, false), p->stream>>>(w.wp, P);
+                k_resolve<false, false, true, false><<<w.wp.n_runs, kThreads, smem_bytes(false), p->stream>>>(w.wp, P);
                 p->n_launches += 1;
                 CK(cudaStreamSynchronize(p->stream));
                 scratch.release();

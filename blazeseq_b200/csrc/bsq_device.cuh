@@ -15,8 +15,7 @@
 //                 (record_batch.mojo:77-87): the lines are staged in shared memory in destination
 //                 layout and written back with TMA bulk stores.
 //
-// In the two-pass path no CTA ever waits on another CTA: the only cross-CTA dependency is the
-// kernel boundary.  k_resolve<..., kFused> is the single-pass alternative (decoupled look-back).
+// No CTA ever waits on another CTA: the only cross-CTA dependency is the kernel boundary.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -38,7 +37,7 @@ constexpr int kWarps = kThreads / 32;
 #define BSQ_STAGES 1
 #endif
 #ifndef BSQ_RESOLVE_CTAS
-#define BSQ_RESOLVE_CTAS 5
+#define BSQ_RESOLVE_CTAS 6
 #endif
 constexpr int kStages = BSQ_STAGES;       // TMA ring depth per CTA
 constexpr int kResolveCtas = BSQ_RESOLVE_CTAS;  // resident CTAs per SM, k_resolve (shared memory + registers)
@@ -69,7 +68,6 @@ constexpr int kLinesCap = kNlCap / 4 + 3; // lines of one class per pass (+ two 
 constexpr int kTilePad = 32;              // readable slack after a tile for unaligned 16-byte loads
 constexpr int kHalo = 1024;               // bytes before the tile kept in shared memory too: a line that began
                                           // up to kHalo bytes before the tile is still read from shared memory
-constexpr int kStage = kHalo + kTile + 128;  // SoA staging: the lines that END in a tile lie in [halo | tile]; + 3 x 32 alignment slack
 constexpr int kMaxWindows = 64;
 
 static_assert(kThreads % 4 == 0 && (kWordsPerThread == 4 || kWordsPerThread == 2) && kChunksPerThread * kThreads == kChunks, "");
@@ -101,7 +99,6 @@ struct ResolveParams {
     uint32_t id_fast;            // 1: ids are packed here on the assumption that none needs stripping;
                                  //    *strip_flag is raised if one does and the host redoes the ids
     uint32_t* strip_flag;
-    uint32_t debug_skip;         // measurement only (BSQ_DEBUG_SKIP env): 1 = no SoA copy, 2 = no line tables
     unsigned long long* bases;   // sum of the sequence lengths of the complete records (all windows)
     uint32_t rec_mod;            // rec_base % batch_size
     int64_t rec_div;             // rec_base / batch_size
@@ -119,15 +116,6 @@ struct ResolveParams {
     int32_t batch_size;
     uint32_t lower, upper;       // quality bounds
     unsigned long long* err;     // min over ((global record << 8) | code)
-    // ---- single-pass (fused) launches only ----
-    uint32_t* tile_status;       // kStatusWords words per tile of the window (decoupled look-back)
-    uint32_t* ticket;            // next tile to claim, window-relative; zeroed before the launch
-    uint32_t epoch;              // tags the status words of this launch (never 0, never reused)
-    uint32_t line_cap;           // entries of line_ends
-    ScanOut* scan_out;           // written by the CTA that owns the window's last tile
-    uint32_t* overflow;          // raised when an output would not fit its (estimated) capacity
-    int64_t seq_cap, qual_cap;   // bytes allocated for seq_out / qual_out
-    int64_t rec_cap;             // entries of ends_abs / id_ends_abs / id_spans pairs
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -203,25 +191,18 @@ struct alignas(128) TileSmem {
     uint32_t k1_red[kWarps * 4];
     alignas(16) uint32_t bm_nl[kWords];       // 1 bit per byte: '\n'
     // ---- k_resolve only ----
-    // (the HI / BAD validation bitmaps live at the start of `stage`: they are consumed before the SoA
-    //  bytes of the tile are staged)
     uint32_t nlx[kHead + kNlCap];             // nlx[kHead + j] = position of local newline j;
                                               // nlx[kHead-1-i] = i-th newline before the list
     uint32_t sdst[3][kLinesCap];              // per class stream: destination of each line
     uint32_t ssrc[3][kLinesCap];              //                   source position of each line
-    alignas(16) uint16_t nl16[kNlCap];        // the tile's newline list from k_summarize (TMA destination)
-    uint32_t tile_total[2];                   // newline count of the current / next tile (double buffered)
-    // ---- single-pass (fused) launches ----
-    BsqPrefix pre;                            // this tile's prefix, from the look-back
-    uint32_t next_tile;                       // the tile this CTA claimed for its next iteration
-    uint32_t first_claim;                     // the tile it claimed at start
-    uint32_t agg_p[4];                        // aggregate of a tile with more than kNlCap newlines
-    alignas(128) uint8_t stage[kStage];       // SoA bytes of the pass, laid out like the destination (mod 16):
-                                              // [id | seq | qual], written back with TMA bulk stores
-    __device__ __forceinline__ uint32_t* bm_hi() { return reinterpret_cast<uint32_t*>(stage); }            // 1 bit per byte: bit 7 set
-    __device__ __forceinline__ uint32_t* bm_bad() { return reinterpret_cast<uint32_t*>(stage) + kWords; }  // outside [lower, upper]
+    alignas(16) uint16_t nl16[kStages][kNlCap];   // the tile's newline list from k_summarize (TMA destination)
+    uint32_t tile_total[kStages + 1];         // newline count words of the tiles in flight (ring, written one tile ahead)
+    // ---- validating instantiations only (the allocation ends here otherwise) ----
+    alignas(16) uint32_t bm_hi[kWords];       // 1 bit per byte: bit 7 set
+    uint32_t bm_bad[kWords];                  // 1 bit per byte: outside [lower, upper]
+    __device__ __forceinline__ uint32_t* bm_hi_p() { return bm_hi; }
+    __device__ __forceinline__ uint32_t* bm_bad_p() { return bm_bad; }
 };
-static_assert(2 * kWords * 4 <= kStage, "the validation bitmaps fit the stage buffer");
 
 // k_summarize: the same front end on its own (double-buffered) ring
 constexpr int kSumStages = 2;
@@ -238,8 +219,8 @@ struct alignas(128) SumSmem {
     // tile-relative newline positions, in order (handed to k_resolve): they live in the halo bytes of ring
     // slot 0, which k_summarize never loads
     __device__ __forceinline__ uint16_t* list() { return reinterpret_cast<uint16_t*>(data[0]); }
-    __device__ __forceinline__ uint32_t* bm_hi() { return nullptr; }    // (never used: build_bitmaps<false, false>)
-    __device__ __forceinline__ uint32_t* bm_bad() { return nullptr; }
+    __device__ __forceinline__ uint32_t* bm_hi_p() { return nullptr; }    // (never used: build_bitmaps<false, false>)
+    __device__ __forceinline__ uint32_t* bm_bad_p() { return nullptr; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -320,8 +301,8 @@ __device__ __forceinline__ void build_bitmaps(SM& S, const TileCursor& c, uint32
         if ((tid & 1u) == 0u) {
             const uint32_t w = chunk >> 1;
             S.bm_nl[w] = (x & 0xFFFFu) | (xo << 16);
-            if (kHi) S.bm_hi()[w] = (x >> 16) | (xo & 0xFFFF0000u);
-            if (kBad) S.bm_bad()[w] = m_bad | (bo << 16);
+            if (kHi) S.bm_hi_p()[w] = (x >> 16) | (xo & 0xFFFF0000u);
+            if (kBad) S.bm_bad_p()[w] = m_bad | (bo << 16);
         }
     }
 }
@@ -745,120 +726,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) k_scan_runs(const BsqSummary*
 }
 
 // ------------------------------------------------------------------------------------------------
-// single pass: per-tile status words + decoupled look-back over the rank algebra
-// ------------------------------------------------------------------------------------------------
-//
-// A fused launch reads every tile ONCE: the CTA that claims a tile (in order, through a ticket)
-// publishes the tile's aggregate -- the part of a BsqSummary that bsq_prefix_from / bsq_totals_from
-// read: newline count, last four newline positions, position sums by index mod 4 -- then combines
-// the aggregates of its predecessors back to the nearest tile whose INCLUSIVE state is already
-// published (32 predecessors per round, one per lane), publishes its own inclusive state and
-// resolves the tile in place.  A tile waits only for tiles with smaller tickets, all of which are
-// owned by running CTAs, so the scheme cannot deadlock whatever the residency.
-
-constexpr int kStatusWords = 32;   // 128 bytes per tile: [flag, -, -, -][aggregate: 12 words][inclusive: 12 words][pad]
-constexpr uint32_t kLbAgg = 1u, kLbInc = 2u;
-
-__device__ __forceinline__ LbState lb_shfl_down(const LbState& v, uint32_t d) {
-    LbState o;
-    o.count = __shfl_down_sync(0xFFFFFFFFu, v.count, d);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        o.last[i] = __shfl_down_sync(0xFFFFFFFFu, v.last[i], d);
-        o.P[i] = __shfl_down_sync(0xFFFFFFFFu, v.P[i], d);
-    }
-    return o;
-}
-__device__ __forceinline__ LbState lb_bcast0(const LbState& v) {
-    LbState o;
-    o.count = __shfl_sync(0xFFFFFFFFu, v.count, 0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        o.last[i] = __shfl_sync(0xFFFFFFFFu, v.last[i], 0);
-        o.P[i] = __shfl_sync(0xFFFFFFFFu, v.P[i], 0);
-    }
-    return o;
-}
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint4 ld_relaxed_v4(const uint32_t* p) {
-    uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_v4(uint32_t* p, uint4 v) {
-    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                 : "memory");
-}
-
-// one thread: payload, fence, flag
-__device__ __forceinline__ void lb_publish(uint32_t* status, uint32_t slot, const LbState& v, uint32_t epoch) {
-    uint32_t* pay = status + 4u + (slot == kLbInc ? 12u : 0u);
-    st_relaxed_v4(pay, make_uint4(v.count, v.last[0], v.last[1], v.last[2]));
-    st_relaxed_v4(pay + 4, make_uint4(v.last[3], v.P[0], v.P[1], v.P[2]));
-    st_relaxed_v4(pay + 8, make_uint4(v.P[3], 0u, 0u, 0u));
-    __threadfence();
-    st_release_u32(status, (epoch << 2) | slot);
-}
-__device__ __forceinline__ LbState lb_load(const uint32_t* status, uint32_t slot) {
-    const uint32_t* pay = status + 4u + (slot == kLbInc ? 12u : 0u);
-    const uint4 a = ld_relaxed_v4(pay), b = ld_relaxed_v4(pay + 4), c = ld_relaxed_v4(pay + 8);
-    LbState v;
-    v.count = a.x; v.last[0] = a.y; v.last[1] = a.z; v.last[2] = a.w;
-    v.last[3] = b.x; v.P[0] = b.y; v.P[1] = b.z; v.P[2] = b.w; v.P[3] = c.x;
-    return v;
-}
-
-// Warp-wide: the state before window tile `ti` (0-based within the window) = window init (+) tiles
-// [0, ti).  Lane l looks at tile ti-1-l; tiles before the window are the (inclusive) init state.
-__device__ __forceinline__ LbState lb_look_back(const uint32_t* tile_status, uint32_t ti, uint32_t begin, uint32_t epoch) {
-    const uint32_t lane = threadIdx.x & 31u;
-    LbState E = lb_identity();
-    bool have = false;                              // E holds at least one tile (it is the later operand)
-    int32_t base = (int32_t)ti - 1;
-    while (true) {
-        const int32_t t = base - (int32_t)lane;
-        uint32_t slot = kLbInc;
-        LbState v = lb_identity();
-        if (t < 0) {
-            if (t == -1) v.last[0] = begin - 1u;    // bsq_summary_window_init
-        } else {
-            const uint32_t* st = tile_status + (size_t)t * kStatusWords;
-            uint32_t f, spins = 0;
-            while (((f = ld_acquire_u32(st)) >> 2) != epoch) {
-                if (++spins > (1u << 22)) __trap();  // a predecessor that never publishes must fault, not hang
-                __nanosleep(32);
-            }
-            slot = f & 3u;
-            v = lb_load(st, slot);
-        }
-        const uint32_t inc = __ballot_sync(0xFFFFFFFFu, slot == kLbInc);
-        // lanes 0..nearest take part.  (The window-init state is not a unit of lb_combine on the
-        // right -- its virtual newline would be lost -- so the lanes beyond are left out, not zeroed.)
-        const uint32_t nearest = inc ? (uint32_t)__ffs((int)inc) - 1u : 31u;
-        // ordered reduction: a higher lane is an EARLIER tile
-#pragma unroll
-        for (uint32_t d = 1; d < 32u; d <<= 1) {
-            const LbState o = lb_shfl_down(v, d);
-            if (lane + d <= nearest) v = lb_combine(o, v);
-        }
-        const LbState R = lb_bcast0(v);
-        E = have ? lb_combine(R, E) : R;
-        have = true;
-        if (inc) break;
-        base -= 32;
-    }
-    return E;
-}
-
-// ------------------------------------------------------------------------------------------------
 // k_resolve
 // ------------------------------------------------------------------------------------------------
 
@@ -992,132 +859,133 @@ __device__ __noinline__ void copy_stream(const TileSmem& S, const TileCursor& c,
     }
 }
 
-// Line-parallel copy (the common case: no line of the pass is long).  One thread owns one line and
-// streams it: every destination vector whose first byte lies in the line is assembled with one
-// unaligned 16-byte shared read and written with one 16-byte store; the vector in which the line
-// ends also takes the first bytes of the following line(s).  Far fewer instructions per byte than
-// the vector-parallel form (no per-vector line lookup), at the price of 16-byte stores that are
-// not coalesced across the warp (adjacent stores of a thread complete each 32-byte sector in L2).
-__device__ __forceinline__ void copy_line(const TileSmem& S, const TileCursor& c, const WinParams& W,
-                                          const StreamJob& J, uint32_t i) {
-    const uint32_t s0 = J.sdst[i], s1 = J.sdst[i + 1];
-    if (s1 == s0) return;                                            // empty line owns nothing
-    const uint32_t v0 = J.d0 >> 4;
-    uint32_t v = s0 == J.d0 ? v0 : (s0 + 15u) >> 4;                  // the line holding d0 owns vector v0
-    const uint32_t vend = (s1 + 15u) >> 4;
-    const uint32_t delta = J.ssrc[i] - s0;                           // source of destination byte d is d + delta
-    for (; v < vend; ++v) {
-        const uint32_t vs = v * 16u;
-        const uint32_t lo = vs < J.d0 ? J.d0 : vs;
-        const uint32_t hi = vs + 16u > J.d1 ? J.d1 : vs + 16u;
-        uint4 acc = load16(S, c, W, vs + delta);
-        if (s1 < hi) {                                               // the line ends inside this vector
-            uint32_t k = i, e = s1;
-            while (e < hi) {
-                ++k;
-                const uint32_t a = e - vs;
-                if (J.sdst[k + 1] != e) acc = splice16(acc, load16(S, c, W, J.ssrc[k] - a), a);
-                e = J.sdst[k + 1];
-            }
-        }
-        uint8_t* p = J.out + (size_t)v * 16u;
-        if (hi - lo == 16u) *reinterpret_cast<uint4*>(p) = acc;
-        else store_partial16(p, acc, lo - vs, hi - vs);
+// ------------------------------------------------------------------------------------------------
+// direct SoA copy: the lines that end in a tile go from [halo | tile] in shared memory straight to their
+// place in the global arenas (no staging buffer).
+//
+// The copy is organised by DESTINATION, not by line: consecutive lanes write consecutive 16-byte
+// vectors of a stream (one coalesced 512-byte store per warp), and their sources are consecutive
+// 16-byte windows of one line in shared memory, read as the two aligned 16-byte vectors that hold
+// them -- so neither side has a bank-conflict pattern that depends on the record stride (a per-line
+// word loop puts lane i at i x stride: 16-way conflicts when the stride is 320 bytes).
+//   interior   every destination vector that lies inside ONE line: one thread per vector
+//   edges      a vector in which a line ends (it also takes the first bytes of the following
+//              line(s)) and the partial first / last vector of the tile's range: one thread per line
+//   ids        short lines, one thread per line, word stores
+// ------------------------------------------------------------------------------------------------
+
+// 16 bytes at byte offset `src` of `data` (any alignment; `data` is 16-byte aligned and has 32 readable
+// bytes past the last one asked for)
+__device__ __forceinline__ uint4 load16_smem(const uint8_t* __restrict__ data, uint32_t src) {
+    const uint4* q = reinterpret_cast<const uint4*>(data + (src & ~15u));
+    const uint4 a = q[0], b = q[1];
+    uint32_t v0 = a.x, v1 = a.y, v2 = a.z, v3 = a.w, v4 = b.x, v5 = b.y;
+    if (src & 8u) { v0 = v2; v1 = v3; v2 = v4; v3 = v5; v4 = b.z; v5 = b.w; }
+    if (src & 4u) { v0 = v1; v1 = v2; v2 = v3; v3 = v4; v4 = v5; }
+    const uint32_t sh = (src & 3u) * 8u;
+    return make_uint4(__funnelshift_r(v0, v1, sh), __funnelshift_r(v1, v2, sh), __funnelshift_r(v2, v3, sh),
+                      __funnelshift_r(v3, v4, sh));
+}
+
+struct DirectJob {
+    const uint32_t* sdst; const uint32_t* ssrc;   // per line: destination (virtual offset) and window position
+    uint32_t n_lines, ra, rb;                      // sdst[0] == ra, sdst[n_lines] == rb
+    uint8_t* out;                                  // 16-byte aligned; destination byte d is out[d]
+};
+
+// interior vectors of one stream (block-wide)
+__device__ __forceinline__ void copy_interior(const uint8_t* __restrict__ data, uint32_t sbias, const DirectJob& J) {
+    const uint32_t v_lo = (J.ra + 15u) >> 4, v_hi = J.rb >> 4;
+    if (v_hi <= v_lo) return;
+    const float inv = (float)J.n_lines / (float)(J.rb - J.ra);   // lines per destination byte: first guess of the line
+    for (uint32_t v = v_lo + threadIdx.x; v < v_hi; v += kThreads) {
+        const uint32_t p = v * 16u;
+        uint32_t i = (uint32_t)((float)(p - J.ra) * inv);
+        if (i >= J.n_lines) i = J.n_lines - 1u;
+        while (J.sdst[i] > p) --i;                 // sdst[0] == ra <= p
+        uint32_t e = J.sdst[i + 1];
+        while (e <= p) { ++i; e = J.sdst[i + 1]; } // sdst[n_lines] == rb > p; skips empty lines
+        if (e >= p + 16u)                          // (a vector with a line end inside belongs to copy_edges)
+            *reinterpret_cast<uint4*>(J.out + p) = load16_smem(data, p + (J.ssrc[i] - J.sdst[i]) + sbias);
     }
 }
 
-// Staged copy (the common case: every line of the pass lies in [halo | tile]).  One thread moves one
-// line from the tile to `stage`, which is laid out like the destination modulo 16: a byte loop up to
-// the first 4-byte boundary of the destination, then one funnel shift per word (each source word is
-// read once), then the last 0-3 bytes.  The staged range leaves through TMA bulk stores, so the
-// global writes cost no instructions and are full 16-byte vectors.
-__device__ __forceinline__ void stage_line(const uint8_t* __restrict__ data, uint8_t* __restrict__ stage,
-                                           uint32_t src, uint32_t dst, uint32_t len) {
+// destination vector V of a stream, assembled from line i (which holds the vector's first byte that lies in
+// [ra, rb)) and as many following lines as begin inside it
+__device__ __forceinline__ void copy_edge_vector(const uint8_t* __restrict__ data, uint32_t sbias, const DirectJob& J,
+                                                 uint32_t i, uint32_t V) {
+    const uint32_t vs = V * 16u;
+    const uint32_t lo = vs < J.ra ? J.ra : vs, hi = vs + 16u > J.rb ? J.rb : vs + 16u;
+    uint4 acc = load16_smem(data, vs + (J.ssrc[i] - J.sdst[i]) + sbias);
+    uint32_t k = i, e = J.sdst[i + 1];
+    while (e < hi) {
+        ++k;
+        const uint32_t a = e - vs, nx = J.sdst[k + 1];
+        if (nx != e) acc = splice16(acc, load16_smem(data, J.ssrc[k] + sbias - a), a);
+        e = nx;
+    }
+    uint8_t* p = J.out + vs;
+    if (hi - lo == 16u) *reinterpret_cast<uint4*>(p) = acc;
+    else store_partial16(p, acc, lo - vs, hi - vs);
+}
+
+// the edge vectors line i owns (one thread per line)
+__device__ __forceinline__ void copy_edges(const uint8_t* __restrict__ data, uint32_t sbias, const DirectJob& J, uint32_t i) {
+    const uint32_t s0 = J.sdst[i], s1 = J.sdst[i + 1];
+    if (s1 == s0) return;                                            // an empty line owns nothing
+    if (s1 & 15u) {                                                  // the line ends inside a vector: its owner is the
+        const uint32_t V = s1 >> 4;                                  // line that holds the vector's first byte in range
+        const uint32_t first = V * 16u < J.ra ? J.ra : V * 16u;
+        if (s0 <= first) copy_edge_vector(data, sbias, J, i, V);
+    }
+    // the partial first vector of the range, when this line fills it to its end
+    if (s0 == J.ra && (J.ra & 15u) && (s1 >> 4) != (J.ra >> 4)) copy_edge_vector(data, sbias, J, i, J.ra >> 4);
+}
+
+// a short line (ids): head bytes to the first 4-byte boundary of the destination, one funnel shift per
+// word, the last 0-3 bytes
+__device__ __forceinline__ void copy_small_line(const uint8_t* __restrict__ data, uint32_t src, uint8_t* __restrict__ out,
+                                                uint32_t dst, uint32_t len) {
     if (len == 0u) return;   // (the source of an empty line may lie outside [halo | tile])
     uint32_t h = (0u - dst) & 3u;
     if (h > len) h = len;
-    for (uint32_t i = 0; i < h; ++i) stage[dst + i] = data[src + i];
+    for (uint32_t i = 0; i < h; ++i) out[dst + i] = data[src + i];
     src += h; dst += h; len -= h;
     const uint32_t nw = len >> 2;
     const uint32_t sh = (src & 3u) * 8u;
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(data + (src & ~3u));
-    uint32_t* dw = reinterpret_cast<uint32_t*>(stage + dst);
+    uint32_t* dw = reinterpret_cast<uint32_t*>(out + dst);
     uint32_t w0 = sw[0];
-    uint32_t i = 0;
-    for (; i + 4u <= nw; i += 4u) {
-        const uint32_t w1 = sw[i + 1], w2 = sw[i + 2], w3 = sw[i + 3], w4 = sw[i + 4];
-        dw[i] = __funnelshift_r(w0, w1, sh);
-        dw[i + 1] = __funnelshift_r(w1, w2, sh);
-        dw[i + 2] = __funnelshift_r(w2, w3, sh);
-        dw[i + 3] = __funnelshift_r(w3, w4, sh);
-        w0 = w4;
-    }
-    for (; i < nw; ++i) {
+    for (uint32_t i = 0; i < nw; ++i) {
         const uint32_t w1 = sw[i + 1];
         dw[i] = __funnelshift_r(w0, w1, sh);
         w0 = w1;
     }
     const uint32_t t = len & 3u;
     src += nw * 4u; dst += nw * 4u;
-    for (uint32_t k = 0; k < t; ++k) stage[dst + k] = data[src + k];
+    for (uint32_t k = 0; k < t; ++k) out[dst + k] = data[src + k];
 }
 
-// One stream's staged range -> global: [ra, rb) are virtual destination offsets (out + offset, out
-// 16-byte aligned), stage[so + (d - (ra & ~15))] holds destination byte d.  The 16-byte aligned
-// interior leaves as one TMA bulk store (thread `issuer`); the <= 15 bytes on either side, which
-// share their vector with a neighbouring tile, are byte stores by lanes 0..31 of warp `wsel`.
-__device__ __forceinline__ void flush_stream(const uint8_t* stage, uint32_t so, uint32_t ra, uint32_t rb, uint8_t* out,
-                                             bool issuer, bool edge_warp) {
-    if (rb <= ra) return;
-    const uint32_t A = ra & ~15u;
-    const uint32_t i0 = (ra + 15u) & ~15u, i1 = rb & ~15u;
-    if (issuer && i1 > i0) tma_store_1d(out + i0, stage + so + (i0 - A), i1 - i0);
-    if (edge_warp) {
-        const uint32_t j = threadIdx.x & 31u;
-        const uint32_t head_end = i0 < rb ? i0 : rb;                 // head = [ra, head_end)
-        const uint32_t tail_beg = i1 > head_end ? i1 : head_end;     // tail = [tail_beg, rb)
-        const uint32_t d = j < 16u ? ra + j : tail_beg + (j - 16u);
-        const bool on = j < 16u ? d < head_end : d < rb;
-        if (on) out[d] = stage[so + (d - A)];
-    }
-}
-
-// kFused = false: the second pass of the two-pass path (run prefixes from k_summarize + k_scan_runs,
-//                 one CTA per run).
-// kFused = true:  the single pass.  Persistent CTAs claim tiles in order; every tile gets its prefix
-//                 from the decoupled look-back above, so the input is read once.  The number of
-//                 complete records is not known in advance: the window's trailing incomplete record is
-//                 treated like any other (its bytes land past the counted totals, its error reports
-//                 carry a record index that the host ignores, its bases are taken back at the end).
-template <bool kAscii, bool kQual, bool kOffsets, bool kPack, bool kFused>
+// The second pass: run prefixes from k_summarize + k_scan_runs, one CTA per run.
+template <bool kAscii, bool kQual, bool kOffsets, bool kPack>
 __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_resolve(const WinParams W, const ResolveParams P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x;
     uint32_t ta = 0, tb = 0;
-    BsqPrefix pre;
-    if (kFused) {
-        pre.rank = 0; pre.prev[0] = pre.prev[1] = pre.prev[2] = 0; pre.cum_seq = pre.cum_qual = pre.cum_id = 0; pre._pad = 0;
-    } else {
-        run_tiles(W, blockIdx.x, ta, tb);
-        pre = P.run_pre[blockIdx.x];
-    }
+    run_tiles(W, blockIdx.x, ta, tb);
+    const BsqPrefix pre = P.run_pre[blockIdx.x];
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&S.full_bar[s], 1);
         mbar_fence_init();
         S.nlx[0] = 0; S.nlx[1] = pre.prev[2]; S.nlx[2] = pre.prev[1]; S.nlx[3] = pre.prev[0];
-        if (kFused) S.first_claim = W.first_tile + atomicAdd(P.ticket, 1u);
     }
     __syncthreads();
-    if (kFused) { ta = S.first_claim; tb = W.n_tiles; }
-    // kList: the ordered newline list of every tile comes from k_summarize (same TMA transaction as the tile),
-    // so the bitmap / scan / list front end runs only where the bitmaps are needed anyway (validation), in the
-    // single pass, and for tiles with more newlines than the list holds
-    // (with validation: k_summarize also screened the tile -- a tile without a single HI / BAD byte needs
-    //  neither the validation bitmaps nor the per-byte walk, and takes the list too)
-    constexpr bool kList = !kFused && kStages == 1;
-    const bool use_list = kList && W.nl_list != nullptr;
+    // use_list: the ordered newline list of every tile comes from k_summarize (same TMA transaction as the tile),
+    // so the bitmap / scan / list front end runs only where the bitmaps are needed anyway (a tile that
+    // k_summarize's validation screen flagged) and for tiles with more newlines than the list holds
+    const bool use_list = W.nl_list != nullptr;
     auto list_count_of = [&](uint32_t tile) -> uint32_t { return W.nl_count[tile - W.first_tile]; };   // raw word
     // newlines of a tile whose list is usable by this instantiation, else 0 (raw = count | screen << 30)
     auto list_ok = [&](uint32_t raw) -> bool {
@@ -1125,18 +993,18 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
         return n <= (uint32_t)kNlCap && !((kAscii && (dirty & 1u)) || (kQual && (dirty & 2u)));
     };
     auto listed_count = [&](uint32_t raw) -> uint32_t { return list_ok(raw) ? (raw & kNlCountMask) : 0u; };
-    uint32_t n_next = 0;                               // (thread 0) newline count of tile t + 1
+    // thread 0 runs the tile ring: tile t + kStages is requested when tile t is done; the newline counts travel
+    // one tile further ahead (a global load whose latency nobody waits for)
+    uint32_t n_ahead = 0;                              // (thread 0) raw count word of tile t + kStages
     if (tid == 0) {
-        if (use_list && ta < tb) {
-            const uint32_t n0 = list_count_of(ta);
-            S.tile_total[0] = n0;
-            issue_tile_load<true>(S, W, ta, 0, S.nl16, listed_count(n0));
-            if (ta + 1u < tb) n_next = list_count_of(ta + 1u);
-        } else {
-            for (uint32_t s = 0; s < (uint32_t)kStages && ta + s < tb; ++s) issue_tile_load<true>(S, W, ta + s, s);
+        for (uint32_t s = 0; s < (uint32_t)kStages && ta + s < tb; ++s) {
+            uint32_t raw = 0;
+            if (use_list) { raw = list_count_of(ta + s); S.tile_total[s] = raw; }
+            issue_tile_load<true>(S, W, ta + s, s, S.nl16[s], listed_count(raw));
         }
+        if (use_list && ta + (uint32_t)kStages < tb) n_ahead = list_count_of(ta + (uint32_t)kStages);
     }
-    if (kOffsets && tid == 0 && (kFused ? ta == W.first_tile : blockIdx.x == 0)) P.line_ends[0] = W.begin - 1u;
+    if (kOffsets && tid == 0 && blockIdx.x == 0) P.line_ends[0] = W.begin - 1u;
 
     const uint32_t addlo = (128u - P.lower) * 0x01010101u, addup = (127u - P.upper) * 0x01010101u;
     uint32_t bases_acc = 0;                                              // this thread's share of sum(seq_len)
@@ -1152,29 +1020,21 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
     const uint32_t bsz = (uint32_t)P.batch_size;
     // window-local index of the next record that closes a batch (uniform; advanced as the run proceeds)
     uint32_t edge_k = (pre.rank >> 2) + (bsz - 1u - (P.rec_mod + (pre.rank >> 2)) % bsz);
-    const uint32_t n_complete = kFused ? 0xFFFFFFFFu : P.n_complete;
+    const uint32_t n_complete = P.n_complete;
+    constexpr uint32_t kRing = (uint32_t)kStages + 1u;  // tile_total ring: written one tile before it is read
 
-    for (uint32_t t = ta, it = 0; t < tb; ++it) {
+    for (uint32_t t = ta, it = 0; t < tb; ++t, ++it) {
         const TileCursor c = make_cursor(W, t, it % kStages);
         mbar_wait(&S.full_bar[c.stage], (it / kStages) & 1u);
-        if (kFused) {
-            if (tid == 0) {                            // claim the next tile now: it waits in L2 when this one is done
-                const uint32_t nt = W.first_tile + atomicAdd(P.ticket, 1u);
-                S.next_tile = nt;
-                if (nt < tb) prefetch_l2(W.base + (size_t)nt * kTile, tile_bytes_rounded(W, nt));
-            }
-            if (tid < 4) S.agg_p[tid] = 0;
-        } else if (kStages == 1 && tid == 0 && t + 1u < tb) {   // single buffer: the next tile waits in L2
+        if (kStages == 1 && tid == 0 && t + 1u < tb) {   // single buffer: the next tile waits in L2
             prefetch_l2(W.base + (size_t)(t + 1u) * kTile, tile_bytes_rounded(W, t + 1u));
-            if (use_list && listed_count(n_next) != 0u)
-                prefetch_l2(W.nl_list + (size_t)(t + 1u - W.first_tile) * kNlCap, (listed_count(n_next) * 2u + 15u) & ~15u);
+            if (use_list && listed_count(n_ahead) != 0u)
+                prefetch_l2(W.nl_list + (size_t)(t + 1u - W.first_tile) * kNlCap, (listed_count(n_ahead) * 2u + 15u) & ~15u);
         }
-        // the newline counts travel ahead of the tiles: thread 0 publishes the next tile's count (loaded one
-        // tile ago) and starts loading the one after it, so that neither costs a round trip here
-        uint32_t n_next2 = 0;
+        uint32_t n_ahead2 = 0;
         if (use_list && tid == 0) {
-            S.tile_total[(it + 1u) & 1u] = n_next;
-            if (t + 2u < tb) n_next2 = list_count_of(t + 2u);
+            S.tile_total[(it + (uint32_t)kStages) % kRing] = n_ahead;   // read kStages tiles from now
+            if (t + (uint32_t)kStages + 1u < tb) n_ahead2 = list_count_of(t + (uint32_t)kStages + 1u);
         }
         NlWords words;
 #pragma unroll
@@ -1182,88 +1042,20 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
         uint32_t total = 0, excl = 0;
         bool listed = false;                           // nlx already holds this tile's newline list
         if (use_list) {
-            const uint32_t raw = S.tile_total[it & 1u];   // written during the previous tile (or the prologue)
+            const uint32_t raw = S.tile_total[it % kRing];   // written kStages tiles ago (or in the prologue)
             total = raw & kNlCountMask;
             listed = list_ok(raw);
         }
         if (listed) {
-            for (uint32_t j = tid; j < total; j += kThreads) S.nlx[kHead + j] = c.origin + (uint32_t)S.nl16[j];
+            const uint16_t* l16 = S.nl16[c.stage];
+            for (uint32_t j = tid; j < total; j += kThreads) S.nlx[kHead + j] = c.origin + (uint32_t)l16[j];
             __syncthreads();
         } else {
-            if (kPack && (kAscii || kQual)) {          // the validation bitmaps reuse `stage`: the previous
-                if (tid == 0) tma_store_wait_read();   // tile's bulk stores and edge stores must be through with it
-                __syncthreads();
-            }
             build_bitmaps<kAscii, kQual>(S, c, addlo, addup);
             __syncthreads();
             words = load_nl_words(S, tid);
             const uint32_t cnt = popc_words(words);
             excl = block_exclusive_scan(S, cnt, total, par);
-        }
-        const uint32_t t_next = kFused ? S.next_tile : t + 1u;
-
-        if (kFused) {
-            // ---- the tile's aggregate, the look-back, the tile's prefix --------------------------
-            const bool one_pass = total <= (uint32_t)kNlCap;
-            if (one_pass) {
-                fill_newline_list<false>(S, c, words, excl, 0u);
-            } else {                                   // rare: position sums straight from the bitmap
-                uint32_t acc[4] = {0, 0, 0, 0};
-                for_each_newline_loop(words, c.origin + tid * kBytesPerThread, excl, [&](uint32_t r, uint32_t p) {
-                    const uint32_t cls = r & 3u;
-                    acc[0] += cls == 0u ? p : 0u; acc[1] += cls == 1u ? p : 0u;
-                    acc[2] += cls == 2u ? p : 0u; acc[3] += cls == 3u ? p : 0u;
-                    if (r + 4u >= total) S.carry[total - 1u - r] = p;      // carry[i] = i-th most recent
-                });
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (acc[k] != 0u) atomicAdd(&S.agg_p[k], acc[k]);
-            }
-            __syncthreads();
-            if (tid < 32u) {
-                const uint32_t lane = tid;
-                LbState mine = lb_identity();
-                mine.count = total;
-                if (one_pass) {
-                    uint32_t a = 0;
-                    for (uint32_t j = lane; j < total; j += 32u) a += S.nlx[kHead + j];   // index mod 4 == lane mod 4
-                    a += __shfl_xor_sync(0xFFFFFFFFu, a, 4);
-                    a += __shfl_xor_sync(0xFFFFFFFFu, a, 8);
-                    a += __shfl_xor_sync(0xFFFFFFFFu, a, 16);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        mine.P[k] = __shfl_sync(0xFFFFFFFFu, a, k);
-                        mine.last[k] = (uint32_t)k < total ? S.nlx[kHead + total - 1u - (uint32_t)k] : 0u;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { mine.P[k] = S.agg_p[k]; mine.last[k] = S.carry[k]; }
-                }
-                const uint32_t ti = t - W.first_tile;
-                uint32_t* const my_status = P.tile_status + (size_t)ti * kStatusWords;
-                if (lane == 0 && ti != 0u) lb_publish(my_status, kLbAgg, mine, P.epoch);
-                const LbState E = lb_look_back(P.tile_status, ti, W.begin, P.epoch);
-                const LbState I = lb_combine(E, mine);
-                if (lane == 0) {
-                    lb_publish(my_status, kLbInc, I, P.epoch);
-                    const BsqPrefix q = bsq_prefix_from(lb_to_summary(E), W.begin);
-                    S.pre = q;
-                    S.nlx[0] = 0; S.nlx[1] = q.prev[2]; S.nlx[2] = q.prev[1]; S.nlx[3] = q.prev[0];
-                    if (t + 1u == tb) {                // the window's last tile: totals for the host
-                        const BsqSummary end = lb_to_summary(I);
-                        P.scan_out->totals = bsq_totals_from(end, W.begin);
-                        P.scan_out->end_state = end;
-                        P.scan_out->region = bsq_summary_identity();
-                        // the sequence line of the trailing incomplete record was counted: take it back
-                        const uint32_t rem = I.count & 3u;
-                        if (rem >= 2u) atomicAdd(P.bases, 0ull - (unsigned long long)(I.last[rem - 2u] - I.last[rem - 1u] - 1u));
-                    }
-                }
-            }
-            __syncthreads();
-            const BsqPrefix q = S.pre;
-            rank = q.rank; cum_id = q.cum_id; cum_seq = q.cum_seq; cum_qual = q.cum_qual;
-            edge_k = (rank >> 2) + (bsz - 1u - (P.rec_mod + (rank >> 2)) % bsz);
         }
 
         // ---- validation from the bitmaps: this thread's 128 bytes, line class known from the rank
@@ -1273,8 +1065,8 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
 #pragma unroll
             for (int i = 0; i < kWordsPerThread; ++i) {
                 const uint32_t nl = words.w[i];
-                const uint32_t hiw = kAscii ? S.bm_hi()[tid * kWordsPerThread + i] : 0u;
-                const uint32_t badw = kQual ? (S.bm_bad()[tid * kWordsPerThread + i] & ~nl) : 0u;
+                const uint32_t hiw = kAscii ? S.bm_hi[tid * kWordsPerThread + i] : 0u;
+                const uint32_t badw = kQual ? (S.bm_bad[tid * kWordsPerThread + i] & ~nl) : 0u;
                 if ((hiw | badw) != 0u) {
                     uint32_t rest = 0xFFFFFFFFu, m = nl, rr = r;
                     while (rest) {
@@ -1296,14 +1088,9 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
 
         for (uint32_t pass = 0; pass < total; pass += kNlCap) {
             const uint32_t n = total - pass < (uint32_t)kNlCap ? total - pass : (uint32_t)kNlCap;
-            if (listed) {
-                // (the list is in place)
-            } else if (!kFused) {
+            if (!listed) {
                 if (total <= (uint32_t)kNlCap) fill_newline_list<false>(S, c, words, excl, 0u);
                 else fill_newline_list<true>(S, c, words, excl, pass);
-                __syncthreads();
-            } else if (total > (uint32_t)kNlCap) {     // (a one-pass tile filled its list before the look-back)
-                fill_newline_list<true>(S, c, words, excl, pass);
                 __syncthreads();
             }
             const uint32_t r0 = rank + pass;  // rank of list entry 0
@@ -1318,14 +1105,8 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
             while (edge_k < k_first) edge_k += bsz;
             const bool batch_edge = kPack && edge_k <= k_last;
 
-            // single pass: the outputs were sized from estimates; what does not fit is dropped and the
-            // host repeats the region with the two-pass path (exact sizes)
-            const bool rec_ok = !kFused || P.rec_base + (int64_t)k_last < P.rec_cap;
-            const bool line_ok = !kFused || 1u + r0 + n <= P.line_cap;
-            if (kFused && tid == 0 && (!rec_ok || (kOffsets && !line_ok))) *P.overflow = 1u;
-
             // views(): the line-end table, one coalesced store per newline
-            if (kOffsets && line_ok)
+            if (kOffsets)
                 for (uint32_t j = tid; j < n; j += kThreads) P.line_ends[1u + r0 + j] = S.nlx[kHead + j];
 
             // one thread per RECORD: it handles the (up to four) lines of its record that end in this
@@ -1334,9 +1115,9 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
             const uint32_t n_rec = k_last - k_first + 1u;
             uint32_t max_len = 0;
             for (uint32_t tb0 = 0; tb0 < n_rec; tb0 += kThreads) {
-                const uint32_t t = tb0 + tid;
-                const uint32_t k = k_first + t;
-                const bool mine = t < n_rec;
+                const uint32_t tr = tb0 + tid;
+                const uint32_t k = k_first + tr;
+                const bool mine = tr < n_rec;
                 const bool live = mine && k < n_complete;
                 const int32_t j0 = (int32_t)(4u * k - r0);                 // list index of the header's newline
                 const uint32_t* e = &S.nlx[kHead] + j0;                    // e[c] = newline of class c, e[-1] = the one before
@@ -1358,7 +1139,7 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
                             nid = z - a;
                             if (kPack && P.id_fast) *P.strip_flag = 1u;   // the optimistic id packing is void
                         }
-                        if ((kOffsets || (kPack && !P.id_fast)) && rec_ok) { P.id_spans[2u * k] = a; P.id_spans[2u * k + 1u] = nid; }
+                        if (kOffsets || (kPack && !P.id_fast)) { P.id_spans[2u * k] = a; P.id_spans[2u * k + 1u] = nid; }
                         if (len > max_len) max_len = len;
                     }
                     l_id = nid; s_id = a;
@@ -1385,7 +1166,7 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
                     if (has0) {
                         const uint32_t i = (uint32_t)(j0 - (int32_t)j_id) >> 2;
                         S.sdst[0][i] = cum_id + e_id + sh_id; S.ssrc[0][i] = s_id;
-                        if (live && P.id_fast && rec_ok) {
+                        if (live && P.id_fast) {
                             const int64_t endv = P.id_base64 + (int64_t)(cum_id + e_id + l_id);
                             P.id_ends_abs[P.rec_base + (int64_t)k] = endv;
                             if (batch_edge) { const uint32_t tb1 = P.rec_mod + k + 1u;
@@ -1399,7 +1180,7 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
                     if (has3) {
                         const uint32_t i = (uint32_t)(j0 + 3 - (int32_t)j_qual) >> 2;
                         S.sdst[2][i] = cum_qual + e_qual + sh_qual; S.ssrc[2][i] = s_qual;
-                        if (live && rec_ok) {
+                        if (live) {
                             const int64_t endv = P.qual_base64 + (int64_t)(cum_qual + e_qual + l_qual);
                             P.ends_abs[P.rec_base + (int64_t)k] = endv;
                             if (batch_edge) { const uint32_t tb1 = P.rec_mod + k + 1u;
@@ -1417,10 +1198,9 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
                     S.sdst[tid][nn] = dd; S.sdst[tid][nn + 1] = dd; S.sdst[tid][nn + 2] = dd;
                     S.ssrc[tid][nn] = c.origin + 16u; S.ssrc[tid][nn + 1] = c.origin + 16u;
                 }
-                if (tid == 0) tma_store_wait_read();   // the previous pass's bulk stores have read `stage`
                 // one barrier: the line tables are complete, every reader of the newline list is done;
                 // long lines (long reads, or a line that began far before the tile) are copied
-                // vector-parallel from wherever they lie, otherwise the pass is staged in shared memory
+                // vector-parallel from wherever they lie, otherwise straight from [halo | tile]
                 const bool long_lines = __syncthreads_or(max_len > (uint32_t)kHalo - 64u) != 0;
                 rotate_head(S, n);                     // (thread 0; next read after the barrier that ends the copy)
                 // room: bytes the id arena can still take.  Destinations past it only arise after a
@@ -1429,62 +1209,34 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
                 const bool do_id = P.id_fast && rb_id > ra_id && (int64_t)rb_id <= P.id_cap - (P.id_base64 - sh_id) && n_id != 0u;
                 const uint32_t ra_seq = d0_seq + sh_seq, rb_seq = cum_seq + sh_seq;
                 const uint32_t ra_qual = d0_qual + sh_qual, rb_qual = cum_qual + sh_qual;
-                bool ok_seq = rb_seq > ra_seq, ok_qual = rb_qual > ra_qual;
-                if (kFused) {
-                    const bool fit_seq = (int64_t)rb_seq <= P.seq_cap - (P.seq_base64 - sh_seq);
-                    const bool fit_qual = (int64_t)rb_qual <= P.qual_cap - (P.qual_base64 - sh_qual);
-                    const bool fit_id = !P.id_fast || n_id == 0u || rb_id <= ra_id || do_id;
-                    if (tid == 0 && !(fit_seq && fit_qual && fit_id)) *P.overflow = 1u;
-                    ok_seq = ok_seq && fit_seq; ok_qual = ok_qual && fit_qual;
-                }
-                if (long_lines || (P.debug_skip & 4u)) {
+                const bool ok_seq = rb_seq > ra_seq, ok_qual = rb_qual > ra_qual;
+                if (long_lines) {
                     StreamJob jobs[3];
                     jobs[0] = StreamJob{S.sdst[0], S.ssrc[0], n_id, ra_id, do_id ? rb_id : ra_id, out_id};
                     jobs[1] = StreamJob{S.sdst[1], S.ssrc[1], n_seq, ra_seq, rb_seq, out_seq};
                     jobs[2] = StreamJob{S.sdst[2], S.ssrc[2], n_qual, ra_qual, rb_qual, out_qual};
-                    if (long_lines) {
 #pragma unroll
-                        for (int st = 0; st < 3; ++st)
-                            if (jobs[st].d1 > jobs[st].d0) copy_stream(S, c, W, jobs[st]);
-                    } else {
-                        // (measurement / cross-check only) the line-parallel direct copy
-                        const uint32_t n1 = ok_seq ? n_seq : 0u, n2 = ok_qual ? n_qual : 0u, n0 = do_id ? n_id : 0u;
-                        for (uint32_t w = tid; w < n1 + n2 + n0; w += kThreads) {
-                            if (w < n1) copy_line(S, c, W, jobs[1], w);
-                            else if (w < n1 + n2) copy_line(S, c, W, jobs[2], w - n1);
-                            else copy_line(S, c, W, jobs[0], w - n1 - n2);
-                        }
-                    }
-                    __syncthreads();
-                } else if (P.debug_skip & 1u) {
-                    __syncthreads();
+                    for (int st = 0; st < 3; ++st)
+                        if (jobs[st].d1 > jobs[st].d0) copy_stream(S, c, W, jobs[st]);
                 } else {
-                    // stage layout: [id | seq | qual], each region starts at the 16-byte vector of its
-                    // first destination byte; lengths are bounded by the bytes of [halo | tile]
-                    const uint32_t A_id = ra_id & ~15u, A_seq = ra_seq & ~15u, A_qual = ra_qual & ~15u;
-                    const uint32_t so_id = 0u;
-                    const uint32_t so_seq = do_id ? ((rb_id - A_id + 15u) & ~15u) : 0u;
-                    const uint32_t so_qual = so_seq + (ok_seq ? ((rb_seq - A_seq + 15u) & ~15u) : 0u);
-                    const uint32_t n1 = ok_seq ? n_seq : 0u, n2 = ok_qual ? n_qual : 0u, n0 = do_id ? n_id : 0u;
                     const uint8_t* const data = S.data[c.stage];
                     const uint32_t sbias = (uint32_t)kHalo - c.origin;          // window offset -> offset in data[stage]
-                    // items: sequence lines, then quality lines, then ids (one line per thread)
+                    const DirectJob jq{S.sdst[1], S.ssrc[1], n_seq, ra_seq, rb_seq, out_seq};
+                    const DirectJob jr{S.sdst[2], S.ssrc[2], n_qual, ra_qual, rb_qual, out_qual};
+                    if (ok_seq) copy_interior(data, sbias, jq);
+                    if (ok_qual) copy_interior(data, sbias, jr);
+                    // one thread per line: the edge vectors of the sequence and quality lines, then the ids
+                    const uint32_t n1 = ok_seq ? n_seq : 0u, n2 = ok_qual ? n_qual : 0u, n0 = do_id ? n_id : 0u;
                     for (uint32_t w = tid; w < n1 + n2 + n0; w += kThreads) {
-                        uint32_t st, i, so, A;
-                        if (w < n1) { st = 1u; i = w; so = so_seq; A = A_seq; }
-                        else if (w < n1 + n2) { st = 2u; i = w - n1; so = so_qual; A = A_qual; }
-                        else { st = 0u; i = w - n1 - n2; so = so_id; A = A_id; }
-                        const uint32_t d = S.sdst[st][i];
-                        stage_line(data, S.stage, S.ssrc[st][i] + sbias, so + (d - A), S.sdst[st][i + 1] - d);
+                        if (w < n1) copy_edges(data, sbias, jq, w);
+                        else if (w < n1 + n2) copy_edges(data, sbias, jr, w - n1);
+                        else {
+                            const uint32_t i = w - n1 - n2, d = S.sdst[0][i];
+                            copy_small_line(data, S.ssrc[0][i] + sbias, out_id, d, S.sdst[0][i + 1] - d);
+                        }
                     }
-                    fence_proxy_async_smem();
-                    __syncthreads();
-                    const uint32_t wsel = tid >> 5;
-                    if (do_id) flush_stream(S.stage, so_id, ra_id, rb_id, out_id, tid == 0, wsel == 0u);
-                    if (ok_seq) flush_stream(S.stage, so_seq, ra_seq, rb_seq, out_seq, tid == 0, wsel == 1u);
-                    if (ok_qual) flush_stream(S.stage, so_qual, ra_qual, rb_qual, out_qual, tid == 0, wsel == 2u);
-                    if (tid == 0) tma_store_commit();
                 }
+                __syncthreads();   // the tile's bytes and the line tables are free again
             } else {
                 __syncthreads();
                 rotate_head(S, n);
@@ -1493,19 +1245,10 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
         }
         rank += total;
         if (total == 0u) __syncthreads();   // (the pass loop ends with a barrier otherwise)
-        if (kFused) {
-            if (tid == 0 && t_next < tb) issue_tile_load<true>(S, W, t_next, c.stage);
-            t = t_next;
-        } else if (use_list) {
-            if (tid == 0 && t + 1u < tb) issue_tile_load<true>(S, W, t + 1u, c.stage, S.nl16, listed_count(n_next));
-            n_next = n_next2;
-            ++t;
-        } else {
-            if (tid == 0 && t + kStages < tb) issue_tile_load<true>(S, W, t + kStages, c.stage);
-            ++t;
-        }
+        if (tid == 0 && t + (uint32_t)kStages < tb)
+            issue_tile_load<true>(S, W, t + (uint32_t)kStages, c.stage, S.nl16[c.stage], use_list ? listed_count(n_ahead) : 0u);
+        n_ahead = n_ahead2;
     }
-    if (kPack && tid == 0) tma_store_wait_all();   // shared memory must outlive the bulk stores
     // one atomic per warp: the run's share of the base count
     unsigned long long b64 = bases_acc;
 #pragma unroll

@@ -93,10 +93,10 @@ int64_t tm_parse(const uint8_t* d, uint32_t begin, uint32_t end, uint32_t run_by
     return tot.records;
 }
 
-// The single-pass kernel's decoupled look-back (bsq_device.cuh: lb_look_back), lane by lane: tile
-// `ti` combines 32 predecessors per round, nearest first, up to the nearest one whose INCLUSIVE state
-// is published (`inc_every`: every n-th tile counts as published-inclusive; 0 = none, so that the
-// walk reaches the window-init state).  Returns the number of tiles whose prefix or whose inclusive
+// Ordered 32-wide tree reductions of lb_combine (the non-commutative monoid k_scan_runs scans with warp
+// shuffles), exercised the way a decoupled look-back would use them: tile `ti` combines 32 predecessors per
+// round, nearest first, up to the nearest one whose INCLUSIVE state is known (`inc_every`: every n-th tile
+// counts as inclusive; 0 = none, so that the walk reaches the window-init state).  Returns the number of tiles whose prefix or whose inclusive
 // state differs from the sequential scan (0 = the algebra holds).
 int64_t tm_lookback_check(const uint8_t* d, uint32_t begin, uint32_t end, uint32_t tile_bytes, uint32_t inc_every) {
     if (tile_bytes == 0) tile_bytes = 1;

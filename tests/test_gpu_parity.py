@@ -248,27 +248,18 @@ def test_long_reads_span_tiles(U, oracle):
     U.check_stream(oracle, bytes(bad), batch_size=4, check_ascii=True)
 
 
-@pytest.mark.parametrize("mutate", ["none", "crlf", "noise", "notail"])
-def test_single_pass_lookback_kernel(U, B, oracle, mutate, monkeypatch):
-    """BSQ_SINGLE_PASS=1 selects k_resolve<..., kFused>: tiles claimed in order, prefixes from the
-    decoupled look-back, outputs sized from estimates (with the two-pass path as the overflow
-    fallback).  Same bit-exact bar as the default two-pass path."""
-    monkeypatch.setenv("BSQ_SINGLE_PASS", "1")
-    rng = np.random.default_rng(abs(hash("sp" + mutate)) % 2**32)
-    for val in (False, True):
-        gpu = B.GpuParser(val, val, B.parse_schema("generic"), 64, buffer_growth_enabled=True)
-        for trial in range(3):
-            data = _rand_stream(rng, int(rng.integers(1, 3000)), mutate)
-            U.check_stream(oracle, data, check_ascii=val, check_quality=val, batch_size=64, growth=True, gpu=gpu,
-                           want=(3, 1, 2)[trial % 3])
-        gpu.close()
-    if mutate == "none":
-        U.check_stream(oracle, oracle.synth(20000, 75, 300, 2, 40, "sanger"), batch_size=4096, check_ascii=True,
-                       check_quality=True)
-        U.check_stream(oracle, b"@ab\nA\n+\nI\n" * 40000, batch_size=1000)      # > kNlCap newlines per tile
-        U.check_stream(oracle, b"\n" * 100000, batch_size=16)                     # estimates overflow -> two-pass fallback
-        seq = bytes(rng.choice(list(b"ACGT"), 70000).astype(np.uint8))
-        U.check_stream(oracle, b"@long\n" + seq + b"\n+\n" + b"I" * 70000 + b"\n@s\nAC\n+\nII\n", batch_size=3)
+@pytest.mark.parametrize("digits", [8, 9])
+def test_record_stride_sweep(U, B, oracle, digits):
+    """Constant-stride streams at every record stride 293 ... 354 bytes (2 L + id digits + 11; 320 = 16 banks
+    apart, 352 = 8): the SoA copy is organised by destination vector, so no stride is special -- and every
+    alignment of (source - destination) mod 16, every line-end position inside a vector, is exercised."""
+    gpu = B.GpuParser(False, False, B.parse_schema("generic"), 1000)
+    total = 10 ** (digits - 1) + 1                 # ids zero padded to `digits`
+    for L in range(137, 168):
+        data = oracle.synth(total, L, L, 2, 40, "sanger", first=12345, count=700)
+        assert data.size == 700 * (2 * L + digits + 11)
+        U.check_stream(oracle, data, batch_size=1000, gpu=gpu, want=2 if L % 2 else 3)
+    gpu.close()
 
 
 def test_validation_screen_of_clean_and_dirty_tiles(U, B, oracle):

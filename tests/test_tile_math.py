@@ -129,9 +129,9 @@ def test_is_space_and_byte_lane_flags(tm):
 
 @pytest.mark.parametrize("mutate", ["none", "noise", "blank", "notail"])
 def test_decoupled_lookback_algebra(tm, mutate):
-    """The single-pass kernel's look-back (tile aggregates combined 32 per round back to the nearest
-    published inclusive state, or to the window-init state) gives every tile the prefix of the
-    sequential scan, whatever the tile size and whichever predecessors are already inclusive."""
+    """Ordered tree reductions of lb_combine (tile aggregates combined 32 per round back to the nearest
+    inclusive state, or to the window-init state) give every tile the prefix of the sequential scan,
+    whatever the tile size and whichever predecessors are inclusive: the monoid k_scan_runs relies on."""
     tm.tm_lookback_check.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     tm.tm_lookback_check.restype = C.c_int64
     rng = np.random.default_rng(abs(hash("lb" + mutate)) % 2**32)
