@@ -8,9 +8,12 @@ batches(4096) -- PER GPU (weak scaling: rank r holds records [r*M, (r+1)*M) of a
 
     python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path through the C ABI)
     python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference path
+    python bench.py --mixed --shard-stream                    # configs[3]: ONE 10 GiB mixed-length stream cut
+                                                              # at arbitrary byte offsets over the N ranks
 
 One "step" = one pass of the hot path over the whole per-GPU input, already resident in HBM
-(`value`), or starting from pinned HOST memory through bsq_parse_host (`e2e`).
+(`value`), or starting from pinned HOST memory through bsq_parse_host (`e2e`).  The default run also
+reports configs[2] (validation on), views() and configs[3] (sharded mixed stream) as `sub_results`.
 """
 from __future__ import annotations
 
@@ -21,15 +24,12 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GIB = 1 << 30
-ALGO_BYTES_BATCHES = 648   # R=319 read + 2L+I+16 = 329 written, per 150 bp record
-ALGO_BYTES_VIEWS = 339
 
 
 def measured_peaks():
@@ -38,6 +38,59 @@ def measured_peaks():
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class Stream:
+    """Geometry of generate_synthetic_fastq_buffer(reads, mn, mx, ...) (utils.mojo:753-768): len_i = mn + (31 i + 7) %
+    (mx - mn + 1), header "@read_<i zero padded to the width of reads - 1>\\n"."""
+
+    def __init__(self, reads: int, mn: int, mx: int):
+        self.reads, self.mn, self.mx = reads, mn, mx
+        self.digits = len(str(reads - 1)) if reads > 1 else 1
+        self.period = mx - mn + 1
+        self.pref = [0]
+        for j in range(self.period):
+            self.pref.append(self.pref[-1] + (31 * j + 7) % self.period)
+        self.overhead = 6 + self.digits + 1 + 4          # '@read_' + digits + 4 line ends + '+'
+        self.id_len = 5 + self.digits
+
+    def offset(self, i: int) -> int:
+        lens = i * self.mn + (i // self.period) * self.pref[self.period] + self.pref[i % self.period]
+        return i * self.overhead + 2 * lens
+
+    def bases(self, a: int, b: int) -> int:
+        return (self.offset(b) - self.offset(a) - (b - a) * self.overhead) // 2
+
+    def record_at(self, byte: int) -> int:
+        """Largest i with offset(i) <= byte."""
+        lo, hi = 0, self.reads
+        while lo < hi:
+            mid = (lo + hi + 1) // 2
+            if self.offset(mid) <= byte:
+                lo = mid
+            else:
+                hi = mid - 1
+        return lo
+
+
+def workload_config(args, world: int, M: int, size: int, rec_bytes: float) -> dict:
+    """The `config` object of the JSON line: identical for this repo's arm and the reference arm."""
+    if args.shard_stream:
+        name = ("configs[3]: ONE %g GiB mixed read-length (75-300 bp) FASTQ stream, validation OFF" if args.mixed
+                else "ONE %g GiB 150 bp FASTQ stream") % args.gib
+        return {"workload": name + f", {args.mode}(4096), cut at arbitrary byte offsets over the ranks",
+                "reads_total": M, "bytes_total": size, "record_bytes": rec_bytes,
+                "l2": "input (>=10 GB) is larger than L2; no flush needed",
+                "parallelism": f"{world} contiguous byte shards; per step: shard summary (k_summarize) -> all-gather of 72 B "
+                               f"-> bsq_shard_prefix -> own records + halo -> all-reduce of counts"}
+    name = ("configs[3]: 10 GiB mixed read-length (75-300 bp) FASTQ, validation OFF" if args.mixed
+            else "configs[2]: 10 GiB 150 bp FASTQ, check_ascii+check_quality, sanger" if args.validate
+            else "configs[1]: 10 GiB in-memory 150 bp Illumina FASTQ, illumina_1.8, validation OFF")
+    if args.crlf:
+        name += ", CRLF line ends"
+    return {"workload": name + f", {args.mode}(4096), per GPU", "reads_per_gpu": M, "bytes_per_gpu": size,
+            "record_bytes": rec_bytes, "l2": "input (>=10 GB) is larger than L2; no flush needed",
+            "parallelism": f"{world} x record-aligned shard, NCCL all-reduce of counts only"}
 
 
 class ClockSampler:
@@ -95,7 +148,7 @@ class ClockSampler:
 
 def reference_arm(args):
     """CPU restatement of the reference path (the oracle port: Mojo cannot be built in this image),
-    all host threads, on a bounded sample of the same workload.  Rank 0 only."""
+    all host threads, on this arm's workload: the rank-0 shard of the same stream, whole.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -104,49 +157,68 @@ def reference_arm(args):
     from concurrent.futures import ThreadPoolExecutor
 
     O.build()
+    world = max(1, args.gpus)
     cores = os.cpu_count() or 1
-    n_total = O.compute_num_reads_for_size(10 * GIB, 150, 150)
-    sample_reads = min(n_total, int(args.ref_sample_gib * GIB) // 319)
-    rec = 319
-    data = np.empty(sample_reads * rec, np.uint8)
-    parts = max(1, min(cores, 32))
+    mn, mx = (75, 300) if args.mixed else (args.read_len, args.read_len)
+    M = O.compute_num_reads_for_size(int(args.gib * GIB), mn, mx)
+    st = Stream(M if args.shard_stream else M * world, mn, mx)
+    first = 0                                       # rank 0's shard: records [0, M)
+    full_size = st.offset(first + M) - st.offset(first)
+    sample_reads = M
+    if args.ref_sample_gib > 0:
+        sample_reads = max(1, min(M, st.record_at(int(args.ref_sample_gib * GIB))))
+    size = st.offset(first + sample_reads) - st.offset(first)
+    data = np.empty(size, np.uint8)
+    parts = max(1, min(cores, 64))
     step = (sample_reads + parts - 1) // parts
 
     def gen(i):
-        first = i * step
-        cnt = min(step, sample_reads - first)
+        a = first + i * step
+        cnt = min(step, first + sample_reads - a)
         if cnt > 0:
-            O.synth(n_total, 150, 150, 2, 40, "illumina_1.8", first=first, count=cnt,
-                    out=data[first * rec:(first + cnt) * rec])
+            lo, hi = st.offset(a) - st.offset(first), st.offset(a + cnt) - st.offset(first)
+            if mn == mx:
+                O.synth(st.reads, mn, mx, 2, 40, "illumina_1.8", first=a, count=cnt, out=data[lo:hi])
+            else:   # (the generator wants room for `cnt` records of the maximum length)
+                data[lo:hi] = O.synth(st.reads, mn, mx, 2, 40, "illumina_1.8", first=a, count=cnt)
     with ThreadPoolExecutor(parts) as ex:
         list(ex.map(gen, range(parts)))
-    cfg = O.config(False, False, "illumina_1.8")
+    cfg = O.config(args.validate, args.validate, "sanger" if args.validate else "illumina_1.8")
+    mode = 1 if args.mode == "batches" else 0
     for _ in range(args.warmup):
-        O.baseline_mt(data, cfg, 1, 4096, cores)
+        O.baseline_mt(data, cfg, mode, 4096, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        n, bases, code = O.baseline_mt(data, cfg, 1, 4096, cores)
+        n, bases, code = O.baseline_mt(data, cfg, mode, 4096, cores)
         assert n == sample_reads and code == 0
     dt = (time.perf_counter() - t0) / args.steps
     value = sample_reads / dt
     # the reference's FastqParser is a sequential object (one parser = one thread, record.mojo:439): the same
-    # sample through ONE thread is what a single BlazeSeq parser delivers; `value` shards the sample by
-    # newline rank over every host thread, which the reference itself does not do
+    # bytes through ONE thread is what a single BlazeSeq parser delivers; `value` shards them by newline rank
+    # over every host thread, which the reference itself does not do
     t1 = time.perf_counter()
-    O.baseline_mt(data, cfg, 1, 4096, 1)
+    O.baseline_mt(data, cfg, mode, 4096, 1)
     one_thread = sample_reads / (time.perf_counter() - t1)
-    sample = f"first {sample_reads} reads ({data.size / GIB:.2f} GiB) of the 10 GiB 150 bp stream, batches(4096)"
+    whole = sample_reads == M
+    sample = (f"{'all' if whole else 'the first'} {sample_reads} reads ({data.size / GIB:.2f} GiB) of the workload"
+              f"{'' if whole else ' (bounded sample)'}, {args.mode}(4096), {cores} threads")
     emit(json.dumps({
         "impl": "reference", "metric": "fastq_reads_per_s", "value": value, "unit": "reads/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "parsed_gb_per_s": data.size / dt / 1e9,
-        "config": {"workload": "configs[1]: 10 GiB in-memory 150 bp Illumina FASTQ, illumina_1.8, validation OFF, "
-                               "batches(4096)", "sample": sample},
+        "higher_is_better": True, "scaling": "strong" if args.shard_stream else "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "parsed_gb_per_s": data.size / dt / 1e9,
+        "config": workload_config(args, world, M, full_size, full_size / M),
         "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port", "sample": sample,
                          "value_1core": one_thread},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+class _DevPtr:
+    """A device address as a torch-importable array (zero copy)."""
+
+    def __init__(self, ptr, n, typestr="|u1"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
 def main():
@@ -159,18 +231,22 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--ref-sample-gib", type=float, default=1.0)
+    ap.add_argument("--no-sub", action="store_true", help="skip the configs[2] / views / configs[3] sub-results")
+    ap.add_argument("--sub-steps", type=int, default=3)
+    ap.add_argument("--ref-sample-gib", type=float, default=0.0, help="reference arm: bound the input (0 = the whole workload)")
     ap.add_argument("--cpu-sample-gib", type=float, default=1.0)
     ap.add_argument("--mode", default="batches", choices=["batches", "views"])
     ap.add_argument("--validate", action="store_true", help="configs[2]: check_ascii + check_quality, sanger")
     ap.add_argument("--mixed", action="store_true", help="configs[3]: mixed read length 75-300 bp instead of 150 bp")
+    ap.add_argument("--shard-stream", action="store_true",
+                    help="strong scaling: ONE stream of --gib cut at arbitrary byte offsets over the ranks (sharding.plan)")
+    ap.add_argument("--crlf", action="store_true", help="CRLF line ends: every id needs _strip_spaces (id strip pipeline)")
     ap.add_argument("--read-len", type=int, default=150, help="read length of the synthetic stream (record stride sweeps)")
     ap.add_argument("--id-digits", type=int, default=0, help="zero-padded id width (0: that of the stream's read count)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
 
-    import numpy as np
     import torch
 
     import blazeseq_b200 as B
@@ -195,69 +271,195 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- input: this rank's shard of an (N * M)-record stream, generated on the device --------
+    def max_over_ranks(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    L = capi.lib()
+    peak, peak_src = measured_peaks()
+
+    def timed(step_fn, steps, gpu):
+        """`steps` calls between barrier+synchronize pairs.  Returns (wall s, max over ranks; per-step device ms [5];
+        per-step device ms of the whole pass, max over ranks; kernel launches)."""
+        barrier()
+        ms_sum, launches = [0.0] * 5, 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_fn()
+            ms, nl = gpu.timing()
+            ms_sum = [a + b for a, b in zip(ms_sum, ms)]
+            launches += nl
+        barrier()
+        wall = time.perf_counter() - t0
+        wall_max, dev_ms_max, launches = max_over_ranks(wall, ms_sum[4] / steps, float(launches))
+        return wall_max, [m / steps for m in ms_sum], dev_ms_max, int(launches)
+
+    # ------------------------------------------------------------------------------------------------
+    # configs[3] / --shard-stream: ONE stream, contiguous byte shards cut at arbitrary offsets
+    # ------------------------------------------------------------------------------------------------
+    def shard_stream_leg(gib, mn, mx, steps, warmup, mode="batches"):
+        schema = B.parse_schema("illumina_1.8")
+        reads = L.bsq_compute_num_reads_for_size(int(gib * GIB), mn, mx)
+        st = Stream(reads, mn, mx)
+        total = st.offset(reads)
+        # cut points: equal shares, moved off every natural alignment
+        bounds = [0] + [total * r // world + 37 * r + 5 for r in range(1, world)] + [total]
+        lo, hi = bounds[rank], bounds[rank + 1]
+        halo = 2 * (st.overhead + 2 * mx)                       # the next shard's first own record starts within one record
+        end = min(total, hi + halo)
+        i0, i1 = st.record_at(lo), min(reads, st.record_at(end - 1) + 1)
+        nbytes = st.offset(i1) - st.offset(i0)
+        tmp = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        g = B.GpuParser(False, False, schema, 4096, device_id=local)
+        assert g.synth_device(tmp.data_ptr(), nbytes, reads, i0, i1 - i0, mn, mx, 2, 40, schema) == nbytes
+        base = tmp.data_ptr() + (lo - st.offset(i0))             # device address of stream byte `lo`
+        want = capi.WANT_BATCHES if mode == "batches" else capi.WANT_OFFSETS
+        first_own = i0 if st.offset(i0) == lo else i0 + 1        # what the stitching must find
+        state = {}
+
+        def step():
+            summary = g.summarize_device(base, hi - lo)
+            if dist is not None:
+                plan = sharding.plan(dist, summary, hi - lo, device=dev)
+            else:
+                plan = sharding.ShardPlan(0, 1, 0, hi - lo, 0, 0)
+            assert plan.first_record == first_own and plan.end - (hi - lo) <= end - hi, (plan, first_own)
+            n = plan.end - plan.begin
+            r = g.parse_device(base + plan.begin, n, lo + plan.begin, plan.first_record, rank == world - 1, want)
+            assert r.bytes_consumed == n and r.stop.code in (capi.OK, capi.EOF), (r.bytes_consumed, n, r.stop.text)
+            state["r"], state["plan"] = r, plan
+            return r
+        for _ in range(max(warmup, 1)):
+            step()
+        wall, ms, dev_ms, launches = timed(step, steps, g)
+        r, plan = state["r"], state["plan"]
+        own_reads = int(r.n_records)
+        own_bases = st.bases(plan.first_record, plan.first_record + own_reads)
+        assert r.n_bases == own_bases
+        tot_reads, tot_bases = own_reads, own_bases
+        if dist is not None:
+            tot_reads, tot_bases = sharding.allreduce_counts(dist, own_reads, own_bases, device=dev)
+        assert (tot_reads, tot_bases) == (reads, st.bases(0, reads)), (tot_reads, reads)
+        g.close()
+        del tmp
+        algo = total / reads + (2 * st.bases(0, reads) / reads + st.id_len + 16 if mode == "batches" else 20)
+        return {"reads": reads, "bytes": total, "record_bytes": total / reads, "wall": wall, "ms": ms, "dev_ms": dev_ms,
+                "launches": launches, "steps": steps, "value": reads / (wall / steps), "ms_per_step": wall / steps * 1e3,
+                "n_windows": int(r.n_windows), "own_reads": own_reads, "algo": algo}
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    if args.shard_stream:
+        mn, mx = (75, 300) if args.mixed else (args.read_len, args.read_len)
+        leg = shard_stream_leg(args.gib, mn, mx, args.steps, max(args.warmup, 3), args.mode)
+        clocks = sampler.stop()
+        resolve_ms = leg["ms"][2]
+        algo_bytes = leg["algo"] * leg["own_reads"]
+        roofline = {"bound": "hbm", "kernel": "k_resolve", "pass": "shard summary + two-pass parse of the own records",
+                    "achieved": algo_bytes / (resolve_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": algo_bytes / (resolve_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_record": leg["algo"], "records_per_launch": leg["own_reads"] / leg["n_windows"],
+                    "launches_per_step": leg["n_windows"], "avg_launch_ms": resolve_ms / leg["n_windows"],
+                    "summarize_ms_per_step": leg["ms"][0], "tail_rebase_ms_per_step": leg["ms"][3], "step_device_ms": leg["dev_ms"],
+                    "note": "rank 0's kernels; `value` is the whole job (max over ranks, summaries + collectives inside)"}
+        if rank == 0:
+            emit(json.dumps({
+                "metric": "fastq_reads_per_s", "value": leg["value"], "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": leg["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "parsed_gb_per_s": leg["bytes"] / (leg["ms_per_step"] * 1e-3) / 1e9,
+                "config": workload_config(args, world, leg["reads"], leg["bytes"], leg["record_bytes"]),
+                "roofline": roofline, "cpu_baseline": None, "e2e": None, "gpu_launches": leg["launches"], "clocks": clocks,
+                "timing": "wall clock between barrier+synchronize pairs (max over ranks)"}))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------------------------------------
+    # the headline: this rank's shard of an (N * M)-record stream, generated on the device
+    # ------------------------------------------------------------------------------------------------
     schema = B.parse_schema("sanger" if args.validate else "illumina_1.8")
     mn, mx = (75, 300) if args.mixed else (args.read_len, args.read_len)
-    M = capi.lib().bsq_compute_num_reads_for_size(int(args.gib * GIB), mn, mx)
+    M = L.bsq_compute_num_reads_for_size(int(args.gib * GIB), mn, mx)
     total_reads = M * world
     stream_reads = total_reads              # ids are zero padded to the width of the stream's last index
     if args.id_digits:
         stream_reads = max(total_reads, 10 ** (args.id_digits - 1) + 1)
-    digits = len(str(stream_reads - 1))
+    st = Stream(stream_reads, mn, mx)
     gpu = B.GpuParser(args.validate, args.validate, schema, 4096, device_id=local)
-    # byte range of this rank's records inside the (world * M)-record stream (utils.mojo:753-768:
-    # len_i = mn + (31 i + 7) % (mx - mn + 1), header "@read_<i zero padded to `digits`>\n")
-    L = capi.lib()
-    period = mx - mn + 1
-    pref = [0]
-    for j in range(period):
-        pref.append(pref[-1] + (31 * j + 7) % period)
-
-    def stream_offset(i):
-        lens = i * mn + (i // period) * pref[period] + pref[i % period]
-        return i * (6 + digits + 1 + 4) + 2 * lens
-    lo_off, hi_off = stream_offset(rank * M), stream_offset((rank + 1) * M)
+    lo_off, hi_off = st.offset(rank * M), st.offset((rank + 1) * M)
     size = hi_off - lo_off
     rec_bytes = size / M                       # average bytes per record
-    bases_expected = (size - M * (6 + digits + 1 + 4)) // 2
+    bases_expected = st.bases(rank * M, (rank + 1) * M)
     buf = torch.empty(size + 256, dtype=torch.uint8, device=dev)
     assert gpu.synth_device(buf.data_ptr(), size, stream_reads, rank * M, M, mn, mx, 2, 40, schema) == size
+    if args.crlf:
+        # "\n" -> "\r\n" on the device: the id loses its "\r" (utils.mojo:221-242), sequence and quality keep it
+        nl = buf[:size] == 10
+        pos = torch.arange(size, device=dev, dtype=torch.int64) + torch.cumsum(nl, 0)
+        out = torch.empty(size + 4 * M + 256, dtype=torch.uint8, device=dev)
+        out[pos] = buf[:size]
+        out[pos[nl] - 1] = 13
+        del nl, pos
+        buf, size = out, size + 4 * M
+        bases_expected += M
+        rec_bytes = size / M
+        lo_off = 0
     want = capi.WANT_BATCHES if args.mode == "batches" else capi.WANT_OFFSETS
     # algorithmic bytes per record (SURVEY 8d): R read + (2L + I + 16) written, or R + 20 for views
-    id_len = 5 + digits
-    algo = rec_bytes + (2 * (bases_expected / M) + id_len + 16 if args.mode == "batches" else 20)
+    algo = rec_bytes + (2 * (bases_expected / M) + st.id_len + 16 if args.mode == "batches" else 20)
 
     def step():
         r = gpu.parse_device(buf.data_ptr(), size, lo_off, rank * M, True, want)
         assert r.n_records == M and r.stop.code == capi.EOF, (r.n_records, r.stop.text)
         return r
 
-    # nvidia-smi needs ~100 ms to start: launch it before the warm-up so that it is sampling (every
-    # 100 ms) while the timed steps run; warm-up samples are under the same load
-    sampler = ClockSampler(local)
-    sampler.start()
+    # nvidia-smi needs ~100 ms to start: it was launched above so that it is sampling (every 20 ms) while the
+    # timed steps run; warm-up samples are under the same load
     for _ in range(max(args.warmup, 3)):
         res = step()
     assert res.n_bases == bases_expected
 
+    # ---- the SoA of the whole pass, checked on the device (untimed): every record, not only the counts ------
+    soa_check = None
+    if args.mode == "batches":
+        v = gpu.soa_view()
+        seq = torch.as_tensor(_DevPtr(v.sequence_buffer, v.sequence_bytes), device=dev)
+        qual = torch.as_tensor(_DevPtr(v.qual_buffer, v.seq_len), device=dev)
+        ids = torch.as_tensor(_DevPtr(v.id_buffer, v.total_id_bytes), device=dev)
+        ends = torch.as_tensor(_DevPtr(v.ends, M, "<i8"), device=dev)
+        id_ends = torch.as_tensor(_DevPtr(v.id_ends, M, "<i8"), device=dev)
+        ok = int(v.seq_len) == bases_expected and int(v.total_id_bytes) == M * st.id_len and int(v.num_records) == M
+        if mn == mx and not args.crlf:
+            # constant stride: the arenas are strided gathers of the input, the ends arithmetic progressions per batch
+            rec, hdr = st.overhead + 2 * mn, st.id_len + 2
+            recs = buf[:size].view(M, rec)
+            ok = ok and bool(torch.equal(seq.view(M, mn), recs[:, hdr:hdr + mn]))
+            ok = ok and bool(torch.equal(qual.view(M, mn), recs[:, hdr + mn + 3:hdr + 2 * mn + 3]))
+            ok = ok and bool(torch.equal(ids.view(M, st.id_len), recs[:, 1:1 + st.id_len]))
+            k = torch.arange(M, device=dev)
+            ok = ok and bool(torch.equal(ends, (k % 4096 + 1) * mn)) and bool(torch.equal(id_ends, (k % 4096 + 1) * st.id_len))
+            del k, recs
+            soa_check = "all %d records: sequence / quality / id arenas == strided gather of the input, ends exact" % M
+        else:
+            # every input byte is an id, sequence or quality byte, '@', '+' or a line end (CRLF: the '\r' of the id
+            # and '+' lines is dropped, the others stay in the arenas): a linear checksum over the arenas
+            total = int(buf[:size].sum(dtype=torch.int64))
+            got = int(seq.sum(dtype=torch.int64)) + int(qual.sum(dtype=torch.int64)) + int(ids.sum(dtype=torch.int64))
+            fixed = M * (ord("@") + ord("+") + 4 * 10) + (M * 13 * 2 if args.crlf else 0)
+            ok = ok and got + fixed == total
+            ok = ok and bool(torch.all(ends[1:] - ends[:-1] != 0)) and int(id_ends[-1]) == (M - (M - 1) // 4096 * 4096) * st.id_len
+            soa_check = "byte-sum checksum of the three arenas == input minus delimiters; sizes and id ends exact"
+        assert ok, "SoA check failed"
+        del seq, qual, ids, ends, id_ends
+
     # ---- timed region ------------------------------------------------------------------------------
-    barrier()
-    ms_sum = [0.0] * 5
-    launches = 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-        ms, nl = gpu.timing()
-        ms_sum = [a + b for a, b in zip(ms_sum, ms)]
-        launches += nl
-    barrier()
-    wall = time.perf_counter() - t0
+    wall_max, ms_avg, dev_ms_max, launches = timed(step, args.steps, gpu)
     clocks = sampler.stop()
-    dev_ms = ms_sum[4] / args.steps
-    t = torch.tensor([wall, dev_ms, float(launches)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wall_max, dev_ms_max, launches = float(t[0]), float(t[1]), int(t[2])
+    dev_ms = ms_avg[4]
     # the one collective of the path: total reads / bases
     reads, bases = M, bases_expected
     if dist is not None:
@@ -267,16 +469,15 @@ def main():
     value = total_reads / (wall_max / args.steps)
 
     # ---- roofline of the dominant kernel (k_resolve: read R, write the SoA) ----------------------
-    peak, peak_src = measured_peaks()
     n_windows = int(res.n_windows)
-    resolve_ms = ms_sum[2] / args.steps           # all k_resolve launches of one step
+    resolve_ms = ms_avg[2]                        # all k_resolve launches of one step
     achieved = algo * M / (resolve_ms * 1e-3) / 1e9
     traffic = None
     try:
         # measured DRAM bytes per record of k_resolve (one ncu --set full capture, profiles/traffic.json),
         # scaled to the records one launch of this run processes
         per_rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_resolve_bytes_per_record"]
-        traffic = per_rec * M / n_windows if args.mode == "batches" and not args.validate else None
+        traffic = per_rec * M / n_windows if args.mode == "batches" and not args.validate and mn == mx == 150 else None
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "k_resolve", "pass": "two-pass (k_summarize + k_scan_runs, then k_resolve)",
@@ -284,9 +485,45 @@ def main():
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_record": algo, "records_per_launch": M / n_windows,
                 "launches_per_step": n_windows, "avg_launch_ms": resolve_ms / n_windows,
-                "summarize_ms_per_step": ms_sum[0] / args.steps, "tail_rebase_ms_per_step": ms_sum[3] / args.steps,
+                "summarize_ms_per_step": ms_avg[0], "tail_rebase_ms_per_step": ms_avg[3],
                 "step_device_ms": dev_ms,
                 "step_frac": algo * M / (dev_ms * 1e-3) / 1e9 / peak}
+
+    # ---- sub-results: the other BASELINE configs on the same box, same run (short) ----------------
+    sub = None
+    plain = not (args.validate or args.mixed or args.crlf or args.mode != "batches" or args.id_digits or args.read_len != 150)
+    if plain and not args.no_sub:
+        sub = {}
+        k = max(1, args.sub_steps)
+
+        def step_views():   # views(): offsets only
+            r = gpu.parse_device(buf.data_ptr(), size, lo_off, rank * M, True, capi.WANT_OFFSETS)
+            assert r.n_records == M and r.stop.code == capi.EOF
+        step_views()
+        w, ms, _, _ = timed(step_views, k, gpu)
+        sub["views"] = {"workload": "configs[1] input, views(): offsets table only, per GPU", "value": total_reads / (w / k),
+                        "unit": "reads/s", "ms_per_step": w / k * 1e3, "steps": k,
+                        "k_resolve_ms_per_launch": ms[2] / n_windows, "summarize_ms_per_step": ms[0]}
+        # configs[2]: validation on (sanger == illumina_1.8 numerically: the same bytes)
+        gv = B.GpuParser(True, True, B.parse_schema("sanger"), 4096, device_id=local)
+
+        def step_val():
+            r = gv.parse_device(buf.data_ptr(), size, lo_off, rank * M, True, capi.WANT_BATCHES)
+            assert r.n_records == M and r.stop.code == capi.EOF and r.n_bases == bases_expected
+        step_val()
+        w, ms, _, _ = timed(step_val, k, gv)
+        sub["configs[2]"] = {"workload": "configs[2]: the same 10 GiB, check_ascii + check_quality, sanger, batches(4096), per GPU",
+                             "value": total_reads / (w / k), "unit": "reads/s", "ms_per_step": w / k * 1e3, "steps": k,
+                             "k_resolve_ms_per_launch": ms[2] / n_windows, "summarize_ms_per_step": ms[0]}
+        gv.close()
+        # configs[3]: one mixed-length 10 GiB stream cut over the ranks at arbitrary byte offsets
+        leg = shard_stream_leg(args.gib, 75, 300, k, 1)
+        sub["configs[3]"] = {"workload": f"configs[3]: ONE {args.gib:g} GiB mixed read-length (75-300 bp) stream, validation OFF, "
+                                         f"batches(4096), {world} byte shard(s) cut at arbitrary offsets (summary -> all-gather -> "
+                                         "shard prefix -> own records + halo -> all-reduce)", "scaling": "strong",
+                             "value": leg["value"], "unit": "reads/s", "ms_per_step": leg["ms_per_step"], "steps": k,
+                             "reads_total": leg["reads"], "parsed_gb_per_s": leg["bytes"] / (leg["ms_per_step"] * 1e-3) / 1e9,
+                             "k_resolve_ms_per_launch": leg["ms"][2] / leg["n_windows"], "summarize_ms_per_step": leg["ms"][0]}
 
     # ---- e2e: the same pass starting from pinned host memory (H2D inside the timed region) -------
     e2e = None
@@ -305,14 +542,31 @@ def main():
             r = gpu.parse_host(harr, lo_off, rank * M, True, want)
             assert r.n_records == M and r.stop.code == capi.EOF
         barrier()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        (dt,) = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
         d2h = 8 * (int(r.n_batches) + 1) * 2 + 8 + 16 + 168   # batch directory + error word + scan totals
-        e2e = {"value": total_reads / float(tt[0]), "unit": "reads/s", "h2d_bytes_per_step": size,
-               "d2h_bytes_per_step": d2h, "ms_per_step": float(tt[0]) * 1e3,
+        e2e = {"value": total_reads / dt, "unit": "reads/s", "h2d_bytes_per_step": size,
+               "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
                "result": "DeviceFastqBatch SoA left on the device + host batch directory"}
+        if args.mode == "batches":
+            # ... and with the reference's HOST product: the whole FastqBatch SoA copied back to pinned memory
+            v = gpu.soa_view()
+            outs = [torch.empty(int(nb), dtype=dt_, pin_memory=True) for nb, dt_ in (
+                (v.sequence_bytes, torch.uint8), (v.seq_len, torch.uint8), (v.total_id_bytes, torch.uint8),
+                (M, torch.int64), (M, torch.int64))]
+            gpu.soa_to_host(*outs)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                r = gpu.parse_host(harr, lo_off, rank * M, True, want)
+                gpu.soa_to_host(*outs)
+            barrier()
+            (dth,) = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+            back = int(v.sequence_bytes) + int(v.seq_len) + int(v.total_id_bytes) + 16 * M
+            assert int(outs[3][-1]) == int(torch.as_tensor(_DevPtr(v.ends, M, "<i8"), device=dev)[-1])
+            e2e["host_batch"] = {"value": total_reads / dth, "unit": "reads/s", "ms_per_step": dth * 1e3,
+                                 "h2d_bytes_per_step": size, "d2h_bytes_per_step": back + d2h,
+                                 "result": "host FastqBatch SoA (five arrays, pinned) via bsq_soa_to_host after the pass"}
+            del outs
         del host, harr
 
     # ---- CPU baseline beside it (rank 0, N=1): the oracle port on a bounded sample ---------------
@@ -322,7 +576,7 @@ def main():
         import oracle_py as O
         cores = os.cpu_count() or 1
         sample_reads = min(M, int(args.cpu_sample_gib * GIB / rec_bytes))
-        sample_bytes = stream_offset(rank * M + sample_reads) - lo_off
+        sample_bytes = (st.offset(rank * M + sample_reads) - st.offset(rank * M)) + (4 * sample_reads if args.crlf else 0)
         sample = buf[:sample_bytes].cpu().numpy()
         cfg = O.config(args.validate, args.validate, "sanger" if args.validate else "illumina_1.8")
         mode = 1 if args.mode == "batches" else 0
@@ -348,13 +602,9 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "parsed_gb_per_s": size * world / (wall_max / args.steps) / 1e9,
-            "config": {"workload": ("configs[3]: 10 GiB mixed read-length (75-300 bp) FASTQ, validation OFF" if args.mixed
-                                    else "configs[2]: 10 GiB 150 bp FASTQ, check_ascii+check_quality, sanger" if args.validate
-                                    else "configs[1]: 10 GiB in-memory 150 bp Illumina FASTQ, illumina_1.8, validation OFF")
-                       + f", {args.mode}(4096), per GPU", "reads_per_gpu": M, "bytes_per_gpu": size,
-                       "record_bytes": rec_bytes, "l2": "input (>=10 GB) is larger than L2; no flush needed",
-                       "parallelism": f"{world} x record-aligned shard, NCCL all-reduce of counts only"},
+            "config": workload_config(args, world, M, size, rec_bytes),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "soa_check": soa_check, "sub_results": sub,
             "timing": "wall clock between barrier+synchronize pairs (max over ranks); kernels timed with CUDA events "
                       "on the parser's stream",
         }

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("BSQ_LIB") or os.path.join(HERE, "lib", "libblazeseq_g
 # FastxErrorCode (blazeseq/errors.mojo:43-56) + library failures
 OK, ID_NO_AT, SEP_NO_PLUS, SEQ_QUAL_LEN_MISMATCH, ASCII_INVALID, QUALITY_OUT_OF_RANGE = range(6)
 EOF, UNEXPECTED_EOF, BUFFER_EXCEEDED, BUFFER_AT_MAX, OTHER, EMPTY_ERROR = range(6, 12)
-E_CUDA, E_ARG, E_NO_DEVICE, E_NOMEM, E_STATE = -1, -2, -3, -4, -5
+E_CUDA, E_ARG, E_NO_DEVICE, E_NOMEM, E_STATE, E_IO = -1, -2, -3, -4, -5, -6
 WANT_OFFSETS, WANT_BATCHES = 1, 2
 
 # every symbol include/blazeseq_gpu.h declares (tests check the library exports exactly these)
@@ -25,7 +25,7 @@ SYMBOLS = [
     "bsq_get_soa", "bsq_batch_to_host", "bsq_offsets_to_host", "bsq_pass_device_input",
     "bsq_last_timing", "bsq_compute_num_reads_for_size", "bsq_synth_size", "bsq_synth_device",
     "bsq_summarize_device", "bsq_shard_prefix", "bsq_stream_open", "bsq_stream_next", "bsq_stream_region",
-    "bsq_stream_get_stats", "bsq_stream_close", "bsq_quality_sums",
+    "bsq_stream_get_stats", "bsq_stream_close", "bsq_quality_sums", "bsq_soa_to_host",
 ]
 
 
@@ -36,6 +36,7 @@ class Config(C.Structure):
         ("buffer_capacity", C.c_int64), ("buffer_max_capacity", C.c_int64),
         ("buffer_growth_enabled", C.c_int32), ("batch_size", C.c_int32),
         ("h2d_chunk_bytes", C.c_int64), ("force_id_slow_path", C.c_int32), ("inflate_threads", C.c_int32),
+        ("compat_q5_width", C.c_int32), ("_pad1", C.c_int32),
     ]
 
 
@@ -146,6 +147,9 @@ def lib():
     L.bsq_stream_close.argtypes = [vp]
     L.bsq_stream_close.restype = None
     L.bsq_quality_sums.argtypes = [vp, i64, i64, vp, vp]
+    L.bsq_soa_to_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.bsq_soa_to_host.restype = i32
+    L.bsq_quality_sums.restype = i32
     for name in ("bsq_stream_open", "bsq_stream_next", "bsq_stream_get_stats", "bsq_create", "bsq_get_offsets", "bsq_get_batch", "bsq_get_soa", "bsq_batch_to_host",
                  "bsq_offsets_to_host", "bsq_last_timing", "bsq_synth_device", "bsq_summarize_device",
                  "bsq_shard_prefix"):

@@ -18,7 +18,7 @@ struct TailParams {
     const uint8_t* base;         // window base
     uint32_t hs, nl0, nl1, nl2, end;  // record start, the three newlines, end of stream
     uint32_t k;                  // window-local record index (== n_complete)
-    uint32_t check_ascii, check_quality, lower, upper;
+    uint32_t check_ascii, check_quality, lower, upper, q5_width;
     uint32_t want_offsets, want_pack, id_fast;
     uint32_t seq_rel, qual_rel, id_rel;   // window-relative stream offsets (totals)
     uint32_t newline_rank;       // rank of the virtual 4th newline (4k + 3)
@@ -66,11 +66,13 @@ __global__ void __launch_bounds__(256, 1) k_tail(const TailParams T, const Resol
         for (uint32_t x = tid; x < seq_len; x += blockDim.x) hi |= B[seq_s + x] & 0x80u;
         for (uint32_t x = tid; x < qual_len; x += blockDim.x) hi |= B[qs + x] & 0x80u;
     }
-    if (T.check_quality)
+    if (T.check_quality) {
+        const uint32_t body = T.q5_width ? qual_len - qual_len % T.q5_width : 0u;   // record.mojo:90-102 as written
         for (uint32_t x = tid; x < qual_len; x += blockDim.x) {
             const uint32_t b = B[qs + x];
-            if (b < T.lower || b > T.upper) bad = 1;
+            if (b < T.lower || b > T.upper || (x < body && b == T.upper)) bad = 1;
         }
+    }
     if (hi) s_flag[1] = 1;
     if (bad) s_flag[2] = 1;
     __syncthreads();
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(256, 1) k_tail(const TailParams T, const Resol
         else if (s_flag[2]) report(P, T.k, 5u);
         out->status = 0; out->id_len = id_len; out->seq_len = seq_len; out->qual_len = qual_len;
         if (T.want_offsets) P.line_ends[1u + T.newline_rank] = T.end;  // record_end
-        if (T.want_offsets || (T.want_pack && !T.id_fast)) { P.id_spans[2u * T.k] = id_s; P.id_spans[2u * T.k + 1u] = id_len; }
+        if (T.want_offsets || T.want_pack) { P.id_spans[2u * T.k] = id_s; P.id_spans[2u * T.k + 1u] = id_len; }
         if (T.want_pack) {
             const int64_t gk = P.rec_base + (int64_t)T.k;
             const int64_t endv = P.qual_base64 + (int64_t)T.qual_rel + (int64_t)qual_len;
@@ -182,20 +184,26 @@ __global__ void __launch_bounds__(256) k_id_bases(const int64_t* __restrict__ id
     }
 }
 
-// one warp per record
+// One thread per record: the ids are short (tens of bytes), so the copies of a warp's 32 records are 32
+// independent byte streams in flight (a warp per record left 19 of 32 lanes idle and serialised the
+// span -> source -> destination dependency of every record).
 __global__ void __launch_bounds__(256) k_id_copy(const WindowTable WT, const uint32_t* __restrict__ id_spans,
                                                  const int64_t* __restrict__ id_ends, uint8_t* __restrict__ id_out,
                                                  int64_t n) {
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31u;
-    for (int64_t i = warp; i < n; i += nwarps) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int w = 0;
         while (w + 1 < WT.n && i >= WT.rec_base[w + 1]) ++w;
-        const uint32_t len = id_spans[2 * i + 1];
-        const uint8_t* src = WT.base[w] + id_spans[2 * i];
+        const uint2 sp = *reinterpret_cast<const uint2*>(id_spans + 2 * i);
+        const uint32_t len = sp.y;
+        const uint8_t* src = WT.base[w] + sp.x;
         uint8_t* dst = id_out + (id_ends[i] - (int64_t)len);
-        for (uint32_t x = lane; x < len; x += 32u) dst[x] = src[x];
+        uint32_t x = 0;
+        for (; x + 4u <= len; x += 4u) {
+            const uint8_t b0 = src[x], b1 = src[x + 1], b2 = src[x + 2], b3 = src[x + 3];
+            dst[x] = b0; dst[x + 1] = b1; dst[x + 2] = b2; dst[x + 3] = b3;
+        }
+        for (; x < len; ++x) dst[x] = src[x];
     }
 }
 

@@ -148,11 +148,19 @@ void set_plain_error(bsq_error* e, int code, const char* text) {
     m.str(text);
 }
 
-// k_resolve: the validation bitmaps are the tail of TileSmem and only allocated by validating passes
-size_t smem_bytes(bool validate = true) {
+// k_resolve: kResolveCtas / SM when it packs; without the SoA stage (views, count/validate-only) kViewCtas / SM
+size_t smem_bytes(bool pack = true, bool validate = true) {
+#if BSQ_COPY_STAGED
+    if (pack) return sizeof(TileSmem) + 128;
+    return offsetof(TileSmem, stage) + (validate ? 2 * kWords * 4 : 0) + 128;
+#else
+    (void)pack;   // the validation bitmaps are the tail of TileSmem, only allocated by validating passes
     return (validate ? sizeof(TileSmem) : offsetof(TileSmem, bm_hi)) + 128;
+#endif
 }
-size_t smem_bytes_summarize() { return sizeof(SumSmem) + 128; }   // k_summarize: kSummarizeCtas / SM
+size_t smem_bytes_summarize(bool sums) {   // k_summarize: SumShape<kSums>
+    return (sums ? sizeof(SumSmemT<SumShape<true>::kStagesOf>) : sizeof(SumSmemT<SumShape<false>::kStagesOf>)) + 128;
+}
 
 template <typename K>
 cudaError_t opt_in_smem(K kernel, size_t bytes) {
@@ -205,7 +213,7 @@ SummarizeKernel pick_summarize(bool sums, bool hi, bool bad) {
 }
 
 bsq_status setup_kernels(bsq_parser* p) {
-    for (int i = 0; i < 8; ++i) CK(opt_in_smem(pick_summarize(i & 4, i & 2, i & 1), smem_bytes_summarize()));
+    for (int i = 0; i < 8; ++i) CK(opt_in_smem(pick_summarize(i & 4, i & 2, i & 1), smem_bytes_summarize(i & 4)));
     for (int i = 0; i < 16; ++i) CK(opt_in_smem(pick_resolve(i & 8, i & 4, i & 2, i & 1), smem_bytes()));
     return BSQ_OK;
 }
@@ -226,8 +234,9 @@ bsq_status summarize_window(bsq_parser* p, Window& w, bool sums, bool hand_off =
     }
     // with the hand-off, a validating pass also screens every tile for HI / BAD bytes (k_resolve skips clean tiles)
     const bool hi = hand_off && p->cfg.check_ascii, bad = hand_off && p->cfg.check_quality;
-    pick_summarize(sums, hi, bad)<<<w.wp.n_runs, kThreads, smem_bytes_summarize(), p->stream>>>(
-        w.wp, p->run_sum.as<BsqSummary>(), (uint32_t)p->cfg.q_lower, (uint32_t)p->cfg.q_upper);
+    pick_summarize(sums, hi, bad)<<<w.wp.n_runs, kThreads, smem_bytes_summarize(sums), p->stream>>>(
+        w.wp, p->run_sum.as<BsqSummary>(), (uint32_t)p->cfg.q_lower,
+        (uint32_t)p->cfg.q_upper - (p->cfg.compat_q5_width > 0 ? 1u : 0u));   // (compat: UPPER itself is suspicious)
     k_scan_runs<<<1, kScanThreads, 0, p->stream>>>(p->run_sum.as<BsqSummary>(), w.wp.n_runs, w.wp.begin,
                                           w.run_pre.as<BsqPrefix>(), p->scan_out.as<ScanOut>());
     p->n_launches += 2;
@@ -376,12 +385,16 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     memset(&p->res, 0, sizeof p->res);
     bsq_pass_result& R = p->res;
     const int32_t m = cfg.batch_size;
-    const size_t smem_res = smem_bytes(cfg.check_ascii || cfg.check_quality);
+    const size_t smem_res = smem_bytes(want_pack, cfg.check_ascii || cfg.check_quality);
     // k_summarize hands every tile's ordered newline list (and, when validating, its HI / BAD screen) to k_resolve
     const bool list_hand_off = true;
     CK(cudaEventRecord(p->ev[0], p->stream));
 
     bool id_fast = cfg.force_id_slow_path == 0;   // optimistic: k_resolve raises the strip flag when an id needs stripping
+    // the reference holds one record in a buffer of buffer_capacity bytes (growing up to buffer_max_capacity when
+    // growth is enabled): a longer record ends the parse with BUFFER_EXCEEDED / BUFFER_AT_MAX (parser.mojo:484-503)
+    const int64_t rec_limit = std::max<int64_t>(1, cfg.buffer_growth_enabled ? cfg.buffer_max_capacity : cfg.buffer_capacity);
+    const int limit_code = cfg.buffer_growth_enabled ? BSQ_BUFFER_AT_MAX : BSQ_BUFFER_EXCEEDED;
 
     // error word, arenas and tables for `rec` records (+1) and the given byte counts
     auto prepare_outputs = [&](int64_t rec, int64_t seq_bytes, int64_t qual_bytes, int64_t id_bytes) -> bsq_status {
@@ -423,6 +436,8 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         P.id_cap = (int64_t)p->id_out.cap;
         P.batch_size = m;
         P.lower = cfg.q_lower; P.upper = cfg.q_upper;
+        P.rec_limit = (uint32_t)std::min<int64_t>(rec_limit, 0xFFFFFFFFll);
+        P.q5_width = cfg.compat_q5_width > 0 ? (uint32_t)cfg.compat_q5_width : 0u;
         P.err = p->err_word.as<unsigned long long>();
         return P;
     };
@@ -469,7 +484,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     Window* lw = nw ? &p->win[nw - 1] : nullptr;
     // SURVEY App. A Q2 (parser.mojo:484-492): the stream's first record is incomplete and the
     // buffer may not grow -> BUFFER_EXCEEDED, whatever the tail looks like
-    bool q2 = false;
+    bool q2 = false, tail_too_long = false;
     // ids: the scanned prefix counts an empty header line as -1; such a line is a structure error,
     // so only records after the first error are affected -- but the arena must still hold them
     int64_t id_room = 64;
@@ -484,7 +499,9 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         q2 = is_last && consumed_total < n && first_record + nrec == 0 && stream_offset == 0 && !cfg.buffer_growth_enabled;
         // (the position sums exist only in pack passes; a wrapped id total means an empty header
         //  line earlier in the window, i.e. an error before the tail -- nothing to append then)
-        have_tail_candidate = is_last && !oversize && !q2 && consumed_total < n && rem == 3u &&
+        // an unterminated last record (or fragment) that would not fit the reference's buffer either
+        tail_too_long = is_last && !oversize && !q2 && consumed_total < n && (int64_t)(n - consumed_total) > rec_limit;
+        have_tail_candidate = is_last && !oversize && !q2 && !tail_too_long && consumed_total < n && rem == 3u &&
                               (!want_pack || (int64_t)lw->scan.totals.id_bytes_unstripped <= (int64_t)lw->wp.end);
     }
     uint32_t tail_seq = 0, tail_qual = 0, tail_id_max = 0;
@@ -516,27 +533,17 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->ev[2], p->stream));
     if (want_pack && id_fast) {
-        // did the optimistic id packing hold?  (CRLF input and padded ids need _strip_spaces)
+        // did the optimistic id packing hold?  (CRLF input and padded ids need _strip_spaces.)  k_resolve wrote
+        // every record's stripped id span, so only the ids are redone, by the strip pipeline below
         CK(cudaMemcpyAsync(p->hm->err, p->err_word.p, 32, cudaMemcpyDeviceToHost, p->stream));
         CK(cudaStreamSynchronize(p->stream));
-        if (p->hm->err[1] != 0) {
-            id_fast = false;   // redo with the id spans materialised; the strip pipeline packs the ids
-            CK(cudaMemsetAsync(p->err_word.p, 0xFF, 8, p->stream));
-            CK(cudaMemsetAsync(p->err_word.as<uint8_t>() + 16, 0, 8, p->stream));
-            for (size_t i = 0; i < nw; ++i) {
-                Window& w = p->win[i];
-                ResolveParams P = make_params(w);
-                kern<<<w.wp.n_runs, kThreads, smem_res, p->stream>>>(w.wp, P);
-                p->n_launches += 1;
-            }
-            CK(cudaGetLastError());
-        }
+        if (p->hm->err[1] != 0) id_fast = false;
     }
 
     if (have_tail_candidate) {
         ResolveParams P = make_params(*lw);
         T.check_ascii = cfg.check_ascii; T.check_quality = cfg.check_quality;
-        T.lower = cfg.q_lower; T.upper = cfg.q_upper;
+        T.lower = cfg.q_lower; T.upper = cfg.q_upper; T.q5_width = cfg.compat_q5_width > 0 ? (uint32_t)cfg.compat_q5_width : 0u;
         T.want_offsets = want_offs; T.want_pack = want_pack; T.id_fast = id_fast;
         T.seq_rel = lw->scan.totals.seq_bytes; T.qual_rel = lw->scan.totals.qual_bytes;
         T.id_rel = lw->scan.totals.id_bytes_unstripped;
@@ -557,7 +564,10 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     const unsigned long long key = p->hm->err[0];
     const bool have_err = key != ~0ull;
     int64_t err_rec = -1; int err_code = 0;
-    if (have_err) { err_rec = (int64_t)(key >> 8) - first_record; err_code = (int)(key & 0xFF); }
+    if (have_err) {
+        err_rec = (int64_t)(key >> 8) - first_record; err_code = (int)(key & 0xFF);
+        if (err_code == 0) err_code = limit_code;   // reported with the lowest code so that it precedes the record's other errors
+    }
     int64_t arena_final = nrec + (tail_emitted ? 1 : 0);
     if (have_err && err_rec < arena_final) {
         good = err_rec;
@@ -583,7 +593,8 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
             WT.n = (int32_t)nw;
             for (size_t i = 0; i < nw; ++i) { WT.base[i] = p->win[i].base; WT.rec_base[i] = p->win[i].rec_base; }
             WT.rec_base[nw] = arena_final;
-            k_id_copy<<<grid, 256, 0, p->stream>>>(WT, p->id_spans.as<uint32_t>(), p->id_ends.as<int64_t>(),
+            const int grid_rec = (int)std::max<int64_t>(1, std::min<int64_t>((arena_final + 255) / 256, 1 << 20));
+            k_id_copy<<<grid_rec, 256, 0, p->stream>>>(WT, p->id_spans.as<uint32_t>(), p->id_ends.as<int64_t>(),
                                                    p->id_out.as<uint8_t>(), arena_final);
             p->n_launches += 5;
         }
@@ -608,6 +619,13 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
     p->total_qual = nqual + (tail_emitted ? tail_qual : 0);
 
     // ---- the stop reason, with the reference's context and text -------------------------------
+    char limit_text[200];
+    if (cfg.buffer_growth_enabled)
+        snprintf(limit_text, sizeof limit_text, "FASTQ record exceeds maximum buffer capacity (%lld bytes). Enable buffer growth or increase max_capacity.",
+                 (long long)cfg.buffer_max_capacity);
+    else
+        snprintf(limit_text, sizeof limit_text, "FASTQ record exceeds buffer capacity (%lld bytes). Enable buffer growth or increase buffer_capacity.",
+                 (long long)cfg.buffer_capacity);
     R.n_newlines = nnl;
     R.n_windows = (int32_t)nw;
     R.id_slow_path = id_fast ? 0 : 1;
@@ -631,7 +649,7 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
                 CK(scratch.ensure(8));
                 CK(cudaMemset(scratch.p, 0xFF, 8));
                 P.err = scratch.as<unsigned long long>();
-                k_resolve<false, false, true, false><<<w.wp.n_runs, kThreads, smem_bytes(false), p->stream>>>(w.wp, P);
+                k_resolve<false, false, true, false><<<w.wp.n_runs, kThreads, smem_bytes(false, false), p->stream>>>(w.wp, P);
                 p->n_launches += 1;
                 CK(cudaStreamSynchronize(p->stream));
                 scratch.release();
@@ -646,7 +664,9 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         stop.code = err_code;
         Msg msg{stop.message, sizeof stop.message, 0};
         msg.str(code_message(err_code));
-        if (err_code <= 3) {
+        if (err_code == BSQ_BUFFER_EXCEEDED || err_code == BSQ_BUFFER_AT_MAX) {
+            set_plain_error(&stop, err_code, limit_text);   // parser.mojo:299-309: no context
+        } else if (err_code <= 3) {
             // ParseError: parser.mojo:332-338 + errors.mojo:178-192
             stop.record_number = gidx + 1; stop.line_number = 4 * gidx + 1; stop.file_position = win_stream_base + o[0];
             std::vector<uint8_t> sn;
@@ -682,6 +702,8 @@ bsq_status run_pass(bsq_parser* p, const uint8_t* d, uint64_t n, int64_t stream_
         snprintf(t, sizeof t, "FASTQ record exceeds maximum buffer capacity (%lld bytes). Enable buffer growth or increase max_capacity.",
                  (long long)kWindowMax);
         set_plain_error(&stop, BSQ_BUFFER_AT_MAX, t);
+    } else if (tail_too_long) {
+        set_plain_error(&stop, limit_code, limit_text);
     } else if (!is_last) {
         stop.code = BSQ_OK;  // more input needed; the caller re-presents the unconsumed tail
     } else if (tail_emitted) {
@@ -822,6 +844,7 @@ struct bsq_stream {
     const uint8_t* region_ptr = nullptr;
     uint64_t region_n = 0;
     std::vector<uint8_t> carry;      // unconsumed tail of the previous region
+    std::vector<uint8_t> big;        // a region whose carry did not fit in front of the pinned buffer
     int64_t stream_pos = 0;          // stream offset of carry[0]
     int64_t records_done = 0;
     bool finished = false;
@@ -1025,7 +1048,9 @@ extern "C" bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t s
     }
     if (!s->gz && !s->fp && !s->zfp) { p->last_error = std::string("cannot open ") + path; delete s; return BSQ_E_ARG; }
     s->region_bytes = region_bytes ? region_bytes : (256ull << 20);
-    s->carry_cap = std::max<uint64_t>(std::min<uint64_t>(s->region_bytes, 64ull << 20), 4096);
+    // room in front of every pinned region for the previous region's unconsumed tail (a larger tail takes the
+    // `big` path of bsq_stream_next)
+    s->carry_cap = std::max<uint64_t>(std::min<uint64_t>(s->region_bytes / 4, 64ull << 20), 4096);
     for (auto& b : s->buf) {
         cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&b.mem), s->carry_cap + s->region_bytes + 64, cudaHostAllocDefault);
         if (e != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, e, "cudaHostAlloc(stream region)"); }
@@ -1076,15 +1101,20 @@ extern "C" bsq_status bsq_stream_next(bsq_stream* s, uint32_t want, bsq_pass_res
     }
     const auto t1 = std::chrono::steady_clock::now();
     s->st.wait_reader_s += std::chrono::duration<double>(t1 - t0).count();
-    if (s->read_error) { p->last_error = "read / inflate error"; s->finished = true; return BSQ_E_ARG; }
-    if (s->carry.size() > s->carry_cap) {
-        s->finished = true;
-        memset(out, 0, sizeof *out);
-        set_plain_error(&out->stop, BSQ_BUFFER_AT_MAX, "FASTQ record exceeds maximum buffer capacity");
-        return BSQ_OK;
+    if (s->read_error) { p->last_error = "read / inflate error"; s->finished = true; return BSQ_E_IO; }
+    uint8_t* region;
+    if (s->carry.size() <= s->carry_cap) {
+        region = b->mem + s->carry_cap - s->carry.size();
+        if (!s->carry.empty()) memcpy(region, s->carry.data(), s->carry.size());
+    } else {
+        // the carry (a partial record plus, for batches, the records of a trailing partial batch: ~ batch_size x
+        // record length, e.g. 4096 long reads) outgrew the area in front of the pinned region: this region is
+        // assembled in a separate buffer.  A record that fits nowhere is reported by the pass itself.
+        s->big.resize(s->carry.size() + b->n_new);
+        memcpy(s->big.data(), s->carry.data(), s->carry.size());
+        memcpy(s->big.data() + s->carry.size(), b->mem + s->carry_cap, b->n_new);
+        region = s->big.data();
     }
-    uint8_t* region = b->mem + s->carry_cap - s->carry.size();
-    if (!s->carry.empty()) memcpy(region, s->carry.data(), s->carry.size());
     const uint64_t n = s->carry.size() + b->n_new;
     const bool is_last = b->eof;
     const uint32_t m = (uint32_t)p->cfg.batch_size;
@@ -1092,14 +1122,18 @@ extern "C" bsq_status bsq_stream_next(bsq_stream* s, uint32_t want, bsq_pass_res
     if (!is_last && (want & BSQ_WANT_BATCHES)) w |= BSQ_WANT_OFFSETS;   // the cut between regions needs offsets
     bsq_status rc = bsq_parse_host(p, region, n, s->stream_pos, s->records_done, is_last ? 1 : 0, w, out);
     if (rc != BSQ_OK) { s->finished = true; return rc; }
-    if (!is_last && out->stop.code == BSQ_OK && (want & BSQ_WANT_BATCHES) && out->n_records % m != 0 && out->n_records >= m) {
-        // keep batches whole across regions: the trailing partial batch is re-presented with the next region
+    if (!is_last && out->stop.code == BSQ_OK && (want & BSQ_WANT_BATCHES) && out->n_records % m != 0) {
+        // keep batches whole across regions: the trailing partial batch (all of the region's records when it holds
+        // fewer than one batch) is re-presented with the next region
         const int64_t keep = out->n_records - out->n_records % m;
-        int wi = 0;
-        while (wi + 1 < p->res.n_windows && keep >= p->win[wi + 1].rec_base) ++wi;
-        uint32_t le = 0;
-        CK(cudaMemcpy(&le, p->win[wi].line_ends.as<uint32_t>() + 4ull * (keep - p->win[wi].rec_base), 4, cudaMemcpyDeviceToHost));
-        const int64_t cut = (int64_t)p->win[wi].region_off - (int64_t)p->win[wi].wp.begin + (int64_t)(le + 1u);
+        int64_t cut = 0;
+        if (keep > 0) {
+            int wi = 0;
+            while (wi + 1 < p->res.n_windows && keep >= p->win[wi + 1].rec_base) ++wi;
+            uint32_t le = 0;
+            CK(cudaMemcpy(&le, p->win[wi].line_ends.as<uint32_t>() + 4ull * (keep - p->win[wi].rec_base), 4, cudaMemcpyDeviceToHost));
+            cut = (int64_t)p->win[wi].region_off - (int64_t)p->win[wi].wp.begin + (int64_t)(le + 1u);
+        }
         out->n_records = keep;
         out->n_batches = keep / m;
         out->bytes_consumed = cut;
@@ -1179,8 +1213,11 @@ static bsq_status fill_batch(const bsq_parser* p, int64_t first, int64_t count, 
     } else {
         // a batch cut short by an error: read the cumulative values of its last record
         int64_t v[2];
-        cudaMemcpy(&v[0], p->ends.as<int64_t>() + (last - 1), 8, cudaMemcpyDeviceToHost);
-        cudaMemcpy(&v[1], p->id_ends.as<int64_t>() + (last - 1), 8, cudaMemcpyDeviceToHost);
+        if (cudaMemcpy(&v[0], p->ends.as<int64_t>() + (last - 1), 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(&v[1], p->id_ends.as<int64_t>() + (last - 1), 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            cudaGetLastError();
+            return BSQ_E_CUDA;
+        }
         q_end = qb + v[0]; i_end = ib + v[1];
     }
     out->seq_len = q_end - qb;
@@ -1234,6 +1271,24 @@ extern "C" bsq_status bsq_batch_to_host(bsq_parser* p, int64_t b, uint8_t* seq, 
     if (id) CK(cudaMemcpyAsync(id, v.id_buffer, v.total_id_bytes, cudaMemcpyDeviceToHost, p->stream));
     if (ends) CK(cudaMemcpyAsync(ends, v.ends, 8 * v.num_records, cudaMemcpyDeviceToHost, p->stream));
     if (id_ends) CK(cudaMemcpyAsync(id_ends, v.id_ends, 8 * v.num_records, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return BSQ_OK;
+}
+
+extern "C" bsq_status bsq_soa_to_host(bsq_parser* p, uint8_t* seq, uint8_t* qual, uint8_t* id, int64_t* ends,
+                                      int64_t* id_ends) {
+    bsq_batch_view v;
+    bsq_status st = bsq_get_soa(p, &v);
+    if (st != BSQ_OK) return st;
+    if (v.num_records == 0) return BSQ_OK;
+    CK(cudaSetDevice(p->cfg.device_id));
+    // two copy queues so that the big arrays travel back to back on the D2H engine
+    if (seq) CK(cudaMemcpyAsync(seq, v.sequence_buffer, v.sequence_bytes, cudaMemcpyDeviceToHost, p->copy_stream));
+    if (qual) CK(cudaMemcpyAsync(qual, v.qual_buffer, v.seq_len, cudaMemcpyDeviceToHost, p->copy_stream));
+    if (id) CK(cudaMemcpyAsync(id, v.id_buffer, v.total_id_bytes, cudaMemcpyDeviceToHost, p->stream));
+    if (ends) CK(cudaMemcpyAsync(ends, v.ends, 8 * v.num_records, cudaMemcpyDeviceToHost, p->stream));
+    if (id_ends) CK(cudaMemcpyAsync(id_ends, v.id_ends, 8 * v.num_records, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->copy_stream));
     CK(cudaStreamSynchronize(p->stream));
     return BSQ_OK;
 }
@@ -1367,7 +1422,7 @@ extern "C" bsq_status bsq_summarize_device(bsq_parser* p, const uint8_t* dev_byt
     Window w;
     while (pos < n) {
         const uint64_t bytes = std::min<uint64_t>(n - pos, kWindowMax);
-        plan_window(p, w, dev_bytes + pos, bytes, false);
+        plan_window(p, w, dev_bytes + pos, bytes, true);
         bsq_status st = summarize_window(p, w, true);
         if (st != BSQ_OK) { w.run_pre.release(); return st; }
         BsqSummary s = w.scan.region;

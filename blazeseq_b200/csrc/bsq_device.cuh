@@ -36,8 +36,11 @@ constexpr int kWarps = kThreads / 32;
 #ifndef BSQ_STAGES
 #define BSQ_STAGES 1
 #endif
+#ifndef BSQ_COPY_STAGED
+#define BSQ_COPY_STAGED 1
+#endif
 #ifndef BSQ_RESOLVE_CTAS
-#define BSQ_RESOLVE_CTAS 6
+#define BSQ_RESOLVE_CTAS (BSQ_COPY_STAGED ? 5 : 6)
 #endif
 constexpr int kStages = BSQ_STAGES;       // TMA ring depth per CTA
 constexpr int kResolveCtas = BSQ_RESOLVE_CTAS;  // resident CTAs per SM, k_resolve (shared memory + registers)
@@ -45,10 +48,14 @@ constexpr int kResolveCtas = BSQ_RESOLVE_CTAS;  // resident CTAs per SM, k_resol
 #define BSQ_VIEW_CTAS 6
 #endif
 constexpr int kViewCtas = BSQ_VIEW_CTAS;  // ... of the instantiations that do not pack (no stage buffer)
-#ifndef BSQ_SUMMARIZE_CTAS
-#define BSQ_SUMMARIZE_CTAS (768 / BSQ_THREADS)
-#endif
-constexpr int kSummarizeCtas = BSQ_SUMMARIZE_CTAS;  // resident CTAs per SM, k_summarize
+// k_summarize comes in two shapes, chosen so that a window's runs (a CTA's static share) fill whole waves:
+//   packing passes (kSums): runs per SM = 2 x kResolveCtas = 10 -> one tile buffer (the next tile waits in L2),
+//                           10 CTAs / SM: ONE wave
+//   the others:             runs per SM = 2 x kViewCtas = 12    -> two tile buffers, 6 CTAs / SM: two waves
+template <bool kSums> struct SumShape {
+    static constexpr int kStagesOf = kSums ? 1 : 2;
+    static constexpr int kCtas = kSums ? 2 * BSQ_RESOLVE_CTAS : BSQ_VIEW_CTAS;
+};
 // runs per SM and window: a whole number of waves for the kernel that dominates the pass (a run is a
 // CTA's static share, so a partial last wave costs a full one): packing passes follow k_resolve (pack),
 // the others k_summarize / k_resolve (views)
@@ -68,6 +75,16 @@ constexpr int kLinesCap = kNlCap / 4 + 3; // lines of one class per pass (+ two 
 constexpr int kTilePad = 32;              // readable slack after a tile for unaligned 16-byte loads
 constexpr int kHalo = 1024;               // bytes before the tile kept in shared memory too: a line that began
                                           // up to kHalo bytes before the tile is still read from shared memory
+// SoA copy of k_resolve: 1 = per-line copy into a shared-memory stage laid out like the destination, written
+// back with TMA bulk stores; 0 = destination-ordered direct copy to global memory (no stage buffer)
+constexpr bool kCopyStaged = BSQ_COPY_STAGED != 0;
+#ifndef BSQ_ROT
+#define BSQ_ROT 1          // staged copy: lanes whose lines start in the same bank start at different words
+#endif
+#ifndef BSQ_INTERLEAVE
+#define BSQ_INTERLEAVE 1   // staged copy: sequence and quality lines alternate over the lanes
+#endif
+constexpr int kStage = kHalo + kTile + 128;  // SoA staging: the lines that END in a tile lie in [halo | tile]; + 3 x 32 alignment slack
 constexpr int kMaxWindows = 64;
 
 static_assert(kThreads % 4 == 0 && (kWordsPerThread == 4 || kWordsPerThread == 2) && kChunksPerThread * kThreads == kChunks, "");
@@ -115,6 +132,9 @@ struct ResolveParams {
     int64_t id_cap;              // bytes allocated for id_out
     int32_t batch_size;
     uint32_t lower, upper;       // quality bounds
+    uint32_t rec_limit;          // a record longer than this many bytes does not fit the reference's buffer
+                                 // (buffer_capacity, or buffer_max_capacity with growth): parser.mojo:484-503
+    uint32_t q5_width;           // 0, or the SIMD width W of record.mojo:90-102 to reproduce (see kQual walk)
     unsigned long long* err;     // min over ((global record << 8) | code)
 };
 
@@ -197,17 +217,27 @@ struct alignas(128) TileSmem {
     uint32_t ssrc[3][kLinesCap];              //                   source position of each line
     alignas(16) uint16_t nl16[kStages][kNlCap];   // the tile's newline list from k_summarize (TMA destination)
     uint32_t tile_total[kStages + 1];         // newline count words of the tiles in flight (ring, written one tile ahead)
+#if BSQ_COPY_STAGED
+    // SoA bytes of the pass, laid out like the destination (mod 16): [id | seq | qual], written back with TMA
+    // bulk stores.  The HI / BAD validation bitmaps live at its start: they are consumed before the SoA bytes
+    // of the tile are staged.  (Passes that do not pack allocate only the bitmaps.)
+    alignas(128) uint8_t stage[kStage];
+    __device__ __forceinline__ uint32_t* bm_hi_p() { return reinterpret_cast<uint32_t*>(stage); }            // 1 bit per byte: bit 7 set
+    __device__ __forceinline__ uint32_t* bm_bad_p() { return reinterpret_cast<uint32_t*>(stage) + kWords; }  // outside [lower, upper]
+#else
     // ---- validating instantiations only (the allocation ends here otherwise) ----
     alignas(16) uint32_t bm_hi[kWords];       // 1 bit per byte: bit 7 set
     uint32_t bm_bad[kWords];                  // 1 bit per byte: outside [lower, upper]
     __device__ __forceinline__ uint32_t* bm_hi_p() { return bm_hi; }
     __device__ __forceinline__ uint32_t* bm_bad_p() { return bm_bad; }
+#endif
 };
+static_assert(2 * kWords * 4 <= kStage, "the validation bitmaps fit the stage buffer");
 
 // k_summarize: the same front end on its own (double-buffered) ring
-constexpr int kSumStages = 2;
 static_assert(kNlCap * 2 <= kHalo, "k_summarize keeps the newline list in an unused halo");
-struct alignas(128) SumSmem {
+template <int kSumStages>
+struct alignas(128) SumSmemT {
     alignas(128) uint8_t data[kSumStages][kHalo + kTile + kTilePad];
     alignas(8) uint64_t full_bar[kSumStages];
     uint32_t warp_tot[2][kWarps][4];
@@ -269,8 +299,8 @@ __device__ __forceinline__ uint32_t mask16(uint32_t f0, uint32_t f1, uint32_t f2
     return m;
 }
 
-template <bool kHi, bool kBad, typename SM>
-__device__ __forceinline__ void build_bitmaps(SM& S, const TileCursor& c, uint32_t addlo, uint32_t addup) {
+template <bool kHi, bool kBad, bool kEdge, typename SM>
+__device__ __forceinline__ void build_bitmaps_t(SM& S, const TileCursor& c, uint32_t addlo, uint32_t addup) {
     const uint8_t* tile = S.data[c.stage] + kHalo;
     const uint32_t tid = threadIdx.x;
     const uint32_t vlo = c.lo - c.origin, vhi = c.hi - c.origin;  // valid offsets in the tile
@@ -279,14 +309,14 @@ __device__ __forceinline__ void build_bitmaps(SM& S, const TileCursor& c, uint32
         const uint32_t chunk = j * kThreads + tid;
         const uint32_t off = chunk * 16u;
         uint32_t m_nl = 0, m_hi = 0, m_bad = 0;
-        if (off < vhi && off + 16u > vlo) {  // warp-uniform except at the two edges of the stream
+        if (!kEdge || (off < vhi && off + 16u > vlo)) {
             const uint4 v = *reinterpret_cast<const uint4*>(tile + off);
             m_nl = mask16(bsq_nl_flags(v.x), bsq_nl_flags(v.y), bsq_nl_flags(v.z), bsq_nl_flags(v.w));
             if (kHi) m_hi = mask16(bsq_hi_flags(v.x), bsq_hi_flags(v.y), bsq_hi_flags(v.z), bsq_hi_flags(v.w));
             if (kBad)
                 m_bad = mask16(bsq_badq_flags(v.x, addlo, addup), bsq_badq_flags(v.y, addlo, addup),
                                bsq_badq_flags(v.z, addlo, addup), bsq_badq_flags(v.w, addlo, addup));
-            if (off < vlo || off + 16u > vhi) {
+            if (kEdge && (off < vlo || off + 16u > vhi)) {
                 uint32_t keep = 0xFFFFu;
                 if (off < vlo) keep &= 0xFFFFu << (vlo - off);
                 if (off + 16u > vhi) keep &= 0xFFFFu >> (off + 16u - vhi);
@@ -306,13 +336,19 @@ __device__ __forceinline__ void build_bitmaps(SM& S, const TileCursor& c, uint32
         }
     }
 }
+// (only the first and the last tile of a window have bytes outside [begin, end): the others skip the edge tests)
+template <bool kHi, bool kBad, typename SM>
+__device__ __forceinline__ void build_bitmaps(SM& S, const TileCursor& c, uint32_t addlo, uint32_t addup) {
+    if (c.lo == c.origin && c.hi == c.origin + (uint32_t)kTile) build_bitmaps_t<kHi, kBad, false>(S, c, addlo, addup);
+    else build_bitmaps_t<kHi, kBad, true>(S, c, addlo, addup);
+}
 
 // k_summarize with validation configured: the newline bitmap as above, plus a SCREEN of the tile for the two
 // validators -- does any byte have bit 7 set / does any non-newline byte lie outside [lower, upper]?  Returns
 // bit 0 / bit 1 for this thread's chunks.  No gathers and no bitmap stores: a clean tile (the normal case)
 // lets k_resolve skip the validation bitmaps and the per-byte walk; a flagged tile is examined there exactly.
-template <bool kHi, bool kBad, typename SM>
-__device__ __forceinline__ uint32_t build_nl_bitmap_and_screen(SM& S, const TileCursor& c, uint32_t addlo, uint32_t addup) {
+template <bool kHi, bool kBad, bool kEdge, typename SM>
+__device__ __forceinline__ uint32_t build_nl_bitmap_and_screen_t(SM& S, const TileCursor& c, uint32_t addlo, uint32_t addup) {
     const uint8_t* tile = S.data[c.stage] + kHalo;
     const uint32_t tid = threadIdx.x;
     const uint32_t vlo = c.lo - c.origin, vhi = c.hi - c.origin;  // valid offsets in the tile
@@ -322,7 +358,7 @@ __device__ __forceinline__ uint32_t build_nl_bitmap_and_screen(SM& S, const Tile
         const uint32_t chunk = j * kThreads + tid;
         const uint32_t off = chunk * 16u;
         uint32_t m_nl = 0;
-        if (off < vhi && off + 16u > vlo) {
+        if (!kEdge || (off < vhi && off + 16u > vlo)) {
             const uint4 v = *reinterpret_cast<const uint4*>(tile + off);
             const uint32_t f0 = bsq_nl_flags(v.x), f1 = bsq_nl_flags(v.y), f2 = bsq_nl_flags(v.z), f3 = bsq_nl_flags(v.w);
             m_nl = mask16(f0, f1, f2, f3);
@@ -330,7 +366,7 @@ __device__ __forceinline__ uint32_t build_nl_bitmap_and_screen(SM& S, const Tile
             if (kBad)
                 any_bad |= (bsq_badq_flags(v.x, addlo, addup) & ~f0) | (bsq_badq_flags(v.y, addlo, addup) & ~f1) |
                            (bsq_badq_flags(v.z, addlo, addup) & ~f2) | (bsq_badq_flags(v.w, addlo, addup) & ~f3);
-            if (off < vlo || off + 16u > vhi) {
+            if (kEdge && (off < vlo || off + 16u > vhi)) {
                 uint32_t keep = 0xFFFFu;
                 if (off < vlo) keep &= 0xFFFFu << (vlo - off);
                 if (off + 16u > vhi) keep &= 0xFFFFu >> (off + 16u - vhi);
@@ -342,6 +378,11 @@ __device__ __forceinline__ uint32_t build_nl_bitmap_and_screen(SM& S, const Tile
     }
     // (bytes outside the window in the two edge tiles are not masked here: the caller flags those tiles)
     return (any_hi != 0u ? 1u : 0u) | (any_bad != 0u ? 2u : 0u);
+}
+template <bool kHi, bool kBad, typename SM>
+__device__ __forceinline__ uint32_t build_nl_bitmap_and_screen(SM& S, const TileCursor& c, uint32_t addlo, uint32_t addup) {
+    if (c.lo == c.origin && c.hi == c.origin + (uint32_t)kTile) return build_nl_bitmap_and_screen_t<kHi, kBad, false>(S, c, addlo, addup);
+    return build_nl_bitmap_and_screen_t<kHi, kBad, true>(S, c, addlo, addup);
 }
 
 // Exclusive prefix of `v` over the block (in thread order) and the block total.  One barrier:
@@ -516,9 +557,11 @@ __device__ __forceinline__ TileCursor make_cursor(const WinParams& W, uint32_t t
 // Shared memory: SumSmem.
 constexpr uint32_t kNlCountMask = 0x0FFFFFFFu;   // nl_count word: newlines | validation screen << 30
 template <bool kSums, bool kHi, bool kBad>
-__global__ void __launch_bounds__(kThreads, kSummarizeCtas) k_summarize(const WinParams W, BsqSummary* __restrict__ run_sum,
+__global__ void __launch_bounds__(kThreads, SumShape<kSums>::kCtas) k_summarize(const WinParams W, BsqSummary* __restrict__ run_sum,
                                                                         uint32_t lower, uint32_t upper) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    constexpr int kSumStages = SumShape<kSums>::kStagesOf;
+    using SumSmem = SumSmemT<kSumStages>;
     SumSmem& S = *reinterpret_cast<SumSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x;
     uint32_t ta, tb;
@@ -543,6 +586,7 @@ __global__ void __launch_bounds__(kThreads, kSummarizeCtas) k_summarize(const Wi
         const uint32_t it = t - ta;
         const TileCursor c = make_cursor(W, t, it % kSumStages);
         mbar_wait(&S.full_bar[c.stage], (it / kSumStages) & 1u);
+        if (kSumStages == 1 && tid == 0 && t + 1u < tb) prefetch_l2(W.base + (size_t)(t + 1u) * kTile, tile_bytes_rounded(W, t + 1u));
         if (kHi || kBad) {
             uint32_t d = build_nl_bitmap_and_screen<kHi, kBad>(S, c, addlo, addup);
             d = __reduce_or_sync(0xFFFFFFFFu, d);
@@ -563,11 +607,18 @@ __global__ void __launch_bounds__(kThreads, kSummarizeCtas) k_summarize(const Wi
                 for_each_newline(words, tid * kBytesPerThread, excl, [&](uint32_t r, uint32_t p) { list[r] = (uint16_t)p; });
             __syncthreads();
             if (kSums) {
-                uint32_t a = 0;                        // index in the run = run_count + j: one class per thread
-                for (uint32_t j = tid; j < total; j += kThreads) a += c.origin + (uint32_t)list[j];
-                const uint32_t cls = (run_count + tid) & 3u;
-                acc[0] += cls == 0u ? a : 0u; acc[1] += cls == 1u ? a : 0u;
-                acc[2] += cls == 2u ? a : 0u; acc[3] += cls == 3u ? a : 0u;
+                // index in the run = run_count + j: thread tid adds entries 2 tid and 2 tid + 1 (+ 2 kThreads, ...),
+                // i.e. two fixed classes; the entries past `total` of the last pair are not counted
+                const uint32_t* l2 = reinterpret_cast<const uint32_t*>(list);
+                uint32_t a0 = 0, a1 = 0;
+                for (uint32_t j = 2u * tid; j < total; j += 2u * kThreads) {
+                    const uint32_t w = l2[j >> 1];
+                    a0 += c.origin + (w & 0xFFFFu);
+                    a1 += j + 1u < total ? c.origin + (w >> 16) : 0u;
+                }
+                const uint32_t cls = (run_count + 2u * tid) & 3u;    // class of the even entry; the odd one is cls + 1
+                acc[0] += cls == 0u ? a0 : (cls == 3u ? a1 : 0u); acc[1] += cls == 1u ? a0 : (cls == 0u ? a1 : 0u);
+                acc[2] += cls == 2u ? a0 : (cls == 1u ? a1 : 0u); acc[3] += cls == 3u ? a0 : (cls == 2u ? a1 : 0u);
             }
             if (W.nl_list != nullptr) {                // coalesced copy-out, two positions per store
                 uint32_t* g = reinterpret_cast<uint32_t*>(W.nl_list + (size_t)(t - W.first_tile) * kNlCap);
@@ -966,6 +1017,102 @@ __device__ __forceinline__ void copy_small_line(const uint8_t* __restrict__ data
     for (uint32_t k = 0; k < t; ++k) out[dst + k] = data[src + k];
 }
 
+#if BSQ_COPY_STAGED
+// ------------------------------------------------------------------------------------------------
+// staged SoA copy: one thread moves one line from [halo | tile] to `stage`, which is laid out like the
+// destination modulo 16: a byte loop up to the first 4-byte boundary of the destination, then one funnel
+// shift per word (each source word is read once), then the last 0-3 bytes.  The staged range leaves
+// through TMA bulk stores, so the global writes cost no instructions and are full 16-byte vectors.
+//
+// Bank conflicts: lane i of a warp reads word (line start of lane i) + k at step k, so lines that start
+// in the same bank collide at every step -- 16 of 32 lanes when the record stride is 320 bytes.  The
+// lanes of a warp whose lines start in the same bank therefore begin at different words: lane with
+// rank r among them copies words [r, nw) first and then [0, r) downwards, which keeps the carried
+// word and costs r_max extra steps (7 at a 320-byte stride with the sequence and quality lines
+// interleaved over the lanes).  Warps whose lanes spread over enough banks skip all of this.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_line(const uint8_t* __restrict__ data, uint8_t* __restrict__ stage,
+                                           uint32_t src, uint32_t dst, uint32_t len, uint32_t lanes) {
+    uint32_t h = (0u - dst) & 3u;
+    if (h > len) h = len;
+    const uint32_t src4 = src + h;
+    // rank of this lane among the lanes of the warp whose word loop starts in the same bank
+    // how many banks do the lanes' first words occupy?  Few banks for many lanes = lanes in step on the same
+    // bank: those get distinct start words (rank among the lanes of their bank).  The common case (at most
+    // ~2 lanes per bank) takes no rotation and pays one warp reduction.
+    uint32_t rot = 0;
+#if BSQ_ROT
+    const uint32_t bank = (src4 >> 2) & 31u;
+    const uint32_t occupied = __reduce_or_sync(lanes, 1u << bank);
+    if (3u * __popc(occupied) < __popc(lanes)) {
+        const uint32_t same = __match_any_sync(lanes, bank);
+        rot = __popc(same & ((1u << (threadIdx.x & 31u)) - 1u));
+    }
+#endif
+    if (len == 0u) return;   // (the source of an empty line may lie outside [halo | tile])
+    for (uint32_t i = 0; i < h; ++i) stage[dst + i] = data[src + i];
+    src += h; dst += h; len -= h;
+    const uint32_t nw = len >> 2;
+    const uint32_t sh = (src & 3u) * 8u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(data + (src & ~3u));
+    uint32_t* dw = reinterpret_cast<uint32_t*>(stage + dst);
+    if (rot >= nw) rot = 0u;
+    const uint32_t wr = sw[rot];
+    uint32_t w0 = wr;
+    uint32_t i = rot;
+    for (; i + 4u <= nw; i += 4u) {
+        const uint32_t w1 = sw[i + 1], w2 = sw[i + 2], w3 = sw[i + 3], w4 = sw[i + 4];
+        dw[i] = __funnelshift_r(w0, w1, sh);
+        dw[i + 1] = __funnelshift_r(w1, w2, sh);
+        dw[i + 2] = __funnelshift_r(w2, w3, sh);
+        dw[i + 3] = __funnelshift_r(w3, w4, sh);
+        w0 = w4;
+    }
+    for (; i < nw; ++i) {
+        const uint32_t w1 = sw[i + 1];
+        dw[i] = __funnelshift_r(w0, w1, sh);
+        w0 = w1;
+    }
+    if (rot != 0u) {                                    // words [0, rot): the loads first (independent), then the stores
+        uint32_t hw[9];
+#pragma unroll
+        for (uint32_t k = 0; k < 9u; ++k) hw[k] = k <= rot ? sw[k] : 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; ++k)
+            if (k < rot) dw[k] = __funnelshift_r(hw[k], hw[k + 1], sh);
+        uint32_t w1 = hw[8];
+        for (uint32_t k = 8u; k < rot; ++k) {           // (more than eight lanes on one bank)
+            const uint32_t w = sw[k + 1];
+            dw[k] = __funnelshift_r(w1, w, sh);
+            w1 = w;
+        }
+    }
+    const uint32_t t = len & 3u;
+    src += nw * 4u; dst += nw * 4u;
+    for (uint32_t k = 0; k < t; ++k) stage[dst + k] = data[src + k];
+}
+
+// One stream's staged range -> global: [ra, rb) are virtual destination offsets (out + offset, out
+// 16-byte aligned), stage[so + (d - (ra & ~15))] holds destination byte d.  The 16-byte aligned
+// interior leaves as one TMA bulk store (thread `issuer`); the <= 15 bytes on either side, which
+// share their vector with a neighbouring tile, are byte stores by lanes 0..31 of warp `wsel`.
+__device__ __forceinline__ void flush_stream(const uint8_t* stage, uint32_t so, uint32_t ra, uint32_t rb, uint8_t* out,
+                                             bool issuer, bool edge_warp) {
+    if (rb <= ra) return;
+    const uint32_t A = ra & ~15u;
+    const uint32_t i0 = (ra + 15u) & ~15u, i1 = rb & ~15u;
+    if (issuer && i1 > i0) tma_store_1d(out + i0, stage + so + (i0 - A), i1 - i0);
+    if (edge_warp) {
+        const uint32_t j = threadIdx.x & 31u;
+        const uint32_t head_end = i0 < rb ? i0 : rb;                 // head = [ra, head_end)
+        const uint32_t tail_beg = i1 > head_end ? i1 : head_end;     // tail = [tail_beg, rb)
+        const uint32_t d = j < 16u ? ra + j : tail_beg + (j - 16u);
+        const bool on = j < 16u ? d < head_end : d < rb;
+        if (on) out[d] = stage[so + (d - A)];
+    }
+}
+#endif  // BSQ_COPY_STAGED
+
 // The second pass: run prefixes from k_summarize + k_scan_runs, one CTA per run.
 template <bool kAscii, bool kQual, bool kOffsets, bool kPack>
 __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_resolve(const WinParams W, const ResolveParams P) {
@@ -979,7 +1126,7 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&S.full_bar[s], 1);
         mbar_fence_init();
-        S.nlx[0] = 0; S.nlx[1] = pre.prev[2]; S.nlx[2] = pre.prev[1]; S.nlx[3] = pre.prev[0];
+        S.nlx[0] = pre.prev3; S.nlx[1] = pre.prev[2]; S.nlx[2] = pre.prev[1]; S.nlx[3] = pre.prev[0];
     }
     __syncthreads();
     // use_list: the ordered newline list of every tile comes from k_summarize (same TMA transaction as the tile),
@@ -1006,7 +1153,9 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
     }
     if (kOffsets && tid == 0 && blockIdx.x == 0) P.line_ends[0] = W.begin - 1u;
 
-    const uint32_t addlo = (128u - P.lower) * 0x01010101u, addup = (127u - P.upper) * 0x01010101u;
+    // (q5_width: k_summarize's screen counts UPPER itself as suspicious; whether it is an error is decided per record)
+    const uint32_t up_bm = P.upper - (kQual && P.q5_width != 0u ? 1u : 0u);
+    const uint32_t addlo = (128u - P.lower) * 0x01010101u, addup = (127u - up_bm) * 0x01010101u;
     uint32_t bases_acc = 0;                                              // this thread's share of sum(seq_len)
     uint32_t rank = pre.rank;                                            // rank of the tile's first newline
     uint32_t cum_id = pre.cum_id, cum_seq = pre.cum_seq, cum_qual = pre.cum_qual;  // stream destinations
@@ -1051,6 +1200,10 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
             for (uint32_t j = tid; j < total; j += kThreads) S.nlx[kHead + j] = c.origin + (uint32_t)l16[j];
             __syncthreads();
         } else {
+            if (kCopyStaged && kPack && (kAscii || kQual)) {   // the validation bitmaps reuse `stage`: the previous
+                if (tid == 0) tma_store_wait_read();           // tile's bulk stores and edge stores must be through with it
+                __syncthreads();
+            }
             build_bitmaps<kAscii, kQual>(S, c, addlo, addup);
             __syncthreads();
             words = load_nl_words(S, tid);
@@ -1065,8 +1218,8 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
 #pragma unroll
             for (int i = 0; i < kWordsPerThread; ++i) {
                 const uint32_t nl = words.w[i];
-                const uint32_t hiw = kAscii ? S.bm_hi[tid * kWordsPerThread + i] : 0u;
-                const uint32_t badw = kQual ? (S.bm_bad[tid * kWordsPerThread + i] & ~nl) : 0u;
+                const uint32_t hiw = kAscii ? S.bm_hi_p()[tid * kWordsPerThread + i] : 0u;
+                const uint32_t badw = kQual ? (S.bm_bad_p()[tid * kWordsPerThread + i] & ~nl) : 0u;
                 if ((hiw | badw) != 0u) {
                     uint32_t rest = 0xFFFFFFFFu, m = nl, rr = r;
                     while (rest) {
@@ -1076,7 +1229,7 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
                         const uint32_t cls = rr & 3u, k = rr >> 2;
                         if (k < n_complete) {
                             if (kAscii && cls != 2u && (hiw & seg)) report(P, k, 4u);
-                            if (kQual && cls == 3u && (badw & seg)) report(P, k, 5u);
+                            if (kQual && cls == 3u && (badw & seg) && P.q5_width == 0u) report(P, k, 5u);
                         }
                         rest &= ~seg;
                         ++rr;
@@ -1139,7 +1292,7 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
                             nid = z - a;
                             if (kPack && P.id_fast) *P.strip_flag = 1u;   // the optimistic id packing is void
                         }
-                        if (kOffsets || (kPack && !P.id_fast)) { P.id_spans[2u * k] = a; P.id_spans[2u * k + 1u] = nid; }
+                        if (kOffsets || kPack) { P.id_spans[2u * k] = a; P.id_spans[2u * k + 1u] = nid; }   // (pack: for the strip pipeline)
                         if (len > max_len) max_len = len;
                     }
                     l_id = nid; s_id = a;
@@ -1153,7 +1306,22 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
                 if (has3) {
                     const uint32_t q1 = e[2], len = e[3] - q1 - 1u;
                     if (live) {
+                        if (e[3] - e[-1] > P.rec_limit) report(P, k, 0u);                    // parser.mojo:484-503 (before any other check)
                         if (e[1] - e[0] - 1u != len) report(P, k, 3u);                       // utils.mojo:458-461
+                        if (kQual && P.q5_width != 0u && (!listed || q1 + 1u < c.origin)) {
+                            // record.mojo:90-102 as written: the first floor(len / W) * W quality bytes fail on
+                            // (b - LOWER) >= span, i.e. UPPER itself is rejected there; the rest on > span.
+                            // Whether a byte == UPPER counts depends on its offset in the line, so in this mode the
+                            // lines of a tile that k_summarize flagged (UPPER counts as suspicious there), and the
+                            // lines that began in an earlier tile, are re-examined byte by byte (cold path)
+                            const uint32_t body = len - len % P.q5_width;
+                            bool bad = false;
+                            for (uint32_t x = 0; x < len; ++x) {
+                                const uint32_t b = byte_at(S, c, W, q1 + 1u + x);
+                                bad = bad || b < P.lower || b > P.upper || (x < body && b == P.upper);
+                            }
+                            if (bad) report(P, k, 5u);
+                        }
                         l_qual = len;
                         if (len > max_len) max_len = len;
                     }
@@ -1198,6 +1366,7 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
                     S.sdst[tid][nn] = dd; S.sdst[tid][nn + 1] = dd; S.sdst[tid][nn + 2] = dd;
                     S.ssrc[tid][nn] = c.origin + 16u; S.ssrc[tid][nn + 1] = c.origin + 16u;
                 }
+                if (kCopyStaged && tid == 0) tma_store_wait_read();   // the previous pass's bulk stores have read `stage`
                 // one barrier: the line tables are complete, every reader of the newline list is done;
                 // long lines (long reads, or a line that began far before the tile) are copied
                 // vector-parallel from wherever they lie, otherwise straight from [halo | tile]
@@ -1210,6 +1379,7 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
                 const uint32_t ra_seq = d0_seq + sh_seq, rb_seq = cum_seq + sh_seq;
                 const uint32_t ra_qual = d0_qual + sh_qual, rb_qual = cum_qual + sh_qual;
                 const bool ok_seq = rb_seq > ra_seq, ok_qual = rb_qual > ra_qual;
+                const uint32_t n1 = ok_seq ? n_seq : 0u, n2 = ok_qual ? n_qual : 0u, n0 = do_id ? n_id : 0u;
                 if (long_lines) {
                     StreamJob jobs[3];
                     jobs[0] = StreamJob{S.sdst[0], S.ssrc[0], n_id, ra_id, do_id ? rb_id : ra_id, out_id};
@@ -1218,15 +1388,51 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
 #pragma unroll
                     for (int st = 0; st < 3; ++st)
                         if (jobs[st].d1 > jobs[st].d0) copy_stream(S, c, W, jobs[st]);
+                    __syncthreads();   // the tile's bytes and the line tables are free again
                 } else {
                     const uint8_t* const data = S.data[c.stage];
                     const uint32_t sbias = (uint32_t)kHalo - c.origin;          // window offset -> offset in data[stage]
+#if BSQ_COPY_STAGED
+                    // stage layout: [id | seq | qual], each region starts at the 16-byte vector of its
+                    // first destination byte; lengths are bounded by the bytes of [halo | tile]
+                    const uint32_t A_id = ra_id & ~15u, A_seq = ra_seq & ~15u, A_qual = ra_qual & ~15u;
+                    const uint32_t so_id = 0u;
+                    const uint32_t so_seq = do_id ? ((rb_id - A_id + 15u) & ~15u) : 0u;
+                    const uint32_t so_qual = so_seq + (ok_seq ? ((rb_seq - A_seq + 15u) & ~15u) : 0u);
+                    // items, one line per thread: sequence and quality lines alternate over the lanes (their
+                    // sources start in different banks), then the ids
+                    // (only when the distance between consecutive sequence lines is a multiple of 16 bytes, the strides
+                    //  whose word loops run in step on few banks: a uniform test on the line table)
+                    const bool in_step = BSQ_INTERLEAVE && n1 > 2u && ((S.ssrc[1][1] - S.ssrc[1][0]) & 15u) == 0u &&
+                                         ((S.ssrc[1][2] - S.ssrc[1][1]) & 15u) == 0u;
+                    const uint32_t npair = in_step ? 2u * (n1 < n2 ? n1 : n2) : 0u, nitem = n1 + n2 + n0;
+                    for (uint32_t w0 = 0; w0 < nitem; w0 += kThreads) {
+                        const uint32_t w = w0 + tid;
+                        const uint32_t lanes = __ballot_sync(0xFFFFFFFFu, w < nitem);
+                        if (w < nitem) {
+                            uint32_t st, i, so, A;
+                            if (w < npair) { st = 1u + (w & 1u); i = w >> 1; }
+                            else if (!in_step && w < n1 + n2) { st = w < n1 ? 1u : 2u; i = w < n1 ? w : w - n1; }
+                            else if (w < n1 + n2) { st = n1 > n2 ? 1u : 2u; i = w - (npair >> 1); }
+                            else { st = 0u; i = w - n1 - n2; }
+                            if (st == 1u) { so = so_seq; A = A_seq; } else if (st == 2u) { so = so_qual; A = A_qual; } else { so = so_id; A = A_id; }
+                            const uint32_t d = S.sdst[st][i];
+                            stage_line(data, S.stage, S.ssrc[st][i] + sbias, so + (d - A), S.sdst[st][i + 1] - d, lanes);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    __syncthreads();
+                    const uint32_t wsel = tid >> 5;
+                    if (do_id) flush_stream(S.stage, so_id, ra_id, rb_id, out_id, tid == 0, wsel == 0u);
+                    if (ok_seq) flush_stream(S.stage, so_seq, ra_seq, rb_seq, out_seq, tid == 0, wsel == 1u);
+                    if (ok_qual) flush_stream(S.stage, so_qual, ra_qual, rb_qual, out_qual, tid == 0, wsel == 2u);
+                    if (tid == 0) tma_store_commit();
+#else
                     const DirectJob jq{S.sdst[1], S.ssrc[1], n_seq, ra_seq, rb_seq, out_seq};
                     const DirectJob jr{S.sdst[2], S.ssrc[2], n_qual, ra_qual, rb_qual, out_qual};
                     if (ok_seq) copy_interior(data, sbias, jq);
                     if (ok_qual) copy_interior(data, sbias, jr);
                     // one thread per line: the edge vectors of the sequence and quality lines, then the ids
-                    const uint32_t n1 = ok_seq ? n_seq : 0u, n2 = ok_qual ? n_qual : 0u, n0 = do_id ? n_id : 0u;
                     for (uint32_t w = tid; w < n1 + n2 + n0; w += kThreads) {
                         if (w < n1) copy_edges(data, sbias, jq, w);
                         else if (w < n1 + n2) copy_edges(data, sbias, jr, w - n1);
@@ -1235,8 +1441,9 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
                             copy_small_line(data, S.ssrc[0][i] + sbias, out_id, d, S.sdst[0][i + 1] - d);
                         }
                     }
+                    __syncthreads();   // the tile's bytes and the line tables are free again
+#endif
                 }
-                __syncthreads();   // the tile's bytes and the line tables are free again
             } else {
                 __syncthreads();
                 rotate_head(S, n);
@@ -1249,6 +1456,7 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
             issue_tile_load<true>(S, W, t + (uint32_t)kStages, c.stage, S.nl16[c.stage], use_list ? listed_count(n_ahead) : 0u);
         n_ahead = n_ahead2;
     }
+    if (kCopyStaged && kPack && tid == 0) tma_store_wait_all();   // shared memory must outlive the bulk stores
     // one atomic per warp: the run's share of the base count
     unsigned long long b64 = bases_acc;
 #pragma unroll

@@ -38,7 +38,8 @@ struct BsqPrefix {
     uint32_t cum_seq;   // bytes of the sequence lines that ended before the run
     uint32_t cum_qual;  // bytes of the quality lines that ended before the run
     uint32_t cum_id;    // UNSTRIPPED id bytes of the header lines that ended before the run
-    uint32_t _pad;
+    uint32_t prev3;     // position of the 4th newline before the run (the start of a record whose last three
+                        // lines end in the run: its length is checked against the buffer limit)
 };
 static_assert(sizeof(BsqPrefix) == 32, "BsqPrefix is 32 bytes");
 
@@ -92,7 +93,7 @@ BSQ_HD BsqPrefix bsq_prefix_from(const BsqSummary& E, uint32_t begin) {
     // header line r (class 0) spans (pos[r-1], pos[r]); pos[-1] is the virtual newline begin-1
     const uint32_t open3 = (ph == 0u && G > 0u) ? E.last[0] : 0u;
     p.cum_id = E.P[0] - (E.P[3] - open3) - (G > 0u ? (begin - 1u) : 0u) - 2u * n0;
-    p._pad = 0;
+    p.prev3 = E.last[3];
     return p;
 }
 

@@ -245,6 +245,9 @@ class DeviceFastqBatch:
 
     def __init__(self, gpu: "GpuParser", index: int, view: capi.BatchView):
         self._gpu, self._index = gpu, index
+        # the pointers below live in the parser's arena and are overwritten by its next pass: every accessor
+        # checks that the parser is still on the pass this batch was cut from
+        self._generation = gpu.generation
         self.num_records = int(view.num_records)
         self.seq_len = int(view.seq_len)
         self.quality_offset = int(view.quality_offset)
@@ -255,7 +258,21 @@ class DeviceFastqBatch:
         self.ends = view.ends
         self.id_ends = view.id_ends
 
+    def valid(self) -> bool:
+        return self._gpu.generation == self._generation
+
+    def _check(self):
+        if not self.valid():
+            raise BlazeSeqError("DeviceFastqBatch is stale: the parser has run another pass since this batch was cut "
+                                "(device batches are views into the parser's arena, valid until its next pass)")
+
+    def pointers(self):
+        """(sequence, quality, id, ends, id_ends) device addresses; raises if the parser has moved on."""
+        self._check()
+        return self.sequence_buffer, self.qual_buffer, self.id_buffer, self.ends, self.id_ends
+
     def copy_to_host(self) -> "FastqBatch":
+        self._check()
         return FastqBatch._from_arrays(*self._gpu.batch_to_host(self._index), quality_offset=self.quality_offset)
 
 
@@ -346,7 +363,7 @@ class GpuParser:
     def __init__(self, check_ascii=False, check_quality=False, schema: QualitySchema | None = None,
                  batch_size=DEFAULT_BATCH_SIZE, device_id=0, buffer_capacity=DEFAULT_CAPACITY,
                  buffer_max_capacity=MAX_CAPACITY, buffer_growth_enabled=False, h2d_chunk_bytes=None,
-                 force_id_slow_path=False, inflate_threads=0):
+                 force_id_slow_path=False, inflate_threads=0, compat_q5_width=0):
         L = capi.lib()
         cfg = capi.default_config()
         cfg.device_id = device_id
@@ -360,7 +377,10 @@ class GpuParser:
             cfg.h2d_chunk_bytes = h2d_chunk_bytes
         cfg.force_id_slow_path = int(force_id_slow_path)
         cfg.inflate_threads = int(inflate_threads)   # BGZF members of a stream are inflated by this many host threads (0 = all)
+        # reproduce the reference's quality check as written for a SIMD width of W bytes (record.mojo:90-102)
+        cfg.compat_q5_width = int(compat_q5_width)
         self.cfg = cfg
+        self.generation = 0   # bumped by every pass: DeviceFastqBatch views of earlier passes are stale
         self._h = C.c_void_p()
         capi.check(L.bsq_create(C.byref(cfg), C.byref(self._h)), None, "bsq_create")
         self.result: Optional[capi.PassResult] = None
@@ -380,12 +400,14 @@ class GpuParser:
         if m != self.cfg.batch_size:
             capi.check(capi.lib().bsq_set_batch_size(self._h, m), self._h)
             self.cfg.batch_size = m
+            self.generation += 1
 
     def parse_host(self, data: np.ndarray, stream_offset=0, first_record=0, is_last=True,
                    want=capi.WANT_OFFSETS) -> capi.PassResult:
         assert data.dtype == np.uint8 and data.flags.c_contiguous
         r = capi.PassResult()
         ptr = C.c_void_p(data.ctypes.data if data.size else 0)
+        self.generation += 1
         capi.check(capi.lib().bsq_parse_host(self._h, ptr, data.size, stream_offset, first_record,
                                              int(is_last), want, C.byref(r)), self._h, "bsq_parse_host")
         self.result = r
@@ -394,6 +416,7 @@ class GpuParser:
     def parse_device(self, dev_ptr: int, n: int, stream_offset=0, first_record=0, is_last=True,
                      want=capi.WANT_BATCHES) -> capi.PassResult:
         r = capi.PassResult()
+        self.generation += 1
         capi.check(capi.lib().bsq_parse_device(self._h, C.c_void_p(dev_ptr), n, stream_offset, first_record,
                                                int(is_last), want, C.byref(r)), self._h, "bsq_parse_device")
         self.result = r
@@ -434,6 +457,15 @@ class GpuParser:
                    self._h, "bsq_batch_to_host")
         return seq, qual, idb, ends, id_ends
 
+    def soa_to_host(self, seq, qual, idb, ends, id_ends):
+        """bsq_soa_to_host into caller arrays (numpy or torch CPU tensors, pinned for asynchronous copies)."""
+        def p(a):
+            if a is None:
+                return C.c_void_p(0)
+            return C.c_void_p(a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data)
+        capi.check(capi.lib().bsq_soa_to_host(self._h, p(seq), p(qual), p(idb), p(ends), p(id_ends)), self._h,
+                   "bsq_soa_to_host")
+
     def quality_sums(self, first_record: int = 0, count: Optional[int] = None, out_device_ptr: int = 0) -> np.ndarray:
         """Per-record sum of Phred scores of the last batches() pass, computed on the device from the SoA
         (bsq_quality_sums): the parse -> consumer hand-off without a host round trip."""
@@ -468,6 +500,7 @@ class GpuParser:
         """Parses the next region of a file stream; returns (PassResult, region bytes as a numpy view,
         stream offset of the region, records before it)."""
         r = capi.PassResult()
+        self.generation += 1
         capi.check(capi.lib().bsq_stream_next(stream, want, C.byref(r)), self._h, "bsq_stream_next")
         n, off, first = C.c_uint64(), C.c_int64(), C.c_int64()
         ptr = capi.lib().bsq_stream_region(stream, C.byref(n), C.byref(off), C.byref(first))
@@ -629,11 +662,14 @@ class FastqParser:
         if not is_last and reg.stop.code == capi.OK and (want & capi.WANT_BATCHES) and reg.n % self._batch_size:
             # keep batches whole across regions: the records of the trailing partial batch are
             # re-presented with the next region (their bytes go back into the carry)
+            # (all of them when the region holds fewer than one batch: the next region is read larger)
             keep = reg.n - reg.n % self._batch_size
             if keep > 0:
                 self._ensure_offsets(reg)
                 reg.consumed = int(reg.offsets[0][keep])
-                reg.n = keep
+            else:
+                reg.consumed = 0
+            reg.n = keep
         self._region = reg
         self._cursor = 0
 
@@ -743,13 +779,18 @@ class FastqParser:
         """parser.mojo:239-251: up to max_records records; EOF ends the batch, any other error is
         re-raised (the partially filled batch is lost, like in the reference)."""
         limit = max_records if max_records else self._batch_size
-        # whole device batches when the cut lines up with the pass
-        if self._region is None and self.has_more():
-            try:
+        # whole device batches when the cut lines up with the pass: a region whose records are used up (more
+        # input follows) is left here, so that the next one is parsed for batches too
+        while True:
+            reg = self._region
+            if reg is not None and self._cursor >= reg.n and reg.stop.code == capi.OK:
+                self._advance_region()
+            if self._region is None and self.has_more():
                 self._batch_size = limit
                 self._load_region(capi.WANT_BATCHES)
-            except BlazeSeqError:
-                raise
+                if self._region.n == 0 and self._region.stop.code == capi.OK:
+                    continue              # fewer records than one batch: read a larger region
+            break
         reg = self._region
         if (reg is not None and (reg.want & capi.WANT_BATCHES) and limit == self._gpu.cfg.batch_size
                 and self._cursor % limit == 0 and self._cursor < reg.n):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BSQ_ABI_VERSION 1
+#define BSQ_ABI_VERSION 2
 
 /* >= 0: FastxErrorCode, identical to blazeseq/errors.mojo:43-56.  < 0: library failures. */
 typedef int32_t bsq_status;
@@ -49,7 +49,8 @@ enum {
     BSQ_E_ARG = -2,            /* bad argument */
     BSQ_E_NO_DEVICE = -3,      /* no usable CUDA device: this library never parses on the CPU */
     BSQ_E_NOMEM = -4,
-    BSQ_E_STATE = -5           /* call sequence error (e.g. results requested before a pass) */
+    BSQ_E_STATE = -5,          /* call sequence error (e.g. results requested before a pass) */
+    BSQ_E_IO = -6              /* bsq_stream_*: reading or inflating the file failed */
 };
 
 /* what a pass materialises */
@@ -64,8 +65,10 @@ typedef struct bsq_config {
     int32_t check_ascii;           /* ParserConfig.check_ascii */
     int32_t check_quality;         /* ParserConfig.check_quality */
     uint8_t q_lower, q_upper, q_offset, _pad0; /* QualitySchema.LOWER/UPPER/OFFSET */
-    int64_t buffer_capacity;       /* ParserConfig.buffer_capacity (error text, tail rule Q2) */
-    int64_t buffer_max_capacity;   /* ParserConfig.buffer_max_capacity */
+    int64_t buffer_capacity;       /* ParserConfig.buffer_capacity: a record longer than this many bytes ends the
+                                      parse with BSQ_BUFFER_EXCEEDED when growth is off (parser.mojo:484-492) */
+    int64_t buffer_max_capacity;   /* ParserConfig.buffer_max_capacity: ... than this, BSQ_BUFFER_AT_MAX with
+                                      growth on (parser.mojo:493-503) */
     int32_t buffer_growth_enabled; /* ParserConfig.buffer_growth_enabled */
     int32_t batch_size;            /* FastqParser._batch_size, DEFAULT_BATCH_SIZE = 4096 */
     int64_t h2d_chunk_bytes;       /* staging chunk for bsq_parse_host (default 64 MiB) */
@@ -73,6 +76,11 @@ typedef struct bsq_config {
     int32_t inflate_threads;       /* bsq_stream_*: host threads that inflate BGZF members / read slices of a plain
                                       file (0 = all cores, at most 8 for plain reads); the
                                       parallelism argument of RapidgzipReader, readers.mojo:380-443 */
+    int32_t compat_q5_width;       /* 0: quality bytes are valid iff LOWER <= b <= UPPER (the documented intent).
+                                      W > 0: reproduce Validator._validate_quality_range as written
+                                      (fastq/record.mojo:90-102) for a host whose SIMD width is W bytes: the first
+                                      floor(n / W) * W quality bytes of a record also fail when b == UPPER */
+    int32_t _pad1;
 } bsq_config;
 
 /* The first error of a pass, with the context the reference prints
@@ -232,6 +240,12 @@ bsq_status bsq_get_soa(const bsq_parser* p, bsq_batch_view* out);
  * num_records). */
 bsq_status bsq_batch_to_host(bsq_parser* p, int64_t batch_index, uint8_t* seq, uint8_t* qual,
                              uint8_t* id, int64_t* ends, int64_t* id_ends);
+/* The whole pass as ONE host FastqBatch-shaped SoA (all batches back to back, ends / id_ends rebased per batch
+ * as in bsq_get_soa): what a caller that wants the reference's host FastqBatch product, not the
+ * DeviceFastqBatch, pays for.  Arrays sized from bsq_get_soa (sequence_bytes, seq_len, total_id_bytes,
+ * num_records, num_records); pinned destinations make the copies asynchronous.  NULL skips an array. */
+bsq_status bsq_soa_to_host(bsq_parser* p, uint8_t* seq, uint8_t* qual, uint8_t* id, int64_t* ends,
+                           int64_t* id_ends);
 /* Copies one window's offsets table to the host (line_ends: 4n+1, id_spans: 2n entries). */
 bsq_status bsq_offsets_to_host(bsq_parser* p, int32_t window, uint32_t* line_ends,
                                uint32_t* id_spans);

@@ -600,6 +600,18 @@ int64_t ora_parse_all(const uint8_t* data, size_t n_, const ora_config* cfg, ora
     int64_t pos = 0, lines = 0, nrec = 0, nb = 0;
     ora_err_clear(err, ORA_EOF);
     if (err) strcpy(err->message, "EOF");
+    /* A record must fit the BufferedReader: buffer_capacity bytes, or buffer_max_capacity once growth has
+     * run its course (parser.mojo:484-503; the streaming model above reaches the same verdict for every
+     * record that ends in a newline -- cross-checked in tests/test_oracle_golden.py). */
+    const int64_t limit = cfg->buffer_growth_enabled ? cfg->buffer_max_capacity : cfg->buffer_capacity;
+    char limit_msg[200];
+    if (cfg->buffer_growth_enabled)
+        snprintf(limit_msg, sizeof limit_msg, "FASTQ record exceeds maximum buffer capacity (%lld bytes). Enable "
+                 "buffer growth or increase max_capacity.", (long long)cfg->buffer_max_capacity);
+    else
+        snprintf(limit_msg, sizeof limit_msg, "FASTQ record exceeds buffer capacity (%lld bytes). Enable buffer "
+                 "growth or increase buffer_capacity.", (long long)cfg->buffer_capacity);
+    const int limit_code = cfg->buffer_growth_enabled ? ORA_BUFFER_AT_MAX : ORA_BUFFER_EXCEEDED;
     for (;;) {
         if (pos == n) break;                                     /* parser.mojo:314-317 */
         const uint8_t* nl[4];
@@ -611,6 +623,10 @@ int64_t ora_parse_all(const uint8_t* data, size_t n_, const ora_config* cfg, ora
             v.sep_start = (nl[1] - data) + 1;
             v.qual_start = (nl[2] - data) + 1;
             v.record_end = nl[3] - data;
+            if (limit > 0 && v.record_end + 1 - pos > limit) {   /* the 4th newline is never seen in the buffer */
+                ora_fill_plain_error(err, limit_code, limit_msg);
+                break;
+            }
             int code = ORA_OK;                                   /* utils.mojo:448-462 */
             if (data[pos] != '@') code = ORA_ID_NO_AT;
             else if (data[v.sep_start] != '+') code = ORA_SEP_NO_PLUS;
@@ -631,6 +647,10 @@ int64_t ora_parse_all(const uint8_t* data, size_t n_, const ora_config* cfg, ora
                          "FASTQ record exceeds buffer capacity (%lld bytes). Enable buffer "
                          "growth or increase buffer_capacity.", (long long)cfg->buffer_capacity);
                 ora_fill_plain_error(err, ORA_BUFFER_EXCEEDED, m);
+                break;
+            }
+            if (limit > 0 && n - pos > limit) {                  /* a tail that fills the buffer is not at "EOF" */
+                ora_fill_plain_error(err, limit_code, limit_msg);
                 break;
             }
             if (found < 3) {

@@ -33,16 +33,25 @@ def gpu_offsets(gpu: B.GpuParser, res):
 
 def check_stream(oracle, data: bytes | np.ndarray, *, check_ascii=False, check_quality=False,
                  schema="generic", batch_size=4096, growth=False, gpu=None, via="host", torch_dev=None,
-                 force_id_slow=False, want=capi.WANT_OFFSETS | capi.WANT_BATCHES):
+                 force_id_slow=False, want=capi.WANT_OFFSETS | capi.WANT_BATCHES, buffer_capacity=None,
+                 buffer_max_capacity=None, compat_q5_width=0):
     """Parses `data` on the GPU through the C ABI and on the CPU with the oracle; asserts that the
     records, offsets, id spans, SoA batches, totals and the stop reason (code, context, text) agree.
     Returns the PassResult."""
     arr = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else data
     own = gpu is None
     if own:
+        kw = {}
+        if buffer_capacity is not None:
+            kw["buffer_capacity"] = buffer_capacity
+        if buffer_max_capacity is not None:
+            kw["buffer_max_capacity"] = buffer_max_capacity
         gpu = B.GpuParser(check_ascii, check_quality, B.parse_schema(schema), batch_size,
-                          buffer_growth_enabled=growth, force_id_slow_path=force_id_slow)
-    cfg = oracle.config(check_ascii, check_quality, schema, buffer_growth_enabled=growth)
+                          buffer_growth_enabled=growth, force_id_slow_path=force_id_slow,
+                          compat_q5_width=compat_q5_width, **kw)
+    cfg = oracle.config(check_ascii, check_quality, schema, buffer_growth_enabled=growth,
+                        buffer_capacity=buffer_capacity, buffer_max_capacity=buffer_max_capacity,
+                        compat_simd_width=compat_q5_width)
     views, bases, err = oracle.parse_all(arr, cfg)
     if via == "host":
         res = gpu.parse_host(np.ascontiguousarray(arr), 0, 0, True, want)

@@ -12,6 +12,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 from ref_cases import BATCH_CASES, CASES, EXAMPLE_IDS  # noqa: E402
 
 
@@ -29,7 +31,8 @@ def U():
 
 def _cfg_kw(kw):
     return dict(check_ascii=kw.get("check_ascii", False), check_quality=kw.get("check_quality", False),
-                schema=kw.get("schema", "generic"), growth=kw.get("buffer_growth_enabled", False))
+                schema=kw.get("schema", "generic"), growth=kw.get("buffer_growth_enabled", False),
+                buffer_capacity=kw.get("buffer_capacity"), buffer_max_capacity=kw.get("buffer_max_capacity"))
 
 
 # ------------------------------------------------------------------ reference literal streams
@@ -40,10 +43,6 @@ def _cfg_kw(kw):
 def test_literal_streams_through_fastq_parser(B, oracle, case, api):
     """The reference's own unit tests, run against the drop-in API."""
     name, cite, data, kw, records, err_sub = case
-    if kw.get("buffer_capacity", 1 << 20) < len(data):
-        # records that outgrow a tiny BufferedReader are host-buffer semantics the GPU path does
-        # not have (a pass holds the whole region); the oracle's streaming model pins those
-        pytest.skip("buffer smaller than the stream: BufferedReader-only behaviour")
     cfg = B.ParserConfig(check_ascii=kw.get("check_ascii", False), check_quality=kw.get("check_quality", False),
                          buffer_capacity=kw.get("buffer_capacity", B.DEFAULT_CAPACITY),
                          buffer_growth_enabled=kw.get("buffer_growth_enabled", False),
@@ -61,8 +60,6 @@ def test_literal_streams_through_fastq_parser(B, oracle, case, api):
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_literal_streams_bit_exact(U, oracle, case):
     name, cite, data, kw, records, err_sub = case
-    if kw.get("buffer_capacity", 1 << 20) < len(data):
-        pytest.skip("BufferedReader-only behaviour")
     U.check_stream(oracle, data, batch_size=2, **_cfg_kw(kw))
 
 
@@ -246,6 +243,78 @@ def test_long_reads_span_tiles(U, oracle):
     bad = bytearray(data)
     bad[len(recs[0]) + len(recs[1]) + 40000] = 0x80  # non-ASCII deep inside a long sequence line
     U.check_stream(oracle, bytes(bad), batch_size=4, check_ascii=True)
+
+
+@pytest.mark.parametrize("growth", [False, True])
+def test_record_longer_than_the_buffer(U, B, oracle, growth):
+    """parser.mojo:484-503: a record that does not fit buffer_capacity (growth off) / buffer_max_capacity (growth
+    on) ends the parse with BUFFER_EXCEEDED / BUFFER_AT_MAX and the reference's text; the records before it are
+    delivered.  Lengths right at the limit, the long record first / in the middle / last, with and without a
+    trailing newline, next to structure errors in the same record."""
+    rng = np.random.default_rng(5 + growth)
+
+    def rec(i, L, bad=False):
+        seq = bytes(rng.choice(list(b"ACGT"), L).astype(np.uint8))
+        return b"@r%d\n" % i + seq + b"\n+\n" + (b"I" * (L - 1 if bad else L)) + b"\n"
+    cap = 300
+    kw = dict(buffer_capacity=cap if not growth else 64, buffer_max_capacity=cap if growth else 1 << 20, growth=growth)
+    for long_at in (0, 7, 19):
+        for total in (cap - 1, cap, cap + 1, 5 * cap):
+            recs = [rec(i, int(rng.integers(20, 100))) for i in range(20)]
+            head = len(b"@r%d\n" % long_at) + 4                    # '@id\n' + '\n+\n' + the two line ends
+            L = (total - head) // 2
+            recs[long_at] = rec(long_at, L)
+            if len(recs[long_at]) != total:                        # odd totals: pad the id
+                recs[long_at] = recs[long_at].replace(b"@r", b"@rr", 1)
+            data = b"".join(recs)
+            res = U.check_stream(oracle, data, batch_size=8, **kw)
+            if len(recs[long_at]) > cap:
+                assert res.n_records == long_at and res.stop.code == (9 if growth else 8), (long_at, total, res.stop.text)
+                assert ("maximum buffer capacity (%d bytes)" % cap if growth else "buffer capacity (%d bytes)" % cap) in res.stop.text
+            else:
+                assert res.n_records == 20
+            U.check_stream(oracle, data[:-1], batch_size=8, **kw)                    # no trailing newline
+            U.check_stream(oracle, data, batch_size=8, want=2, **kw)
+    # too long AND malformed: the buffer error comes first (the record is never scanned to its end)
+    recs = [rec(0, 30), rec(1, 400, bad=True), rec(2, 30)]
+    res = U.check_stream(oracle, b"".join(recs), batch_size=8, **kw)
+    assert res.n_records == 1 and res.stop.code == (9 if growth else 8)
+    # an unterminated fragment longer than the buffer
+    U.check_stream(oracle, rec(0, 30) + b"@frag\n" + b"A" * 500, batch_size=8, **kw)
+    U.check_stream(oracle, rec(0, 30) + b"@frag\n" + b"A" * 200 + b"\n+\n" + b"I" * 200, batch_size=8, **kw)
+
+
+@pytest.mark.parametrize("width", [16, 32, 64])
+def test_quality_check_as_written_in_the_reference(U, B, oracle, width):
+    """bsq_config.compat_q5_width = W reproduces Validator._validate_quality_range as written (record.mojo:90-102):
+    the first floor(n / W) * W quality bytes of a record are also rejected when they EQUAL the schema's upper bound
+    ('~'), the remaining ones only above it.  Oracle: ora_config.compat_simd_width."""
+    rng = np.random.default_rng(width)
+    base = oracle.synth(4000, 90, 210, 2, 40, "sanger")           # several tiles; no '~' anywhere
+    views, _, _ = oracle.parse_all(base, oracle.config(True, True, "sanger"))
+    kw = dict(check_quality=True, schema="sanger", batch_size=500, compat_q5_width=width)
+    U.check_stream(oracle, base, **kw)
+    for trial in range(12):
+        k = int(rng.integers(0, len(views)))
+        v = views[k]
+        n = int(v["qual_len"])
+        body = n - n % width
+        where = [0, body - 1, body, n - 1, int(rng.integers(0, n))][trial % 5]
+        if where < 0 or where >= n:
+            continue
+        data = base.copy()
+        data[int(v["qual_start"]) + where] = ord("~")
+        res = U.check_stream(oracle, data, **kw)
+        assert (res.n_records == k and res.stop.code == 5) if where < body else res.n_records == len(views), (k, where, body)
+        U.check_stream(oracle, data, check_quality=True, schema="sanger", batch_size=500)   # documented intent: '~' is valid
+    # a long read whose '~' sits in an earlier tile than the end of its quality line
+    L = 40007
+    seq = bytes(rng.choice(list(b"ACGT"), L).astype(np.uint8))
+    for where in (5, L - L % width - 1, min(L - L % width, L - 1), L - 1, L - 7):
+        q = bytearray(b"I" * L)
+        q[where] = ord("~")
+        data = b"@a\nAC\n+\nII\n@long\n" + seq + b"\n+\n" + bytes(q) + b"\n@b\nAC\n+\nII\n"
+        U.check_stream(oracle, data, check_quality=True, schema="sanger", batch_size=2, compat_q5_width=width)
 
 
 @pytest.mark.parametrize("digits", [8, 9])
@@ -514,6 +583,76 @@ def test_shard_summaries_locate_record_starts(B, oracle):
 # ------------------------------------------------------------------ FastqParser streaming (several passes)
 
 
+def _shard_worker(rank, world, port, data_bytes, cuts, halo, out_q):
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import blazeseq_b200 as B
+    from blazeseq_b200 import sharding
+    import gpu_util as U
+    import oracle_py as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)     # both ranks drive cuda:0: gloo carries the 72 bytes
+    data = np.frombuffer(data_bytes, np.uint8)
+    views, bases, err = O.parse_all(data, O.config(buffer_growth_enabled=True))
+    bounds = [0] + list(cuts) + [data.size]
+    lo, hi = bounds[rank], bounds[rank + 1]
+    end = min(data.size, hi + halo)
+    shard = torch.from_numpy(data[lo:end].copy()).cuda()              # own bytes + halo
+    gpu = B.GpuParser(batch_size=512, buffer_growth_enabled=True)
+    plan = sharding.plan(dist, gpu.summarize_device(shard.data_ptr(), hi - lo), hi - lo)
+    n = plan.end - plan.begin
+    assert plan.end <= end - lo
+    res = gpu.parse_device(shard.data_ptr() + plan.begin, n, lo + plan.begin, plan.first_record, rank == world - 1, 3)
+    ok = res.bytes_consumed == n and res.stop.code == (O.EOF if rank == world - 1 else O.OK)
+    k0, cnt = plan.first_record, int(res.n_records)
+    g = U.gpu_offsets(gpu, res)                                        # absolute stream offsets (stream_base carries lo + begin)
+    mine = views[k0:k0 + cnt]
+    for name in U.NAMES5 + ("id_start", "id_len"):
+        ok = ok and np.array_equal(g[name], mine[name])
+    for b in range(int(res.n_batches)):
+        seq, qual, idb, ends, id_ends = gpu.batch_to_host(b)
+        oi, os_, oq, oie, oe = O.build_batch(data, mine[b * 512:(b + 1) * 512])
+        ok = ok and all(np.array_equal(x, y) for x, y in ((seq, os_), (qual, oq), (idb, oi), (ends, oe), (id_ends, oie)))
+    reads, total_bases = sharding.allreduce_counts(dist, cnt, int(res.n_bases))
+    out_q.put((rank, k0, cnt, reads, total_bases, bool(ok), len(views), bases))
+    gpu.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_parse_on_device(oracle, world):
+    """SURVEY 8e on the device: one mixed-length stream cut at arbitrary byte offsets, one process per shard.  Every
+    rank summarises its shard (bsq_summarize_device), the summaries are all-gathered, bsq_shard_prefix gives the cut
+    points, the rank parses its own records + halo (bsq_parse_device) -- offsets and SoA batches equal the oracle's
+    slice for that shard, and the all-reduced totals equal the whole stream's."""
+    import socket
+    import torch.multiprocessing as mp
+    data = oracle.synth(60000, 75, 300, 2, 40, "illumina_1.8")
+    rng = np.random.default_rng(world)
+    cuts = sorted(int(x) for x in rng.integers(1, data.size - 1, world - 1))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, data.tobytes(), cuts, 1024, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    first = 0
+    for rank, k0, cnt, reads, total_bases, ok, n_all, bases in results:
+        assert ok and k0 == first and (reads, total_bases) == (n_all, bases), (rank, k0, first, cnt, ok)
+        first += cnt
+    assert first == results[0][6]
+
+
 @pytest.mark.parametrize("region_bytes", [700, 4096, 100000])
 @pytest.mark.parametrize("mutate", ["none", "crlf", "notail", "noise"])
 def test_fastq_parser_streams_in_regions(B, oracle, region_bytes, mutate):
@@ -540,6 +679,34 @@ def test_fastq_parser_streams_in_regions(B, oracle, region_bytes, mutate):
     assert str(ei.value) == err.text
     assert (ei.value.record_number, ei.value.line_number, ei.value.file_position) == \
         (err.record_number, err.line_number, err.file_position)
+
+
+def test_device_batches_in_every_region_and_stale_views(B, oracle, tmp_path):
+    """batches() stays on the device fast path after the first region (every batch of every region hands out
+    its DeviceFastqBatch), also when the records of a trailing partial batch are carried into the next region and
+    the carry is larger than the room in front of the pinned region buffer; a DeviceFastqBatch of an earlier pass
+    refuses to be read once the parser has moved on."""
+    data = oracle.synth(3000, 140, 160, 2, 40, "sanger")
+    views, _, _ = oracle.parse_all(data, oracle.config())
+    path = tmp_path / "r.fastq"
+    path.write_bytes(data.tobytes())
+    for reader, region in ((B.MemoryReader(data.tobytes()), 40000), (B.MemoryReader(data.tobytes()), 100000),
+                           (B.FileReader(str(path)), 64 << 10), (B.FileReader(str(path)), 20000)):
+        p = B.FastqParser(reader, batch_size=150, schema="sanger", region_bytes=region)   # 64 KiB: carry > 16 KiB
+        seen, first_dev = 0, None
+        for batch in p.batches(150):
+            dev = batch.to_device()
+            assert dev is not None and dev.valid(), seen                # device path in every region
+            first_dev = first_dev or dev
+            oi, os_, oq, oie, oe = oracle.build_batch(data, views[seen:seen + len(batch)])
+            assert np.array_equal(batch._sequence_bytes, os_) and np.array_equal(batch._ends, oe)
+            assert np.array_equal(batch._id_bytes, oi) and np.array_equal(batch._id_ends, oie)
+            seen += len(batch)
+        assert seen == 3000
+        assert not first_dev.valid()
+        with pytest.raises(B.BlazeSeqError, match="stale"):
+            first_dev.copy_to_host()
+        p.close()
 
 
 @pytest.mark.parametrize("region_bytes", [5000, 1 << 30])

@@ -25,12 +25,12 @@ def test_library_exports_every_declared_symbol(B):
     L = B._capi.lib()
     for name in declared:
         assert getattr(L, name) is not None
-    assert L.bsq_abi_version() == 1
+    assert L.bsq_abi_version() == 2
 
 
 def test_struct_layouts_match_header(B):
     c = B._capi
-    assert C.sizeof(c.Config) == 56 and C.sizeof(c.Error) == 1056 and C.sizeof(c.Summary) == 64
+    assert C.sizeof(c.Config) == 64 and C.sizeof(c.Error) == 1056 and C.sizeof(c.Summary) == 64
     assert C.sizeof(c.PassResult) == 48 + 1056 and C.sizeof(c.OffsetsView) == 48
     assert C.sizeof(c.BatchView) == 80 and C.sizeof(c.ShardStart) == 32
 

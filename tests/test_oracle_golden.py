@@ -323,3 +323,34 @@ def test_mt_baseline_matches(oracle):
         for mode in (0, 1):
             n, nb, code = oracle.baseline_mt(b, oracle.config(True, True), mode, 4096, threads)
             assert (n, nb, code) == (len(views), bases, 0)
+
+
+def test_record_limit_of_the_canonical_parse_equals_the_streaming_model(oracle):
+    """parser.mojo:484-503.  ora_parse_all reports a record longer than buffer_capacity (growth off) or
+    buffer_max_capacity (growth on) as BUFFER_EXCEEDED / BUFFER_AT_MAX.  For streams whose records all end in a
+    newline the BufferedReader model (ora_open / ora_next_view) must give the same records and the same stop."""
+    rng = np.random.default_rng(1)
+
+    def rec(i, L):
+        return b"@r%d\n" % i + bytes(rng.choice(list(b"ACGT"), L).astype(np.uint8)) + b"\n+\n" + b"I" * L + b"\n"
+    hits = 0
+    for trial in range(300):
+        cap = int(rng.integers(40, 300))
+        growth = bool(trial % 2)
+        mx = int(rng.integers(cap, 600))
+        data = b"".join(rec(i, int(rng.integers(1, 160))) for i in range(int(rng.integers(1, 30))))
+        cfg = oracle.config(False, False, "generic", buffer_capacity=cap, buffer_growth_enabled=growth,
+                            buffer_max_capacity=mx)
+        views, bases, err = oracle.parse_all(data, cfg)
+        p = oracle.StreamParser(data, cfg)
+        n = 0
+        while True:
+            rc, v, se = p.next_view()
+            if rc != oracle.OK:
+                break
+            assert (v.header_start, v.record_end) == (int(views[n]["header_start"]), int(views[n]["record_end"]))
+            n += 1
+        assert n == len(views), (trial, cap, growth, mx)
+        assert (se.code, se.message) == (err.code, err.message), (trial, cap, growth, mx, se.message, err.message)
+        hits += err.code in (8, 9)
+    assert hits > 50   # the limit was exercised
