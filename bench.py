@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--mixed", action="store_true", help="configs[3]: mixed read length 75-300 bp instead of 150 bp")
     ap.add_argument("--shard-stream", action="store_true",
                     help="strong scaling: ONE stream of --gib cut at arbitrary byte offsets over the ranks (sharding.plan)")
+    ap.add_argument("--gzip", action="store_true", help="configs[4]: .fastq.gz / BGZF files through the stream pipeline (--gib 4)")
     ap.add_argument("--crlf", action="store_true", help="CRLF line ends: every id needs _strip_spaces (id strip pipeline)")
     ap.add_argument("--read-len", type=int, default=150, help="read length of the synthetic stream (record stride sweeps)")
     ap.add_argument("--id-digits", type=int, default=0, help="zero-padded id width (0: that of the stream's read count)")
@@ -349,8 +350,114 @@ def main():
                 "launches": launches, "steps": steps, "value": reads / (wall / steps), "ms_per_step": wall / steps * 1e3,
                 "n_windows": int(r.n_windows), "own_reads": own_reads, "algo": algo}
 
+    # ------------------------------------------------------------------------------------------------
+    # configs[4]: a .fastq.gz through the native stream pipeline (bsq_stream_*), file -> results
+    # ------------------------------------------------------------------------------------------------
+    def gzip_leg(gib, region_mib=256):
+        """Writes `gib` of the 150 bp stream as a plain file, as BGZF (gzip level 6, 64 KiB members) and as ordinary
+        multi-member gzip, and streams each through bsq_stream_next(WANT_BATCHES).  BGZF: the compressed members
+        cross PCIe and are inflated on the device (k_inflate_members); ordinary gzip goes through zlib on the reader
+        thread.  The CPU arm beside it: zlib on every host thread (BGZF members) feeding nothing (inflate only)."""
+        import gzip as gz
+        import shutil
+        import zlib
+        from concurrent.futures import ThreadPoolExecutor
+        from blazeseq_b200 import bgzf
+        schema = B.parse_schema("illumina_1.8")
+        g = B.GpuParser(False, False, schema, 4096, device_id=local)
+        gh = B.GpuParser(False, False, schema, 4096, device_id=local, host_inflate=True)
+        reads = L.bsq_compute_num_reads_for_size(int(gib * GIB), 150, 150)
+        nbytes = L.bsq_synth_size(reads, 150, 150)
+        dbuf = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        g.synth_device(dbuf.data_ptr(), nbytes, reads, 0, reads, 150, 150, 2, 40, schema)
+        host = dbuf[:nbytes].cpu().numpy()
+        del dbuf
+        tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        cores = os.cpu_count() or 1
+        try:
+            plain, gzp, bgz = (os.path.join(tmp, n) for n in ("x.fastq", "x.fastq.gz", "x.fastq.bgz"))
+            host.tofile(plain)
+            step = 32 << 20     # ordinary gzip, written by all cores as 32 MiB members (gzread concatenates them)
+            with ThreadPoolExecutor(cores) as ex:
+                parts = list(ex.map(lambda i: gz.compress(host[i:i + step].tobytes(), compresslevel=6), range(0, nbytes, step)))
+            with open(gzp, "wb") as f:
+                for part in parts:
+                    f.write(part)
+            del parts
+            blob = bgzf.compress(host, 6, threads=cores)
+            with open(bgz, "wb") as f:
+                f.write(blob)
+
+            def run(parser, path):
+                st_ = parser.stream_open(path, capi.SOURCE_AUTO, region_mib << 20)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                n = 0
+                while True:
+                    res, off, first = parser.stream_next_result(st_, capi.WANT_BATCHES)
+                    n += int(res.n_records)
+                    if res.stop.code != capi.OK:
+                        assert res.stop.code == capi.EOF, res.stop.text
+                        break
+                torch.cuda.synchronize()
+                wall = time.perf_counter() - t0
+                s_ = parser.stream_stats(st_)
+                parser.stream_close(st_)
+                assert n == reads, (n, reads)
+                return {"wall_s": wall, "reads_per_s": reads / wall, "uncompressed_gb_per_s": nbytes / wall / 1e9,
+                        "reader_busy_s": s_.reader_busy_s, "gpu_pass_s": s_.parse_s, "caller_wait_reader_s": s_.wait_reader_s,
+                        "regions": int(s_.regions), "h2d_compressed_s": s_.h2d_s, "inflate_kernels_s": s_.inflate_s,
+                        "compressed_bytes_over_pcie": int(s_.compressed_bytes)}
+            run(g, plain)                     # warm the page cache and the arenas
+            run(g, bgz)
+            out = {"bgzf_device_inflate": run(g, bgz), "bgzf_host_threads": run(gh, bgz), "plain_file": run(g, plain)}
+            out["gzip_zlib_reader_thread"] = run(g, gzp) if gib <= 1.0 else None     # 0.26 GB/s: only on small inputs
+            # CPU arm: zlib over the same BGZF members on every host thread (what the reference's parallel reader does)
+            offs, pos = [], 0
+            while pos < len(blob):
+                total = (blob[pos + 16] | (blob[pos + 17] << 8)) + 1
+                offs.append((pos, total))
+                pos += total
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(cores) as ex:
+                def work(k):
+                    tot = 0
+                    for a, t_ in offs[k::cores]:
+                        tot += len(zlib.decompress(blob[a + 18:a + t_ - 8], -15))
+                    return tot
+                assert sum(ex.map(work, range(cores))) == nbytes
+            out["cpu_zlib_all_threads_inflate_only"] = {"wall_s": time.perf_counter() - t0, "threads": cores,
+                                                        "uncompressed_gb_per_s": nbytes / (time.perf_counter() - t0) / 1e9}
+            out.update({"reads": reads, "uncompressed_bytes": nbytes, "bgzf_bytes": len(blob), "gzip_bytes": os.path.getsize(gzp),
+                        "region_mib": region_mib})
+            return out
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+            g.close(); gh.close()
+
     sampler = ClockSampler(local)
     sampler.start()
+
+    if args.gzip:
+        gib = args.gib if args.gib != 10.0 else 4.0
+        leg = gzip_leg(gib)
+        clocks = sampler.stop()
+        best = leg["bgzf_device_inflate"]
+        if rank == 0:
+            emit(json.dumps({
+                "metric": "fastq_reads_per_s", "value": best["reads_per_s"], "unit": "reads/s", "n_gpus": 1, "steps": 1, "warmup": 1,
+                "ms_per_step": best["wall_s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic", "parsed_gb_per_s": best["uncompressed_gb_per_s"],
+                "config": {"workload": "configs[4]: %.2f GiB (uncompressed) 150 bp FASTQ as BGZF (gzip -6, 64 KiB members), file -> "
+                                       "bsq_stream_next(batches 4096): compressed members over PCIe, inflated on the device, "
+                                       "regions of %d MiB" % (leg["uncompressed_bytes"] / GIB, leg["region_mib"])},
+                "roofline": None, "cpu_baseline": {"value": leg["cpu_zlib_all_threads_inflate_only"]["uncompressed_gb_per_s"], "unit": "GB/s",
+                                                   "cores": leg["cpu_zlib_all_threads_inflate_only"]["threads"], "kind": "port",
+                                                   "sample": "zlib over the same BGZF members on every host thread, inflate only"},
+                "e2e": {"value": best["reads_per_s"], "unit": "reads/s", "h2d_bytes_per_step": leg["bgzf_bytes"], "d2h_bytes_per_step": 0,
+                        "result": "DeviceFastqBatch SoA per region"},
+                "gzip": leg, "clocks": clocks}))
+        return
 
     if args.shard_stream:
         mn, mx = (75, 300) if args.mixed else (args.read_len, args.read_len)
@@ -524,6 +631,20 @@ def main():
                              "value": leg["value"], "unit": "reads/s", "ms_per_step": leg["ms_per_step"], "steps": k,
                              "reads_total": leg["reads"], "parsed_gb_per_s": leg["bytes"] / (leg["ms_per_step"] * 1e-3) / 1e9,
                              "k_resolve_ms_per_launch": leg["ms"][2] / leg["n_windows"], "summarize_ms_per_step": leg["ms"][0]}
+        if rank == 0 and world == 1:
+            # configs[4] (scaled to 1 GiB to keep the default run short; `bench.py --gzip` runs the 4 GiB case)
+            try:
+                gl = gzip_leg(1.0)
+                sub["configs[4]"] = {"workload": "configs[4] scaled: 1 GiB (uncompressed) 150 bp FASTQ as BGZF / gzip files -> "
+                                                 "bsq_stream_next(batches 4096)", "unit": "GB/s of FASTQ text",
+                                     "bgzf_device_inflate": gl["bgzf_device_inflate"]["uncompressed_gb_per_s"],
+                                     "bgzf_host_threads": gl["bgzf_host_threads"]["uncompressed_gb_per_s"],
+                                     "gzip_zlib_reader_thread": (gl["gzip_zlib_reader_thread"] or {}).get("uncompressed_gb_per_s"),
+                                     "plain_file": gl["plain_file"]["uncompressed_gb_per_s"],
+                                     "cpu_zlib_all_threads_inflate_only": gl["cpu_zlib_all_threads_inflate_only"]["uncompressed_gb_per_s"],
+                                     "value": gl["bgzf_device_inflate"]["reads_per_s"], "ms_per_step": gl["bgzf_device_inflate"]["wall_s"] * 1e3}
+            except Exception as e:   # (no room in /dev/shm, ...): the headline does not depend on it
+                sub["configs[4]"] = {"skipped": repr(e)[:200]}
 
     # ---- e2e: the same pass starting from pinned host memory (H2D inside the timed region) -------
     e2e = None

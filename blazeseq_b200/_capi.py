@@ -25,7 +25,7 @@ SYMBOLS = [
     "bsq_get_soa", "bsq_batch_to_host", "bsq_offsets_to_host", "bsq_pass_device_input",
     "bsq_last_timing", "bsq_compute_num_reads_for_size", "bsq_synth_size", "bsq_synth_device",
     "bsq_summarize_device", "bsq_shard_prefix", "bsq_stream_open", "bsq_stream_next", "bsq_stream_region",
-    "bsq_stream_get_stats", "bsq_stream_close", "bsq_quality_sums", "bsq_soa_to_host",
+    "bsq_stream_get_stats", "bsq_stream_close", "bsq_quality_sums", "bsq_soa_to_host", "bsq_stream_region_info",
 ]
 
 
@@ -36,7 +36,7 @@ class Config(C.Structure):
         ("buffer_capacity", C.c_int64), ("buffer_max_capacity", C.c_int64),
         ("buffer_growth_enabled", C.c_int32), ("batch_size", C.c_int32),
         ("h2d_chunk_bytes", C.c_int64), ("force_id_slow_path", C.c_int32), ("inflate_threads", C.c_int32),
-        ("compat_q5_width", C.c_int32), ("_pad1", C.c_int32),
+        ("compat_q5_width", C.c_int32), ("host_inflate", C.c_int32),
     ]
 
 
@@ -85,7 +85,8 @@ class Summary(C.Structure):
 
 class StreamStats(C.Structure):
     _fields_ = [("bytes_read", C.c_uint64), ("regions", C.c_uint64), ("reader_busy_s", C.c_double),
-                ("parse_s", C.c_double), ("wait_reader_s", C.c_double)]
+                ("parse_s", C.c_double), ("wait_reader_s", C.c_double), ("h2d_s", C.c_double), ("inflate_s", C.c_double),
+                ("compressed_bytes", C.c_uint64)]
 
 
 SOURCE_PLAIN, SOURCE_GZIP, SOURCE_AUTO = 0, 1, 2
@@ -143,6 +144,8 @@ def lib():
     L.bsq_stream_next.argtypes = [vp, u32, C.POINTER(PassResult)]
     L.bsq_stream_region.argtypes = [vp, C.POINTER(u64), C.POINTER(i64), C.POINTER(i64)]
     L.bsq_stream_region.restype = vp
+    L.bsq_stream_region_info.argtypes = [vp, C.POINTER(u64), C.POINTER(i64), C.POINTER(i64)]
+    L.bsq_stream_region_info.restype = None
     L.bsq_stream_get_stats.argtypes = [vp, C.POINTER(StreamStats)]
     L.bsq_stream_close.argtypes = [vp]
     L.bsq_stream_close.restype = None
@@ -168,7 +171,7 @@ def check(status: int, handle=None, what: str = "") -> int:
         if handle:
             detail = lib().bsq_last_error_text(handle).decode("latin-1")
         names = {E_CUDA: "CUDA failure", E_ARG: "bad argument", E_NO_DEVICE: "no usable CUDA device",
-                 E_NOMEM: "out of memory", E_STATE: "call sequence error"}
+                 E_NOMEM: "out of memory", E_STATE: "call sequence error", E_IO: "read / inflate failure"}
         raise BsqLibraryError(f"{what or 'blazeseq_gpu'}: {names.get(status, status)} {detail}".strip())
     return status
 

@@ -26,6 +26,7 @@
 #include "../../include/blazeseq_gpu.h"
 #include "bsq_aux.cuh"
 #include "bsq_device.cuh"
+#include "bsq_inflate.cuh"
 
 using namespace bsq;
 
@@ -864,6 +865,79 @@ struct bsq_stream {
     struct Member { size_t coff; uint32_t clen; uint64_t ooff; uint32_t isize; };
     std::vector<Member> members;
 
+    // ---- BGZF inflated on the device (cfg.gpu_inflate): the reader thread only READS -- it fills a pinned buffer
+    // with whole compressed members (parallel pread + a walk over the member headers); bsq_stream_next sends the
+    // compressed bytes over PCIe and k_inflate_members writes the region straight into HBM, in front of which the
+    // previous region's unconsumed tail is copied device to device.  The inflated bytes visit the host only when
+    // the caller asks for them (bsq_stream_region).
+    bool gpu_inflate = false;
+    struct ZBuf { uint8_t* mem = nullptr; uint64_t n = 0; std::vector<bsq::InflateMember> members; uint64_t out_bytes = 0; };
+    ZBuf zb[2];
+    uint64_t zcap = 0;                   // compressed bytes a pinned buffer holds
+    std::vector<uint8_t> zcarry;         // compressed bytes read but not yet handed out (a partial member, or over budget)
+    int64_t zfile_pos = 0;
+    DevBuf zdev, mdev, sdev, rdev[2];    // compressed bytes, member table, member status, inflated regions (ping-pong)
+    int rcur = 0;
+    uint64_t dev_carry_off = 0, dev_carry_len = 0;   // unconsumed tail of the region in rdev[rcur]
+    std::vector<uint8_t> region_host;    // the current region on the host, fetched on demand
+    std::vector<uint32_t> status_host;
+    bool region_host_valid = false;
+    uint64_t region_dev_n = 0;
+
+    // fills zb[which] with whole members: at most region_bytes of output, at most zcap compressed bytes
+    bool fill_bgzf_raw(ZBuf& z, bool* eof) {
+        z.members.clear(); z.n = 0; z.out_bytes = 0;
+        uint64_t have = zcarry.size();
+        if (have) memcpy(z.mem, zcarry.data(), have);
+        zcarry.clear();
+        // parallel pread of the next compressed bytes
+        const uint64_t want = (uint64_t)std::min<int64_t>((int64_t)(zcap - have), file_size - zfile_pos);
+        if (want > 0) {
+            const int nt = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)io_threads, want >> 22));
+            const uint64_t slice = (want + (uint64_t)nt - 1) / (uint64_t)nt;
+            std::atomic<bool> bad{false};
+            auto work = [&](int t) {
+                uint64_t a = std::min<uint64_t>(want, slice * (uint64_t)t), b2 = std::min<uint64_t>(want, a + slice);
+                while (a < b2) {
+                    const ssize_t k = pread(fileno(zfp), z.mem + have + a, (size_t)std::min<uint64_t>(b2 - a, 1u << 30), (off_t)(zfile_pos + (int64_t)a));
+                    if (k <= 0) { bad = true; return; }
+                    a += (uint64_t)k;
+                }
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+            work(0);
+            for (auto& th : pool) th.join();
+            if (bad.load()) return false;
+            zfile_pos += (int64_t)want;
+            have += want;
+        }
+        // walk the member headers
+        uint64_t pos = 0;
+        while (pos + 18 <= have) {
+            const uint8_t* h = z.mem + pos;
+            if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4) || h[10] != 6 || h[11] != 0 || h[12] != 'B' || h[13] != 'C' ||
+                h[14] != 2 || h[15] != 0)
+                return false;
+            const uint32_t total = ((uint32_t)h[16] | ((uint32_t)h[17] << 8)) + 1u;
+            if (total < 18u + 8u) return false;
+            if (pos + total > have) break;                              // the member continues in bytes not read yet
+            const uint8_t* t = h + total - 8;
+            const uint32_t crc = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+            const uint32_t isz = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+            if (isz > (1u << 16)) return false;
+            if (z.out_bytes + isz > region_bytes && !z.members.empty()) break;   // belongs to the next region
+            if (isz > 0) z.members.push_back(bsq::InflateMember{pos + 18, total - 18u - 8u, isz, z.out_bytes, crc, 0u});
+            z.out_bytes += isz;
+            pos += total;
+        }
+        if (pos == 0 && have > 0 && (have >= zcap || zfile_pos >= file_size)) return false;   // a member that never completes
+        z.n = pos;
+        zcarry.assign(z.mem + pos, z.mem + have);
+        *eof = zfile_pos >= file_size && zcarry.empty();
+        return true;
+    }
+
     // next member (header + payload) appended to `to`; returns 1 ok, 0 clean EOF, -1 malformed
     int read_member(std::vector<uint8_t>& to, uint32_t* clen, uint32_t* isize) {
         uint8_t h[18];
@@ -953,8 +1027,12 @@ struct bsq_stream {
             const auto t0 = std::chrono::steady_clock::now();
             uint64_t got = 0;
             bool eof = false, err = false;
-            uint8_t* dst = b->mem + carry_cap;
-            if (bgzf) {
+            uint8_t* dst = b->mem ? b->mem + carry_cap : nullptr;
+            if (gpu_inflate) {
+                ZBuf& z = zb[next_fill];
+                if (!fill_bgzf_raw(z, &eof)) err = true;
+                got = z.out_bytes;
+            } else if (bgzf) {
                 if (!fill_bgzf(dst, &got, &eof)) err = true;
             } else if (kind == BSQ_SOURCE_PLAIN && file_size >= 0) {
                 // regular file: the region is read as `io_threads` slices with pread (one memcpy-bound
@@ -1027,9 +1105,14 @@ extern "C" bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t s
             s->bgzf = true;
             s->zfp = f;
             int nt = p->cfg.inflate_threads;
-            if (const char* e = getenv("BSQ_INFLATE_THREADS")) nt = atoi(e);
             if (nt <= 0) nt = (int)std::max(1u, std::thread::hardware_concurrency());
             s->inflate_threads = std::min(nt, 64);
+            struct stat sb;
+            if (!p->cfg.host_inflate && fstat(fileno(f), &sb) == 0 && S_ISREG(sb.st_mode)) {
+                s->gpu_inflate = true;           // the members cross PCIe compressed and are inflated by k_inflate_members
+                s->file_size = (int64_t)sb.st_size;
+                s->io_threads = std::min(nt, 8);
+            }
         } else {
             if (f) fclose(f);
             s->gz = gzopen(path, "rb");
@@ -1041,7 +1124,6 @@ extern "C" bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t s
         if (s->fp && fstat(fileno(s->fp), &sb) == 0 && S_ISREG(sb.st_mode)) {
             s->file_size = (int64_t)sb.st_size;
             int nt = p->cfg.inflate_threads;
-            if (const char* e = getenv("BSQ_INFLATE_THREADS")) nt = atoi(e);
             if (nt <= 0) nt = (int)std::max(1u, std::thread::hardware_concurrency());
             s->io_threads = std::min(nt, 8);
         }
@@ -1051,6 +1133,15 @@ extern "C" bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t s
     // room in front of every pinned region for the previous region's unconsumed tail (a larger tail takes the
     // `big` path of bsq_stream_next)
     s->carry_cap = std::max<uint64_t>(std::min<uint64_t>(s->region_bytes / 4, 64ull << 20), 4096);
+    if (s->gpu_inflate) {
+        s->zcap = std::max<uint64_t>(s->region_bytes / 2 + (1ull << 20), 256ull << 10);
+        for (auto& z : s->zb) {
+            cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&z.mem), s->zcap + 64, cudaHostAllocDefault);
+            if (e != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, e, "cudaHostAlloc(compressed region)"); }
+        }
+        cudaError_t e = opt_in_smem(k_inflate_members, sizeof(InflateTables) * kInfWarps);
+        if (e != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, e, "k_inflate_members shared memory"); }
+    } else
     for (auto& b : s->buf) {
         cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&b.mem), s->carry_cap + s->region_bytes + 64, cudaHostAllocDefault);
         if (e != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, e, "cudaHostAlloc(stream region)"); }
@@ -1072,7 +1163,32 @@ extern "C" void bsq_stream_close(bsq_stream* s) {
     if (s->fp) fclose(s->fp);
     if (s->zfp) fclose(s->zfp);
     for (auto& b : s->buf) if (b.mem) cudaFreeHost(b.mem);
+    for (auto& z : s->zb) if (z.mem) cudaFreeHost(z.mem);
+    if (s->p) cudaSetDevice(s->p->cfg.device_id);
+    s->zdev.release(); s->mdev.release(); s->sdev.release(); s->rdev[0].release(); s->rdev[1].release();
     delete s;
+}
+
+// keep batches whole across regions: the trailing partial batch (all of the region's records when it holds fewer than one
+// batch) is left unconsumed, to be re-presented with the next region
+static bsq_status trim_to_whole_batches(bsq_parser* p, uint32_t want, bool is_last, uint32_t m, bsq_pass_result* out) {
+    if (!is_last && out->stop.code == BSQ_OK && (want & BSQ_WANT_BATCHES) && out->n_records % m != 0) {
+        const int64_t keep = out->n_records - out->n_records % m;
+        int64_t cut = 0;
+        if (keep > 0) {
+            int wi = 0;
+            while (wi + 1 < p->res.n_windows && keep >= p->win[wi + 1].rec_base) ++wi;
+            uint32_t le = 0;
+            CK(cudaMemcpy(&le, p->win[wi].line_ends.as<uint32_t>() + 4ull * (keep - p->win[wi].rec_base), 4, cudaMemcpyDeviceToHost));
+            cut = (int64_t)p->win[wi].region_off - (int64_t)p->win[wi].wp.begin + (int64_t)(le + 1u);
+        }
+        out->n_records = keep;
+        out->n_batches = keep / m;
+        out->bytes_consumed = cut;
+        out->n_bases = -1;
+        p->res.n_records = keep; p->res.n_batches = keep / m; p->res.bytes_consumed = cut;
+    }
+    return BSQ_OK;
 }
 
 extern "C" bsq_status bsq_stream_next(bsq_stream* s, uint32_t want, bsq_pass_result* out) {
@@ -1102,6 +1218,67 @@ extern "C" bsq_status bsq_stream_next(bsq_stream* s, uint32_t want, bsq_pass_res
     const auto t1 = std::chrono::steady_clock::now();
     s->st.wait_reader_s += std::chrono::duration<double>(t1 - t0).count();
     if (s->read_error) { p->last_error = "read / inflate error"; s->finished = true; return BSQ_E_IO; }
+    if (s->gpu_inflate) {
+        // ---- compressed members -> device -> k_inflate_members -> pass over the device region ----
+        bsq_stream::ZBuf& z = s->zb[s->cur];
+        const int nxt = s->rcur ^ 1;
+        const uint64_t n = s->dev_carry_len + z.out_bytes;
+        CK(s->rdev[nxt].ensure(n + 256, 1 << 20));
+        uint8_t* region = s->rdev[nxt].as<uint8_t>();
+        if (s->dev_carry_len)   // the unconsumed tail of the previous region, device to device
+            CK(cudaMemcpyAsync(region, s->rdev[s->rcur].as<uint8_t>() + s->dev_carry_off, s->dev_carry_len, cudaMemcpyDeviceToDevice, p->stream));
+        const uint32_t nm = (uint32_t)z.members.size();
+        if (nm) {
+            CK(s->zdev.ensure(z.n + 64, 1 << 20));
+            CK(s->mdev.ensure(sizeof(InflateMember) * nm, 1 << 16));
+            CK(s->sdev.ensure(4ull * nm, 1 << 12));
+            CK(cudaEventRecord(p->ev[0], p->stream));
+            CK(cudaMemcpyAsync(s->zdev.p, z.mem, z.n, cudaMemcpyHostToDevice, p->stream));
+            CK(cudaMemcpyAsync(s->mdev.p, z.members.data(), sizeof(InflateMember) * nm, cudaMemcpyHostToDevice, p->stream));
+            CK(cudaEventRecord(p->ev[1], p->stream));
+            const uint32_t grid = (nm + kInfWarps - 1) / kInfWarps;
+            k_inflate_members<<<grid, kInfWarps * 32, sizeof(InflateTables) * kInfWarps, p->stream>>>(
+                s->zdev.as<uint8_t>(), region + s->dev_carry_len, s->mdev.as<InflateMember>(), nm, s->sdev.as<uint32_t>());
+            k_crc32_members<<<grid, kInfWarps * 32, 0, p->stream>>>(region + s->dev_carry_len, s->mdev.as<InflateMember>(), nm,
+                                                                     s->sdev.as<uint32_t>());
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(p->ev[2], p->stream));
+            s->status_host.resize(nm);
+            CK(cudaMemcpyAsync(s->status_host.data(), s->sdev.p, 4ull * nm, cudaMemcpyDeviceToHost, p->stream));
+            CK(cudaStreamSynchronize(p->stream));
+            float ms_copy = 0.f, ms_inf = 0.f;
+            cudaEventElapsedTime(&ms_copy, p->ev[0], p->ev[1]);
+            cudaEventElapsedTime(&ms_inf, p->ev[1], p->ev[2]);
+            s->st.h2d_s += ms_copy * 1e-3; s->st.inflate_s += ms_inf * 1e-3; s->st.compressed_bytes += z.n;
+            for (uint32_t i = 0; i < nm; ++i)
+                if (s->status_host[i] != 0u) {
+                    char t[128];
+                    snprintf(t, sizeof t, "BGZF member %u of the region does not inflate (status %u)", i, s->status_host[i]);
+                    p->last_error = t; s->finished = true;
+                    return BSQ_E_IO;
+                }
+        }
+        const bool is_last = b->eof;
+        const uint32_t m = (uint32_t)p->cfg.batch_size;
+        uint32_t w = want;
+        if (!is_last && (want & BSQ_WANT_BATCHES)) w |= BSQ_WANT_OFFSETS;   // the cut between regions needs offsets
+        InputFeed none;
+        bsq_status rc = run_pass(p, region, n, s->stream_pos, s->records_done, is_last ? 1 : 0, w, kWindowMax, none, out);
+        if (rc != BSQ_OK) { s->finished = true; return rc; }
+        rc = trim_to_whole_batches(p, want, is_last, m, out);
+        if (rc != BSQ_OK) { s->finished = true; return rc; }
+        s->rcur = nxt;
+        s->region_dev_n = n; s->region_host_valid = false;
+        s->region_ptr = nullptr; s->region_n = n;
+        s->st.parse_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+        s->st.regions += 1;
+        const uint64_t consumed = (uint64_t)out->bytes_consumed;
+        s->dev_carry_off = consumed; s->dev_carry_len = n - consumed;
+        s->stream_pos += (int64_t)consumed;
+        s->records_done += out->n_records;
+        if (out->stop.code != BSQ_OK) s->finished = true;
+        return BSQ_OK;
+    }
     uint8_t* region;
     if (s->carry.size() <= s->carry_cap) {
         region = b->mem + s->carry_cap - s->carry.size();
@@ -1122,24 +1299,8 @@ extern "C" bsq_status bsq_stream_next(bsq_stream* s, uint32_t want, bsq_pass_res
     if (!is_last && (want & BSQ_WANT_BATCHES)) w |= BSQ_WANT_OFFSETS;   // the cut between regions needs offsets
     bsq_status rc = bsq_parse_host(p, region, n, s->stream_pos, s->records_done, is_last ? 1 : 0, w, out);
     if (rc != BSQ_OK) { s->finished = true; return rc; }
-    if (!is_last && out->stop.code == BSQ_OK && (want & BSQ_WANT_BATCHES) && out->n_records % m != 0) {
-        // keep batches whole across regions: the trailing partial batch (all of the region's records when it holds
-        // fewer than one batch) is re-presented with the next region
-        const int64_t keep = out->n_records - out->n_records % m;
-        int64_t cut = 0;
-        if (keep > 0) {
-            int wi = 0;
-            while (wi + 1 < p->res.n_windows && keep >= p->win[wi + 1].rec_base) ++wi;
-            uint32_t le = 0;
-            CK(cudaMemcpy(&le, p->win[wi].line_ends.as<uint32_t>() + 4ull * (keep - p->win[wi].rec_base), 4, cudaMemcpyDeviceToHost));
-            cut = (int64_t)p->win[wi].region_off - (int64_t)p->win[wi].wp.begin + (int64_t)(le + 1u);
-        }
-        out->n_records = keep;
-        out->n_batches = keep / m;
-        out->bytes_consumed = cut;
-        out->n_bases = -1;
-        p->res.n_records = keep; p->res.n_batches = keep / m; p->res.bytes_consumed = cut;
-    }
+    rc = trim_to_whole_batches(p, want, is_last, m, out);
+    if (rc != BSQ_OK) { s->finished = true; return rc; }
     s->region_ptr = region; s->region_n = n;
     s->st.parse_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
     s->st.regions += 1;
@@ -1156,11 +1317,32 @@ extern "C" bsq_status bsq_stream_next(bsq_stream* s, uint32_t want, bsq_pass_res
     return BSQ_OK;
 }
 
-extern "C" const uint8_t* bsq_stream_region(const bsq_stream* s, uint64_t* n, int64_t* stream_offset, int64_t* first_record) {
+extern "C" void bsq_stream_region_info(const bsq_stream* s, uint64_t* n, int64_t* stream_offset, int64_t* first_record) {
+    if (n) *n = (s && s->cur >= 0) ? s->region_n : 0;
+    if (stream_offset) *stream_offset = (s && s->cur >= 0) ? s->p->pass_stream_offset : 0;
+    if (first_record) *first_record = (s && s->cur >= 0) ? s->records_done - s->p->res.n_records : 0;
+}
+
+extern "C" const uint8_t* bsq_stream_region(const bsq_stream* cs, uint64_t* n, int64_t* stream_offset, int64_t* first_record) {
+    bsq_stream* s = const_cast<bsq_stream*>(cs);
     if (!s || s->cur < 0) return nullptr;
     if (n) *n = s->region_n;
     if (stream_offset) *stream_offset = s->p->pass_stream_offset;
     if (first_record) *first_record = s->records_done - s->p->res.n_records;
+    if (s->gpu_inflate) {
+        // the region was inflated on the device: its bytes come to the host only on this request
+        if (!s->region_host_valid) {
+            s->region_host.resize(s->region_dev_n ? s->region_dev_n : 1);
+            cudaSetDevice(s->p->cfg.device_id);
+            if (s->region_dev_n &&
+                cudaMemcpy(s->region_host.data(), s->rdev[s->rcur].p, s->region_dev_n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            s->region_host_valid = true;
+        }
+        return s->region_host.data();
+    }
     return s->region_ptr;
 }
 

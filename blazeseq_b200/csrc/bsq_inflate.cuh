@@ -1,0 +1,390 @@
+// bsq_inflate.cuh -- DEFLATE (RFC 1951) on the device for BGZF input (SAM specification 4.1).
+//
+// The reference reads gzip input through RapidgzipReader(parallelism) (blazeseq/io/readers.mojo:380-443), a
+// parallel decoder on host threads.  A BGZF file is a series of gzip members of <= 64 KiB of payload each,
+// every one an independent DEFLATE stream with its compressed size in the header and its inflated size in
+// the trailer -- tens of thousands of independent streams per GiB.  Here the COMPRESSED members cross PCIe
+// and ONE WARP inflates ONE member straight into the parse window in HBM:
+//
+//   lane 0 owns the bit reader and the Huffman tables of the member (shared memory, rebuilt per block) and
+//   decodes symbols; literals are single byte stores; for a match the (length, distance) pair is broadcast
+//   and the whole warp copies it (LZ77 history is the member's own output, read back from L1 / L2);
+//   stored blocks are warp copies as well.
+//
+// The decode chain of one member is serial by nature; the parallelism is across members (a 256 MiB region is
+// ~4,000 warps of work).  Output is bit-exact zlib (tests compare with zlib.decompress on the reference's own
+// .bgz fixtures and synthetic files); a malformed or truncated member sets a per-member status and the
+// stream reports BSQ_E_IO.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bsq {
+
+struct InflateMember {
+    uint64_t src;        // byte offset of the member's DEFLATE payload in the compressed buffer
+    uint32_t src_len;    // payload bytes
+    uint32_t isize;      // inflated size (gzip ISIZE)
+    uint64_t dst;        // byte offset of the member's output in the destination buffer
+    uint32_t crc;        // gzip CRC-32 of the inflated bytes (checked by k_crc32_members)
+    uint32_t _pad;
+};
+
+constexpr int kInfWarps = 4;               // members (warps) per CTA
+constexpr int kLitBits = 10, kDistBits = 8;
+constexpr uint32_t kKindLit = 0u, kKindLen = 1u, kKindEob = 2u, kKindSlow = 3u;
+
+// Decode table entry: [value:16][extra bits:8][kind:4][code length:4]; code length 0 = no such code.
+__device__ __forceinline__ uint32_t inf_entry(uint32_t value, uint32_t extra, uint32_t kind, uint32_t len) {
+    return (value << 16) | (extra << 8) | (kind << 4) | len;
+}
+
+__device__ const uint16_t kInfLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115,
+                                             131, 163, 195, 227, 258};
+__device__ const uint8_t kInfLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__device__ const uint16_t kInfDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537,
+                                              2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__device__ const uint8_t kInfDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__device__ const uint8_t kInfClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+struct InflateTables {
+    uint32_t lit[1 << kLitBits];
+    uint32_t dist[1 << kDistBits];
+    // canonical form for codes longer than the lookup width (puff-style): symbols ordered by (length, symbol)
+    uint16_t lit_sym[288], dist_sym[32];
+    uint16_t lit_count[16], dist_count[16];
+    uint8_t lens[320];                     // code lengths of the block being set up
+};
+
+struct BitReader {
+    const uint32_t* wp;                    // next word to fetch
+    const uint32_t* wend;                  // one past the last word that holds payload bytes
+    uint64_t buf;
+    uint32_t cnt;                          // valid bits in buf
+    uint32_t nextw;                        // prefetched word
+    uint64_t consumed;                     // bits consumed so far
+};
+
+__device__ __forceinline__ void br_init(BitReader& b, const uint8_t* p, uint32_t nbytes) {
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+    b.wp = reinterpret_cast<const uint32_t*>(p - a);
+    b.wend = reinterpret_cast<const uint32_t*>(p - a) + ((a + nbytes + 3u) >> 2);
+    const uint32_t first = b.wp < b.wend ? __ldg(b.wp) : 0u;
+    ++b.wp;
+    b.buf = (uint64_t)(first >> (8u * a));
+    b.cnt = 32u - 8u * a;
+    b.nextw = b.wp < b.wend ? __ldg(b.wp) : 0u;
+    ++b.wp;
+    b.consumed = 0;
+}
+// at least 33 valid bits afterwards
+__device__ __forceinline__ void br_fill(BitReader& b) {
+    if (b.cnt <= 32u) {
+        b.buf |= (uint64_t)b.nextw << b.cnt;
+        b.cnt += 32u;
+        b.nextw = b.wp < b.wend ? __ldg(b.wp) : 0u;   // (past the end: zeros; the overrun is caught by `consumed`)
+        ++b.wp;
+    }
+}
+__device__ __forceinline__ uint32_t br_peek(const BitReader& b, uint32_t n) { return (uint32_t)b.buf & ((1u << n) - 1u); }
+__device__ __forceinline__ void br_skip(BitReader& b, uint32_t n) { b.buf >>= n; b.cnt -= n; b.consumed += n; }
+__device__ __forceinline__ uint32_t br_take(BitReader& b, uint32_t n) {
+    const uint32_t v = br_peek(b, n);
+    br_skip(b, n);
+    return v;
+}
+
+__device__ __forceinline__ uint32_t inf_rev(uint32_t code, uint32_t len) { return __brev(code) >> (32u - len); }
+
+// Builds one decoding table from code lengths (lane 0).  Returns false for an over-subscribed set; an incomplete
+// set is accepted when it is the single-code case RFC 1951 allows (or leaves unused entries = invalid codes).
+__device__ bool inf_build(const uint8_t* lens, uint32_t n, uint32_t* tab, uint32_t tbits, uint16_t* sym, uint16_t* count,
+                          bool is_dist) {
+    uint32_t offs[16];
+    for (int i = 0; i < 16; ++i) count[i] = 0;
+    for (uint32_t s = 0; s < n; ++s) count[lens[s]]++;
+    count[0] = 0;
+    int32_t left = 1;
+    for (int l = 1; l < 16; ++l) {
+        left = (left << 1) - (int32_t)count[l];
+        if (left < 0) return false;                       // over-subscribed
+    }
+    offs[1] = 0;
+    for (int l = 1; l < 15; ++l) offs[l + 1] = offs[l] + count[l];
+    for (uint32_t s = 0; s < n; ++s)
+        if (lens[s]) sym[offs[lens[s]]++] = (uint16_t)s;
+    for (uint32_t i = 0; i < (1u << tbits); ++i) tab[i] = 0u;
+    // canonical codes in (length, symbol) order
+    uint32_t code = 0, idx = 0;
+    for (uint32_t l = 1; l < 16; ++l) {
+        for (uint32_t k = 0; k < count[l]; ++k, ++idx, ++code) {
+            const uint32_t s = sym[idx];
+            uint32_t e;
+            if (is_dist) {
+                if (s >= 30u) { e = 0u; }
+                else e = inf_entry(kInfDistBase[s], kInfDistExtra[s], kKindLen, l <= tbits ? l : 0u);
+            } else if (s < 256u) e = inf_entry(s, 0u, kKindLit, l <= tbits ? l : 0u);
+            else if (s == 256u) e = inf_entry(0u, 0u, kKindEob, l <= tbits ? l : 0u);
+            else if (s < 286u) e = inf_entry(kInfLenBase[s - 257u], kInfLenExtra[s - 257u], kKindLen, l <= tbits ? l : 0u);
+            else e = 0u;
+            if (l <= tbits) {
+                if (e != 0u)
+                    for (uint32_t r = inf_rev(code, l); r < (1u << tbits); r += 1u << l) tab[r] = e;
+            } else {
+                // a long code: every table slot that shares its first tbits bits takes the slow (canonical) path
+                const uint32_t r = inf_rev(code, l) & ((1u << tbits) - 1u);
+                tab[r] = inf_entry(0u, 0u, kKindSlow, 0u) | 15u;   // (length field only marks the entry as used)
+            }
+        }
+        code <<= 1;
+    }
+    return true;
+}
+
+// canonical decode, one bit at a time (codes longer than the lookup width); returns the symbol or -1
+__device__ int32_t inf_slow(BitReader& b, const uint16_t* sym, const uint16_t* count) {
+    int32_t code = 0, first = 0, index = 0;
+    for (int l = 1; l < 16; ++l) {
+        code |= (int32_t)br_take(b, 1);
+        const int32_t c = count[l];
+        if (code - c < first) return sym[index + (code - first)];
+        index += c; first += c; first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+// One warp per member.  status[m]: 0 ok, 1 bad block type / table, 2 output overrun or bad distance,
+// 3 input overrun, 4 inflated size differs from ISIZE.
+__global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members(const uint8_t* __restrict__ zbuf, uint8_t* __restrict__ out,
+                                                                  const InflateMember* __restrict__ members, uint32_t n_members,
+                                                                  uint32_t* __restrict__ status) {
+    extern __shared__ __align__(16) uint8_t inf_smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t m = blockIdx.x * kInfWarps + warp;
+    if (m >= n_members) return;
+    InflateTables& T = reinterpret_cast<InflateTables*>(inf_smem)[warp];
+    const InflateMember M = members[m];
+    uint8_t* const dst = out + M.dst;
+    const uint32_t cap = M.isize;
+    BitReader br;
+    uint32_t pos = 0, err = 0;
+    if (lane == 0) br_init(br, zbuf + M.src, M.src_len);
+    bool last = false;
+    int tables = 0;                            // 0 none, 1 fixed, 2 dynamic (lane 0)
+    while (!last && err == 0u) {
+        // ---- block header (lane 0) ----
+        uint32_t btype = 0, stored_len = 0, stored_src = 0;
+        if (lane == 0) {
+            br_fill(br);
+            last = br_take(br, 1) != 0u;
+            btype = br_take(br, 2);
+            if (btype == 0u) {
+                br_skip(br, br.cnt & 7u);                             // to the byte boundary
+                br_fill(br);
+                const uint32_t len = br_take(br, 16);
+                br_fill(br);
+                const uint32_t nlen = br_take(br, 16);
+                if ((len ^ nlen) != 0xFFFFu) err = 1u;
+                stored_len = len;
+                stored_src = (uint32_t)(br.consumed >> 3);            // payload offset of the raw bytes
+            } else if (btype == 1u) {
+                if (tables != 1) {
+                    for (int s = 0; s < 144; ++s) T.lens[s] = 8;
+                    for (int s = 144; s < 256; ++s) T.lens[s] = 9;
+                    for (int s = 256; s < 280; ++s) T.lens[s] = 7;
+                    for (int s = 280; s < 288; ++s) T.lens[s] = 8;
+                    inf_build(T.lens, 288, T.lit, kLitBits, T.lit_sym, T.lit_count, false);
+                    for (int s = 0; s < 30; ++s) T.lens[s] = 5;
+                    inf_build(T.lens, 30, T.dist, kDistBits, T.dist_sym, T.dist_count, true);
+                    tables = 1;
+                }
+            } else if (btype == 2u) {
+                const uint32_t hlit = br_take(br, 5) + 257u, hdist = br_take(br, 5) + 1u, hclen = br_take(br, 4) + 4u;
+                if (hlit > 286u || hdist > 30u) err = 1u;
+                uint8_t* cl = T.lens + 300;                             // 19 code-length code lengths
+                for (int i = 0; i < 19; ++i) cl[i] = 0;
+                for (uint32_t i = 0; i < hclen && err == 0u; ++i) { br_fill(br); cl[kInfClOrder[i]] = (uint8_t)br_take(br, 3); }
+                // the code-length code shares the distance table's storage (7-bit lookup)
+                if (err == 0u && !inf_build(cl, 19, T.dist, 7, T.dist_sym, T.dist_count, false)) err = 1u;
+                uint32_t i = 0;
+                while (i < hlit + hdist && err == 0u) {
+                    br_fill(br);
+                    const uint32_t e = T.dist[br_peek(br, 7)];
+                    if ((e & 15u) == 0u || ((e >> 4) & 15u) != kKindLit) { err = 1u; break; }
+                    br_skip(br, e & 15u);
+                    const uint32_t s = e >> 16;
+                    if (s < 16u) { T.lens[i++] = (uint8_t)s; continue; }
+                    uint32_t rep, val = 0;
+                    if (s == 16u) { if (i == 0u) { err = 1u; break; } val = T.lens[i - 1]; rep = 3u + br_take(br, 2); }
+                    else if (s == 17u) rep = 3u + br_take(br, 3);
+                    else rep = 11u + br_take(br, 7);
+                    if (i + rep > hlit + hdist) { err = 1u; break; }
+                    while (rep--) T.lens[i++] = (uint8_t)val;
+                }
+                if (err == 0u && T.lens[256] == 0) err = 1u;            // no end-of-block code
+                if (err == 0u) {
+                    // distance lengths follow the literal/length lengths: move them out before lens is reused
+                    uint8_t dl[32];
+                    for (uint32_t k = 0; k < 32u; ++k) dl[k] = k < hdist ? T.lens[hlit + k] : 0;
+                    if (!inf_build(T.lens, hlit, T.lit, kLitBits, T.lit_sym, T.lit_count, false)) err = 1u;
+                    for (uint32_t k = 0; k < 32u; ++k) T.lens[k] = dl[k];
+                    if (err == 0u && !inf_build(T.lens, hdist, T.dist, kDistBits, T.dist_sym, T.dist_count, true)) err = 1u;
+                    tables = 2;
+                }
+            } else {
+                err = 1u;
+            }
+        }
+        btype = __shfl_sync(0xFFFFFFFFu, btype, 0);
+        err = __shfl_sync(0xFFFFFFFFu, err, 0);
+        last = __shfl_sync(0xFFFFFFFFu, (uint32_t)last, 0) != 0u;
+        if (err != 0u) break;
+        if (btype == 0u) {
+            // ---- stored block: a warp copy ----
+            stored_len = __shfl_sync(0xFFFFFFFFu, stored_len, 0);
+            stored_src = __shfl_sync(0xFFFFFFFFu, stored_src, 0);
+            pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+            if (pos + stored_len > cap) { err = 2u; break; }
+            if (stored_src + stored_len > M.src_len) { err = 3u; break; }
+            const uint8_t* s = zbuf + M.src + stored_src;
+            for (uint32_t i = lane; i < stored_len; i += 32u) dst[pos + i] = s[i];
+            __syncwarp();
+            if (lane == 0) {
+                pos += stored_len;
+                br_init(br, s + stored_len, M.src_len - stored_src - stored_len);
+                br.consumed = (uint64_t)(stored_src + stored_len) * 8u;
+            }
+            continue;
+        }
+        // ---- compressed block: lane 0 decodes up to the next match, the warp copies it ----
+        while (true) {
+            uint32_t mlen = 0, mdist = 0, done = 0;
+            if (lane == 0) {
+                while (true) {
+                    br_fill(br);
+                    uint32_t e = T.lit[br_peek(br, kLitBits)];
+                    uint32_t kind = (e >> 4) & 15u;
+                    int32_t s = -1;
+                    if (kind == kKindSlow) {                              // a code longer than the table width
+                        s = inf_slow(br, T.lit_sym, T.lit_count);
+                        if (s < 0) { err = 1u; break; }
+                    } else {
+                        if ((e & 15u) == 0u) { err = 1u; break; }
+                        br_skip(br, e & 15u);
+                    }
+                    uint32_t base, extra;
+                    if (kind == kKindLit || (s >= 0 && s < 256)) {
+                        if (pos >= cap) { err = 2u; break; }
+                        dst[pos++] = (uint8_t)(s >= 0 ? (uint32_t)s : (e >> 16));
+                        continue;
+                    }
+                    if (kind == kKindEob || s == 256) { done = 1u; break; }
+                    if (s >= 0) {
+                        if (s >= 286) { err = 1u; break; }
+                        base = kInfLenBase[s - 257]; extra = kInfLenExtra[s - 257];
+                    } else {
+                        base = e >> 16; extra = (e >> 8) & 255u;
+                    }
+                    mlen = base + br_take(br, extra);
+                    br_fill(br);
+                    e = T.dist[br_peek(br, kDistBits)];
+                    kind = (e >> 4) & 15u;
+                    if (kind == kKindSlow) {
+                        const int32_t d = inf_slow(br, T.dist_sym, T.dist_count);
+                        if (d < 0 || d >= 30) { err = 1u; break; }
+                        base = kInfDistBase[d]; extra = kInfDistExtra[d];
+                    } else {
+                        if ((e & 15u) == 0u) { err = 1u; break; }
+                        br_skip(br, e & 15u);
+                        base = e >> 16; extra = (e >> 8) & 255u;
+                    }
+                    br_fill(br);
+                    mdist = base + br_take(br, extra);
+                    if (mdist > pos || pos + mlen > cap) err = 2u;
+                    break;
+                }
+            }
+            err = __shfl_sync(0xFFFFFFFFu, err, 0);
+            done = __shfl_sync(0xFFFFFFFFu, done, 0);
+            if (err != 0u || done != 0u) break;
+            mlen = __shfl_sync(0xFFFFFFFFu, mlen, 0);
+            mdist = __shfl_sync(0xFFFFFFFFu, mdist, 0);
+            const uint32_t p0 = __shfl_sync(0xFFFFFFFFu, pos, 0);
+            __syncwarp();                                             // lane 0's literal stores are visible to the warp
+            const uint8_t* src = dst + p0 - mdist;
+            if (mdist >= mlen) {
+                for (uint32_t i = lane; i < mlen; i += 32u) dst[p0 + i] = src[i];
+            } else {
+                for (uint32_t i = lane; i < mlen; i += 32u) dst[p0 + i] = src[i % mdist];   // the pattern repeats
+            }
+            __syncwarp();
+            if (lane == 0) pos = p0 + mlen;
+        }
+    }
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+    uint32_t over = 0;
+    if (lane == 0) over = br.consumed > (uint64_t)M.src_len * 8u ? 1u : 0u;
+    over = __shfl_sync(0xFFFFFFFFu, over, 0);
+    if (lane == 0) {
+        uint32_t st = err;
+        if (st == 0u && over) st = 3u;
+        if (st == 0u && pos != cap) st = 4u;
+        status[m] = st;
+    }
+}
+
+// CRC-32 (gzip, reflected 0xEDB88320) of every member's inflated bytes: one warp per member, each lane a
+// contiguous slice, the slices' CRCs combined with x^(8 n) mod P multiplications.
+__device__ __forceinline__ uint32_t crc_mul(uint32_t a, uint32_t b) {      // a * b mod P, bit-reflected operands
+    uint32_t p = 0;
+    for (int i = 0; i < 32; ++i) {
+        if (a & 0x80000000u) p ^= b;
+        a <<= 1;
+        b = (b >> 1) ^ ((b & 1u) ? 0xEDB88320u : 0u);
+    }
+    return p;
+}
+__device__ __forceinline__ uint32_t crc_xpow8n(uint32_t n) {               // x^(8 n) mod P
+    uint32_t r = 0x80000000u, base = 0x00800000u;                          // 1, x^8
+    while (n) {
+        if (n & 1u) r = crc_mul(r, base);
+        base = crc_mul(base, base);
+        n >>= 1;
+    }
+    return r;
+}
+__global__ void __launch_bounds__(kInfWarps * 32) k_crc32_members(const uint8_t* __restrict__ out, const InflateMember* __restrict__ members,
+                                                                uint32_t n_members, uint32_t* __restrict__ status) {
+    __shared__ uint32_t tab[256];
+    for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
+        tab[i] = c;
+    }
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t m = blockIdx.x * kInfWarps + warp;
+    if (m >= n_members) return;
+    const InflateMember M = members[m];
+    // lane 0 takes the first per + (n mod 32) bytes, every other lane `per` bytes: all right-hand operands of the
+    // combine tree are multiples of `per` long, so one power of x serves a whole level
+    const uint32_t n = M.isize, per = n / 32u, rem = n - 32u * per;
+    const uint32_t a = lane == 0u ? 0u : rem + lane * per, b = rem + (lane + 1u) * per;
+    const uint8_t* p = out + M.dst;
+    uint32_t c = 0;                                                        // raw CRC register of the slice (init 0)
+    for (uint32_t i = a; i < b; ++i) c = tab[(c ^ p[i]) & 255u] ^ (c >> 8);
+    // crc(A || B) = crc(A) * x^(8 |B|) + crc(B) on raw (init 0, no final xor) registers
+    uint32_t xp = crc_xpow8n(per);                                         // x^(8 per), squared per level
+    for (uint32_t d = 1; d < 32u; d <<= 1) {
+        const uint32_t c2 = __shfl_down_sync(0xFFFFFFFFu, c, d);
+        if ((lane & (2u * d - 1u)) == 0u) c = crc_mul(c, xp) ^ c2;
+        xp = crc_mul(xp, xp);
+    }
+    if (lane == 0) {
+        // standard CRC = raw(init 0xFFFFFFFF) ^ 0xFFFFFFFF, and raw(init I) = raw(init 0) ^ I * x^(8 n)
+        const uint32_t crc = c ^ crc_mul(0xFFFFFFFFu, crc_xpow8n(n)) ^ 0xFFFFFFFFu;
+        if (status[m] == 0u && crc != M.crc) status[m] = 5u;
+    }
+}
+
+}  // namespace bsq

@@ -363,7 +363,7 @@ class GpuParser:
     def __init__(self, check_ascii=False, check_quality=False, schema: QualitySchema | None = None,
                  batch_size=DEFAULT_BATCH_SIZE, device_id=0, buffer_capacity=DEFAULT_CAPACITY,
                  buffer_max_capacity=MAX_CAPACITY, buffer_growth_enabled=False, h2d_chunk_bytes=None,
-                 force_id_slow_path=False, inflate_threads=0, compat_q5_width=0):
+                 force_id_slow_path=False, inflate_threads=0, compat_q5_width=0, host_inflate=False):
         L = capi.lib()
         cfg = capi.default_config()
         cfg.device_id = device_id
@@ -379,6 +379,7 @@ class GpuParser:
         cfg.inflate_threads = int(inflate_threads)   # BGZF members of a stream are inflated by this many host threads (0 = all)
         # reproduce the reference's quality check as written for a SIMD width of W bytes (record.mojo:90-102)
         cfg.compat_q5_width = int(compat_q5_width)
+        cfg.host_inflate = int(host_inflate)       # BGZF members inflated by host threads instead of k_inflate_members
         self.cfg = cfg
         self.generation = 0   # bumped by every pass: DeviceFastqBatch views of earlier passes are stale
         self._h = C.c_void_p()
@@ -496,20 +497,37 @@ class GpuParser:
                    self._h, "bsq_stream_open")
         return h
 
+    def stream_next_result(self, stream, want: int):
+        """bsq_stream_next without touching the region's bytes (a region inflated on the device stays there)."""
+        r = capi.PassResult()
+        self.generation += 1
+        capi.check(capi.lib().bsq_stream_next(stream, want, C.byref(r)), self._h, "bsq_stream_next")
+        self.result = r
+        return r, None, None
+
     def stream_next(self, stream, want: int):
         """Parses the next region of a file stream; returns (PassResult, region bytes as a numpy view,
         stream offset of the region, records before it)."""
         r = capi.PassResult()
         self.generation += 1
         capi.check(capi.lib().bsq_stream_next(stream, want, C.byref(r)), self._h, "bsq_stream_next")
+        self.result = r
+        n, off, first = self.stream_region_info(stream)
+        return r, self.stream_region_bytes(stream), off, first
+
+    def stream_region_info(self, stream):
+        """(bytes, stream offset, records before it) of the region last parsed, without fetching its bytes."""
+        n, off, first = C.c_uint64(), C.c_int64(), C.c_int64()
+        capi.lib().bsq_stream_region_info(stream, C.byref(n), C.byref(off), C.byref(first))
+        return int(n.value), int(off.value), int(first.value)
+
+    def stream_region_bytes(self, stream) -> np.ndarray:
+        """The region's bytes as a numpy view (a device-inflated region is copied to the host by this call)."""
         n, off, first = C.c_uint64(), C.c_int64(), C.c_int64()
         ptr = capi.lib().bsq_stream_region(stream, C.byref(n), C.byref(off), C.byref(first))
         if ptr and n.value:
-            data = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n.value,))
-        else:
-            data = np.zeros(0, np.uint8)
-        self.result = r
-        return r, data, off.value, first.value
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n.value,))
+        return np.zeros(0, np.uint8)
 
     def stream_stats(self, stream) -> capi.StreamStats:
         st = capi.StreamStats()
@@ -543,15 +561,24 @@ def shard_prefix(summaries, shard_bytes):
 class _Region:
     """One pass: the host bytes it covered and the tables it produced."""
 
-    def __init__(self, data: np.ndarray, stream_offset: int, first_record: int, result: capi.PassResult, want: int,
-                 is_last: bool = True):
-        self.data, self.stream_offset, self.first_record, self.want = data, stream_offset, first_record, want
+    def __init__(self, data, stream_offset: int, first_record: int, result: capi.PassResult, want: int,
+                 is_last: bool = True, size: Optional[int] = None):
+        # `data`: the region's bytes, or a function that fetches them (a region inflated on the device is only
+        # copied to the host when somebody looks at its bytes)
+        self._data, self.stream_offset, self.first_record, self.want = data, stream_offset, first_record, want
+        self.size = int(size if size is not None else data.size)
         self.is_last = is_last
         self.n = int(result.n_records)
         self.stop = result.stop
         self.consumed = int(result.bytes_consumed)
         self.n_windows = int(result.n_windows)
         self.offsets = None  # (start[5][n] int64 absolute in region, id_start, id_len)
+
+    @property
+    def data(self) -> np.ndarray:
+        if callable(self._data):
+            self._data = self._data()
+        return self._data
 
 
 class FastqParser:
@@ -565,7 +592,8 @@ class FastqParser:
 
     def __init__(self, reader: Reader, quality_schema: Optional[str] = None, *, batch_size: Optional[int] = None,
                  schema: str = "generic", config: Optional[ParserConfig] = None, device_id: int = 0,
-                 region_bytes: int = 1 << 30, _force_id_slow_path: bool = False, native_io: bool = True):
+                 region_bytes: int = 1 << 30, _force_id_slow_path: bool = False, native_io: bool = True,
+                 host_inflate: bool = False):
         self.config = config or ParserConfig()
         if quality_schema is not None:                      # parser.mojo:117
             self.quality_schema = parse_schema(quality_schema)
@@ -582,7 +610,7 @@ class FastqParser:
                               self._batch_size, device_id, self.config.buffer_capacity,
                               self.config.buffer_max_capacity, self.config.buffer_growth_enabled,
                               force_id_slow_path=_force_id_slow_path,
-                              inflate_threads=int(getattr(reader, "parallelism", 0) or 0))
+                              inflate_threads=int(getattr(reader, "parallelism", 0) or 0), host_inflate=host_inflate)
         self._carry = np.zeros(0, np.uint8)   # unconsumed tail of the previous region
         self._stream_pos = 0                  # stream offset of _carry[0]
         self._records_done = 0                # records of finished regions
@@ -632,10 +660,17 @@ class FastqParser:
     def _load_region(self, want: int):
         if self._stream is not None:
             self._gpu.set_batch_size(self._batch_size)
-            res, data, off, first = self._gpu.stream_next(self._stream, want)
+            res, _, _ = self._gpu.stream_next_result(self._stream, want)
+            stream, gpu, gen = self._stream, self._gpu, self._gpu.generation
+            n, off, first = gpu.stream_region_info(stream)
+
+            def fetch():
+                if gpu.generation != gen:
+                    raise BlazeSeqError("the region's bytes are gone: the parser has moved to another region")
+                return gpu.stream_region_bytes(stream)
             is_last = res.stop.code != capi.OK
-            reg = _Region(data, off, first, res, want | (0 if is_last else (capi.WANT_OFFSETS if want & capi.WANT_BATCHES else 0)),
-                          is_last)
+            reg = _Region(fetch, off, first, res, want | (0 if is_last else (capi.WANT_OFFSETS if want & capi.WANT_BATCHES else 0)),
+                          is_last, size=n)
             self._stream_done = is_last
             self._region = reg
             self._cursor = 0
@@ -721,7 +756,7 @@ class FastqParser:
                 return True
             if self._region.stop.code == capi.OK:
                 return True
-            unconsumed = self._region.data.size - self._region.consumed
+            unconsumed = self._region.size - self._region.consumed
             return unconsumed > 0 or not self._eof_seen
         if self._stream is not None:
             return not self._eof_seen

@@ -80,7 +80,8 @@ typedef struct bsq_config {
                                       W > 0: reproduce Validator._validate_quality_range as written
                                       (fastq/record.mojo:90-102) for a host whose SIMD width is W bytes: the first
                                       floor(n / W) * W quality bytes of a record also fail when b == UPPER */
-    int32_t _pad1;
+    int32_t host_inflate;          /* bsq_stream_*: 0 = the members of a BGZF file cross PCIe compressed and are inflated on the
+                                      device (k_inflate_members); 1 = by inflate_threads host threads (zlib) */
 } bsq_config;
 
 /* The first error of a pass, with the context the reference prints
@@ -195,8 +196,9 @@ bsq_status bsq_parse_host(bsq_parser* p, const uint8_t* host_bytes, uint64_t n,
  * carried in front of the next region, like BufferedReader._compact_from (:239-260). */
 typedef struct bsq_stream bsq_stream;
 #define BSQ_SOURCE_PLAIN 0
-#define BSQ_SOURCE_GZIP 1          /* gzip: BGZF members are inflated block-parallel by cfg.inflate_threads host
-                                      threads, any other gzip stream sequentially with zlib (gzread) */
+#define BSQ_SOURCE_GZIP 1          /* gzip: BGZF members are inflated on the device, one warp per member (or block-parallel by
+                                      cfg.inflate_threads host threads with cfg.host_inflate); any other gzip stream goes
+                                      through zlib on the reader thread */
 #define BSQ_SOURCE_AUTO 2          /* by suffix: .gz / .bgz -> gzip (python/blazeseq_parser.mojo:100-114) */
 
 typedef struct bsq_stream_stats {
@@ -205,6 +207,9 @@ typedef struct bsq_stream_stats {
     double reader_busy_s;          /* reader thread: time spent reading / inflating */
     double parse_s;                /* caller: time inside the GPU passes (incl. H2D) */
     double wait_reader_s;          /* caller: time blocked waiting for the reader thread */
+    double h2d_s;                  /* device-inflated BGZF: device time of the compressed bytes' H2D copies ... */
+    double inflate_s;              /* ... and of k_inflate_members + k_crc32_members (CUDA events) */
+    uint64_t compressed_bytes;     /* ... and the compressed bytes that crossed PCIe */
 } bsq_stream_stats;
 
 bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t source_kind, uint64_t region_bytes,
@@ -216,6 +221,9 @@ bsq_status bsq_stream_next(bsq_stream* s, uint32_t want, bsq_pass_result* out);
 /* Host bytes of the region just parsed (offset tables index these); *stream_offset = position of
  * byte 0 in the file's (decompressed) stream; *first_record = records before it. */
 const uint8_t* bsq_stream_region(const bsq_stream* s, uint64_t* n, int64_t* stream_offset, int64_t* first_record);
+/* The same numbers without the bytes: a region that was inflated on the device (BGZF) is copied to the host only by
+ * bsq_stream_region; callers that consume device batches never pay for that copy. */
+void bsq_stream_region_info(const bsq_stream* s, uint64_t* n, int64_t* stream_offset, int64_t* first_record);
 bsq_status bsq_stream_get_stats(const bsq_stream* s, bsq_stream_stats* out);
 void bsq_stream_close(bsq_stream* s);
 

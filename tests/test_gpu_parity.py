@@ -809,8 +809,8 @@ def test_bgzf_parallel_inflate(B, oracle, tmp_path, golden_dir):
     path = tmp_path / "p.fastq.gz"
     blob = bgzf.compress(data.tobytes(), level=1)
     path.write_bytes(blob)
-    for threads in (1, 3, 0):
-        p = B.FastqParser(B.RapidgzipReader(str(path), threads), "sanger", region_bytes=1 << 20,
+    for threads, host_inflate in ((1, True), (3, True), (0, True), (0, False)):
+        p = B.FastqParser(B.RapidgzipReader(str(path), threads), "sanger", region_bytes=1 << 20, host_inflate=host_inflate,
                           config=B.ParserConfig(check_ascii=True, check_quality=True))
         n = nb = 0
         for batch in p.batches(1000):
@@ -820,15 +820,87 @@ def test_bgzf_parallel_inflate(B, oracle, tmp_path, golden_dir):
     bad = bytearray(blob)
     bad[len(bad) // 2] ^= 0x55
     path.write_bytes(bytes(bad))
-    gpu = B.GpuParser(False, False, B.parse_schema("sanger"), 512)
-    st = gpu.stream_open(str(path), capi.SOURCE_AUTO, 1 << 20)
-    with pytest.raises(Exception):
-        while True:
+    for host_inflate in (True, False):
+        gpu = B.GpuParser(False, False, B.parse_schema("sanger"), 512, host_inflate=host_inflate)
+        st = gpu.stream_open(str(path), capi.SOURCE_AUTO, 1 << 20)
+        with pytest.raises(Exception):
+            while True:
+                res, region, off, first = gpu.stream_next(st, capi.WANT_OFFSETS)
+                if res.stop.code != capi.OK:
+                    break
+        gpu.stream_close(st)
+        gpu.close()
+
+
+def test_device_inflate_is_bit_exact_zlib(B, tmp_path, golden_dir):
+    """k_inflate_members against zlib on every kind of DEFLATE block: the reference's own .bgz fixtures, text at
+    compression levels 1 / 6 / 9, stored blocks (level 0 and incompressible bytes), fixed-Huffman blocks (tiny
+    members), long runs (overlapping matches), a byte alphabet that forces code lengths beyond the 10-bit lookup,
+    an empty file; a payload bit flip and a wrong CRC are both reported as BSQ_E_IO."""
+    import struct
+    import zlib
+    from blazeseq_b200 import _capi as capi, bgzf
+    rng = np.random.default_rng(11)
+
+    def inflate_on_device(blob: bytes):
+        path = tmp_path / "x.bgz"
+        path.write_bytes(blob)
+        gpu = B.GpuParser(batch_size=64)
+        st = gpu.stream_open(str(path), capi.SOURCE_GZIP, 256 << 20)
+        try:
             res, region, off, first = gpu.stream_next(st, capi.WANT_OFFSETS)
-            if res.stop.code != capi.OK:
-                break
-    gpu.stream_close(st)
-    gpu.close()
+            return bytes(region)
+        finally:
+            gpu.stream_close(st)
+            gpu.close()
+
+    def member(chunk: bytes, level: int, strategy=zlib.Z_DEFAULT_STRATEGY) -> bytes:
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+        d = c.compress(chunk) + c.flush()
+        assert len(d) + 26 <= 0x10000
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(d) + 25) + d +
+                struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+    eof = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    for f in ("example.fastq.bgz", "example_dos.fastq.bgz"):
+        blob = open(os.path.join(golden_dir, "corpus", f), "rb").read()
+        d = zlib.decompressobj(31)
+        exp = b""
+        rest = blob
+        while rest:                                  # every gzip member of the file
+            d = zlib.decompressobj(31)
+            exp += d.decompress(rest)
+            rest = d.unused_data
+        assert inflate_on_device(blob) == exp, f
+    text = b"".join(b"@read_%07d some/description here\nACGTTGCANNACGT%s\n+\nIIIIHHHHFFFF%s\n" % (
+        i, bytes(rng.choice(list(b"ACGT"), 80).astype(np.uint8)), bytes(rng.integers(35, 75, 80).astype(np.uint8)))
+        for i in range(40000))
+    skew = bytes(np.minimum(rng.geometric(0.02, 600000), 255).astype(np.uint8))     # ~250 symbols, very uneven: long codes
+    cases = {
+        "text level 1": (text, 1), "text level 6": (text, 6), "text level 9": (text, 9), "stored (level 0)": (text[:500000], 0),
+        "incompressible": (rng.integers(0, 256, 700001, dtype=np.uint8).tobytes(), 6),
+        "runs": (b"A" * 300000 + b"ab" * 100000 + b"xyz" * 70000 + bytes(200000), 6),
+        "skewed alphabet": (skew, 9),
+        "huffman only": (text[:400000], (6, zlib.Z_HUFFMAN_ONLY)), "fixed codes": (text[:300000], (6, zlib.Z_FIXED)),
+    }
+    for name, (data, level) in cases.items():
+        strategy = zlib.Z_DEFAULT_STRATEGY
+        if isinstance(level, tuple):
+            level, strategy = level
+        step = 0xFF00 if level else 60000
+        blob = b"".join(member(data[i:i + step], level, strategy) for i in range(0, len(data), step)) + eof
+        got = inflate_on_device(blob)
+        assert got == data, name
+    # tiny members (fixed Huffman), members of every size around the 32-lane slicing of the CRC kernel, empty input
+    tiny = [text[i * 97:i * 97 + n] for i, n in enumerate(list(range(1, 70)) + [255, 256, 257, 1023, 1024, 1025, 4097])]
+    assert inflate_on_device(b"".join(member(t, 6) for t in tiny) + eof) == b"".join(tiny)
+    assert inflate_on_device(eof) == b""
+    # damage: a flipped payload bit (caught by the decoder or by the CRC), a wrong CRC on intact data
+    good = b"".join(member(text[i:i + 0xFF00], 6) for i in range(0, 400000, 0xFF00)) + eof
+    flipped = bytearray(good); flipped[20000] ^= 0x10
+    wrong_crc = bytearray(good); first_len = struct.unpack_from("<H", good, 16)[0] + 1; wrong_crc[first_len - 8] ^= 1
+    for blob in (bytes(flipped), bytes(wrong_crc)):
+        with pytest.raises(capi.BsqLibraryError):
+            inflate_on_device(blob)
 
 
 @pytest.mark.parametrize("src", ["example", "synthetic"])
