@@ -241,6 +241,7 @@ def main():
     ap.add_argument("--shard-stream", action="store_true",
                     help="strong scaling: ONE stream of --gib cut at arbitrary byte offsets over the ranks (sharding.plan)")
     ap.add_argument("--gzip", action="store_true", help="configs[4]: .fastq.gz / BGZF files through the stream pipeline (--gib 4)")
+    ap.add_argument("--region-mib", type=int, default=256, help="--gzip: region size of the stream pipeline")
     ap.add_argument("--crlf", action="store_true", help="CRLF line ends: every id needs _strip_spaces (id strip pipeline)")
     ap.add_argument("--read-len", type=int, default=150, help="read length of the synthetic stream (record stride sweeps)")
     ap.add_argument("--id-digits", type=int, default=0, help="zero-padded id width (0: that of the stream's read count)")
@@ -440,7 +441,7 @@ def main():
 
     if args.gzip:
         gib = args.gib if args.gib != 10.0 else 4.0
-        leg = gzip_leg(gib)
+        leg = gzip_leg(gib, args.region_mib)
         clocks = sampler.stop()
         best = leg["bgzf_device_inflate"]
         if rank == 0:

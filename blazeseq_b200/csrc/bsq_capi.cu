@@ -1139,7 +1139,7 @@ extern "C" bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t s
             cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&z.mem), s->zcap + 64, cudaHostAllocDefault);
             if (e != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, e, "cudaHostAlloc(compressed region)"); }
         }
-        cudaError_t e = opt_in_smem(k_inflate_members, sizeof(InflateTables) * kInfWarps);
+        cudaError_t e = opt_in_smem(k_inflate_members, sizeof(InflateTables) * kInfPerCta);
         if (e != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, e, "k_inflate_members shared memory"); }
     } else
     for (auto& b : s->buf) {
@@ -1236,11 +1236,10 @@ extern "C" bsq_status bsq_stream_next(bsq_stream* s, uint32_t want, bsq_pass_res
             CK(cudaMemcpyAsync(s->zdev.p, z.mem, z.n, cudaMemcpyHostToDevice, p->stream));
             CK(cudaMemcpyAsync(s->mdev.p, z.members.data(), sizeof(InflateMember) * nm, cudaMemcpyHostToDevice, p->stream));
             CK(cudaEventRecord(p->ev[1], p->stream));
-            const uint32_t grid = (nm + kInfWarps - 1) / kInfWarps;
-            k_inflate_members<<<grid, kInfWarps * 32, sizeof(InflateTables) * kInfWarps, p->stream>>>(
+            k_inflate_members<<<(nm + kInfPerCta - 1) / kInfPerCta, kInfWarps * 32, sizeof(InflateTables) * kInfPerCta, p->stream>>>(
                 s->zdev.as<uint8_t>(), region + s->dev_carry_len, s->mdev.as<InflateMember>(), nm, s->sdev.as<uint32_t>());
-            k_crc32_members<<<grid, kInfWarps * 32, 0, p->stream>>>(region + s->dev_carry_len, s->mdev.as<InflateMember>(), nm,
-                                                                     s->sdev.as<uint32_t>());
+            k_crc32_members<<<(nm + kCrcWarps - 1) / kCrcWarps, kCrcWarps * 32, 0, p->stream>>>(
+                region + s->dev_carry_len, s->mdev.as<InflateMember>(), nm, s->sdev.as<uint32_t>());
             CK(cudaGetLastError());
             CK(cudaEventRecord(p->ev[2], p->stream));
             s->status_host.resize(nm);

@@ -30,11 +30,21 @@ struct InflateMember {
     uint32_t _pad;
 };
 
-constexpr int kInfWarps = 4;               // members (warps) per CTA
-constexpr int kLitBits = 10, kDistBits = 8;
-constexpr uint32_t kKindLit = 0u, kKindLen = 1u, kKindEob = 2u, kKindSlow = 3u;
+#ifndef BSQ_INF_LANES
+#define BSQ_INF_LANES 32
+#endif
+#ifndef BSQ_INF_WARPS
+#define BSQ_INF_WARPS 4
+#endif
+constexpr int kInfWarps = BSQ_INF_WARPS;   // warps per CTA
+constexpr int kInfLanes = BSQ_INF_LANES;   // lanes per member: one decodes, all copy
+constexpr int kInfPerWarp = 32 / kInfLanes;
+constexpr int kInfPerCta = kInfWarps * kInfPerWarp;   // members per CTA
+constexpr int kLitBits = 9, kDistBits = 7;
+// Decode table entry: [value:16][extra bits:8][kind:4][code length:4]
+constexpr uint32_t kKindLit = 0u, kKindLen = 1u, kKindEob = 2u, kKindSlow = 3u, kKindBad = 15u;
+constexpr uint32_t kEntryBad = kKindBad << 4;          // no such code
 
-// Decode table entry: [value:16][extra bits:8][kind:4][code length:4]; code length 0 = no such code.
 __device__ __forceinline__ uint32_t inf_entry(uint32_t value, uint32_t extra, uint32_t kind, uint32_t len) {
     return (value << 16) | (extra << 8) | (kind << 4) | len;
 }
@@ -54,40 +64,48 @@ struct InflateTables {
     uint16_t lit_sym[288], dist_sym[32];
     uint16_t lit_count[16], dist_count[16];
     uint8_t lens[320];                     // code lengths of the block being set up
+    uint8_t dl[32];                        // ... and the distance code lengths while the literal table is built
 };
 
 struct BitReader {
     const uint32_t* wp;                    // next word to fetch
     const uint32_t* wend;                  // one past the last word that holds payload bytes
+    const uint32_t* w0;                    // first word
     uint64_t buf;
     uint32_t cnt;                          // valid bits in buf
     uint32_t nextw;                        // prefetched word
-    uint64_t consumed;                     // bits consumed so far
+    uint32_t lead;                         // bits of the first word that precede the payload (8 x misalignment)
+    uint32_t base_bytes;                   // payload bytes before w0's payload start (after a stored block)
 };
 
-__device__ __forceinline__ void br_init(BitReader& b, const uint8_t* p, uint32_t nbytes) {
+__device__ __forceinline__ void br_init(BitReader& b, const uint8_t* p, uint32_t nbytes, uint32_t base_bytes) {
     const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
-    b.wp = reinterpret_cast<const uint32_t*>(p - a);
-    b.wend = reinterpret_cast<const uint32_t*>(p - a) + ((a + nbytes + 3u) >> 2);
+    b.w0 = b.wp = reinterpret_cast<const uint32_t*>(p - a);
+    b.wend = b.w0 + ((a + nbytes + 3u) >> 2);
     const uint32_t first = b.wp < b.wend ? __ldg(b.wp) : 0u;
     ++b.wp;
     b.buf = (uint64_t)(first >> (8u * a));
     b.cnt = 32u - 8u * a;
+    b.lead = 8u * a;
     b.nextw = b.wp < b.wend ? __ldg(b.wp) : 0u;
     ++b.wp;
-    b.consumed = 0;
+    b.base_bytes = base_bytes;
+}
+// payload bits consumed so far (the prefetched word is not in buf yet)
+__device__ __forceinline__ uint64_t br_consumed(const BitReader& b) {
+    return (uint64_t)b.base_bytes * 8u + (uint64_t)(b.wp - b.w0 - 1) * 32u - b.lead - b.cnt;
 }
 // at least 33 valid bits afterwards
 __device__ __forceinline__ void br_fill(BitReader& b) {
     if (b.cnt <= 32u) {
         b.buf |= (uint64_t)b.nextw << b.cnt;
         b.cnt += 32u;
-        b.nextw = b.wp < b.wend ? __ldg(b.wp) : 0u;   // (past the end: zeros; the overrun is caught by `consumed`)
+        b.nextw = b.wp < b.wend ? __ldg(b.wp) : 0u;   // (past the end: zeros; the overrun is caught by br_consumed)
         ++b.wp;
     }
 }
 __device__ __forceinline__ uint32_t br_peek(const BitReader& b, uint32_t n) { return (uint32_t)b.buf & ((1u << n) - 1u); }
-__device__ __forceinline__ void br_skip(BitReader& b, uint32_t n) { b.buf >>= n; b.cnt -= n; b.consumed += n; }
+__device__ __forceinline__ void br_skip(BitReader& b, uint32_t n) { b.buf >>= n; b.cnt -= n; }
 __device__ __forceinline__ uint32_t br_take(BitReader& b, uint32_t n) {
     const uint32_t v = br_peek(b, n);
     br_skip(b, n);
@@ -96,8 +114,8 @@ __device__ __forceinline__ uint32_t br_take(BitReader& b, uint32_t n) {
 
 __device__ __forceinline__ uint32_t inf_rev(uint32_t code, uint32_t len) { return __brev(code) >> (32u - len); }
 
-// Builds one decoding table from code lengths (lane 0).  Returns false for an over-subscribed set; an incomplete
-// set is accepted when it is the single-code case RFC 1951 allows (or leaves unused entries = invalid codes).
+// Builds one decoding table from code lengths (one lane).  Returns false for an over-subscribed set; an incomplete
+// set leaves unused entries (= invalid codes).
 __device__ bool inf_build(const uint8_t* lens, uint32_t n, uint32_t* tab, uint32_t tbits, uint16_t* sym, uint16_t* count,
                           bool is_dist) {
     uint32_t offs[16];
@@ -113,27 +131,23 @@ __device__ bool inf_build(const uint8_t* lens, uint32_t n, uint32_t* tab, uint32
     for (int l = 1; l < 15; ++l) offs[l + 1] = offs[l] + count[l];
     for (uint32_t s = 0; s < n; ++s)
         if (lens[s]) sym[offs[lens[s]]++] = (uint16_t)s;
-    for (uint32_t i = 0; i < (1u << tbits); ++i) tab[i] = 0u;
+    for (uint32_t i = 0; i < (1u << tbits); ++i) tab[i] = kEntryBad;
     // canonical codes in (length, symbol) order
     uint32_t code = 0, idx = 0;
     for (uint32_t l = 1; l < 16; ++l) {
         for (uint32_t k = 0; k < count[l]; ++k, ++idx, ++code) {
             const uint32_t s = sym[idx];
             uint32_t e;
-            if (is_dist) {
-                if (s >= 30u) { e = 0u; }
-                else e = inf_entry(kInfDistBase[s], kInfDistExtra[s], kKindLen, l <= tbits ? l : 0u);
-            } else if (s < 256u) e = inf_entry(s, 0u, kKindLit, l <= tbits ? l : 0u);
-            else if (s == 256u) e = inf_entry(0u, 0u, kKindEob, l <= tbits ? l : 0u);
-            else if (s < 286u) e = inf_entry(kInfLenBase[s - 257u], kInfLenExtra[s - 257u], kKindLen, l <= tbits ? l : 0u);
-            else e = 0u;
+            if (is_dist) e = s < 30u ? inf_entry(kInfDistBase[s], kInfDistExtra[s], kKindLen, l) : kEntryBad;
+            else if (s < 256u) e = inf_entry(s, 0u, kKindLit, l);
+            else if (s == 256u) e = inf_entry(0u, 0u, kKindEob, l);
+            else if (s < 286u) e = inf_entry(kInfLenBase[s - 257u], kInfLenExtra[s - 257u], kKindLen, l);
+            else e = kEntryBad;
             if (l <= tbits) {
-                if (e != 0u)
-                    for (uint32_t r = inf_rev(code, l); r < (1u << tbits); r += 1u << l) tab[r] = e;
+                for (uint32_t r = inf_rev(code, l); r < (1u << tbits); r += 1u << l) tab[r] = e;
             } else {
-                // a long code: every table slot that shares its first tbits bits takes the slow (canonical) path
-                const uint32_t r = inf_rev(code, l) & ((1u << tbits) - 1u);
-                tab[r] = inf_entry(0u, 0u, kKindSlow, 0u) | 15u;   // (length field only marks the entry as used)
+                // a long code: the table slot that holds its first tbits bits sends the decoder down the canonical path
+                tab[inf_rev(code, l) & ((1u << tbits) - 1u)] = inf_entry(0u, 0u, kKindSlow, 0u);
             }
         }
         code <<= 1;
@@ -153,40 +167,54 @@ __device__ int32_t inf_slow(BitReader& b, const uint16_t* sym, const uint16_t* c
     return -1;
 }
 
-// One warp per member.  status[m]: 0 ok, 1 bad block type / table, 2 output overrun or bad distance,
-// 3 input overrun, 4 inflated size differs from ISIZE.
+// kInfLanes lanes per member (kInfPerWarp members per warp): the group's first lane decodes, every lane of the group
+// copies.  Only one lane in kInfLanes does the serial Huffman work, so a warp instruction of the decode loop advances
+// kInfPerWarp members at once -- the kernel is bound by instruction issue, not by memory.
+// status[m]: 0 ok, 1 bad block type / table / code, 2 output overrun or bad distance, 3 input overrun, 4 inflated
+// size differs from ISIZE (5: CRC mismatch, set by k_crc32_members).
 __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members(const uint8_t* __restrict__ zbuf, uint8_t* __restrict__ out,
                                                                   const InflateMember* __restrict__ members, uint32_t n_members,
                                                                   uint32_t* __restrict__ status) {
     extern __shared__ __align__(16) uint8_t inf_smem[];
+    constexpr uint32_t kFull = 0xFFFFFFFFu;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t m = blockIdx.x * kInfWarps + warp;
-    if (m >= n_members) return;
-    InflateTables& T = reinterpret_cast<InflateTables*>(inf_smem)[warp];
-    const InflateMember M = members[m];
+    const uint32_t g = lane / kInfLanes, gl = lane % kInfLanes, lead = lane - gl;
+    const uint32_t m = (blockIdx.x * kInfWarps + warp) * kInfPerWarp + g;
+    const bool valid = m < n_members;
+    InflateTables& T = reinterpret_cast<InflateTables*>(inf_smem)[warp * kInfPerWarp + g];
+    InflateMember M{};
+    if (valid) M = members[m];
     uint8_t* const dst = out + M.dst;
+    const uint8_t* const src0 = zbuf + M.src;
     const uint32_t cap = M.isize;
-    BitReader br;
-    uint32_t pos = 0, err = 0;
-    if (lane == 0) br_init(br, zbuf + M.src, M.src_len);
-    bool last = false;
-    int tables = 0;                            // 0 none, 1 fixed, 2 dynamic (lane 0)
-    while (!last && err == 0u) {
-        // ---- block header (lane 0) ----
-        uint32_t btype = 0, stored_len = 0, stored_src = 0;
-        if (lane == 0) {
+    const bool leader = gl == 0u && valid;
+    BitReader br{};
+    uint32_t pos = 0, err = 0;            // (leader)
+    bool last = false, in_block = false, finished = false;   // (leader)
+    int tables = 0;                        // 0 none, 1 fixed, 2 dynamic (leader)
+    if (leader) br_init(br, src0, M.src_len, 0u);
+    bool done = !valid;                    // (whole group)
+    uint32_t pend_pos = 0xFFFFFFFFu;       // a match byte loaded but not yet stored (every lane)
+    uint8_t pend_val = 0;
+
+    while (true) {
+        // ---- block headers: the leaders that stand between two blocks ----
+        uint32_t st_len = 0, st_src = 0, st_go = 0;
+        if (leader && !done && !in_block && !finished && err == 0u) {
             br_fill(br);
             last = br_take(br, 1) != 0u;
-            btype = br_take(br, 2);
+            const uint32_t btype = br_take(br, 2);
             if (btype == 0u) {
                 br_skip(br, br.cnt & 7u);                             // to the byte boundary
                 br_fill(br);
                 const uint32_t len = br_take(br, 16);
                 br_fill(br);
                 const uint32_t nlen = br_take(br, 16);
+                st_src = (uint32_t)(br_consumed(br) >> 3);            // payload offset of the raw bytes
                 if ((len ^ nlen) != 0xFFFFu) err = 1u;
-                stored_len = len;
-                stored_src = (uint32_t)(br.consumed >> 3);            // payload offset of the raw bytes
+                else if (pos + len > cap) err = 2u;
+                else if (st_src + len > M.src_len) err = 3u;
+                else { st_len = len; st_go = 1u; }
             } else if (btype == 1u) {
                 if (tables != 1) {
                     for (int s = 0; s < 144; ++s) T.lens[s] = 8;
@@ -198,19 +226,20 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members(const uint8_
                     inf_build(T.lens, 30, T.dist, kDistBits, T.dist_sym, T.dist_count, true);
                     tables = 1;
                 }
+                in_block = true;
             } else if (btype == 2u) {
                 const uint32_t hlit = br_take(br, 5) + 257u, hdist = br_take(br, 5) + 1u, hclen = br_take(br, 4) + 4u;
                 if (hlit > 286u || hdist > 30u) err = 1u;
                 uint8_t* cl = T.lens + 300;                             // 19 code-length code lengths
                 for (int i = 0; i < 19; ++i) cl[i] = 0;
                 for (uint32_t i = 0; i < hclen && err == 0u; ++i) { br_fill(br); cl[kInfClOrder[i]] = (uint8_t)br_take(br, 3); }
-                // the code-length code shares the distance table's storage (7-bit lookup)
+                // the code-length code borrows the distance table's storage (7-bit lookup)
                 if (err == 0u && !inf_build(cl, 19, T.dist, 7, T.dist_sym, T.dist_count, false)) err = 1u;
                 uint32_t i = 0;
                 while (i < hlit + hdist && err == 0u) {
                     br_fill(br);
                     const uint32_t e = T.dist[br_peek(br, 7)];
-                    if ((e & 15u) == 0u || ((e >> 4) & 15u) != kKindLit) { err = 1u; break; }
+                    if ((e & 0xF0u) != 0u) { err = 1u; break; }        // not a (valid) symbol of the code-length code
                     br_skip(br, e & 15u);
                     const uint32_t s = e >> 16;
                     if (s < 16u) { T.lens[i++] = (uint8_t)s; continue; }
@@ -223,113 +252,116 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members(const uint8_
                 }
                 if (err == 0u && T.lens[256] == 0) err = 1u;            // no end-of-block code
                 if (err == 0u) {
-                    // distance lengths follow the literal/length lengths: move them out before lens is reused
-                    uint8_t dl[32];
-                    for (uint32_t k = 0; k < 32u; ++k) dl[k] = k < hdist ? T.lens[hlit + k] : 0;
+                    for (uint32_t k = 0; k < 32u; ++k) T.dl[k] = k < hdist ? T.lens[hlit + k] : 0;
                     if (!inf_build(T.lens, hlit, T.lit, kLitBits, T.lit_sym, T.lit_count, false)) err = 1u;
-                    for (uint32_t k = 0; k < 32u; ++k) T.lens[k] = dl[k];
-                    if (err == 0u && !inf_build(T.lens, hdist, T.dist, kDistBits, T.dist_sym, T.dist_count, true)) err = 1u;
+                    if (err == 0u && !inf_build(T.dl, hdist, T.dist, kDistBits, T.dist_sym, T.dist_count, true)) err = 1u;
                     tables = 2;
+                    in_block = true;
                 }
             } else {
                 err = 1u;
             }
         }
-        btype = __shfl_sync(0xFFFFFFFFu, btype, 0);
-        err = __shfl_sync(0xFFFFFFFFu, err, 0);
-        last = __shfl_sync(0xFFFFFFFFu, (uint32_t)last, 0) != 0u;
-        if (err != 0u) break;
-        if (btype == 0u) {
-            // ---- stored block: a warp copy ----
-            stored_len = __shfl_sync(0xFFFFFFFFu, stored_len, 0);
-            stored_src = __shfl_sync(0xFFFFFFFFu, stored_src, 0);
-            pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-            if (pos + stored_len > cap) { err = 2u; break; }
-            if (stored_src + stored_len > M.src_len) { err = 3u; break; }
-            const uint8_t* s = zbuf + M.src + stored_src;
-            for (uint32_t i = lane; i < stored_len; i += 32u) dst[pos + i] = s[i];
-            __syncwarp();
-            if (lane == 0) {
-                pos += stored_len;
-                br_init(br, s + stored_len, M.src_len - stored_src - stored_len);
-                br.consumed = (uint64_t)(stored_src + stored_len) * 8u;
-            }
-            continue;
+        // ---- stored blocks: a copy by the group ----
+        st_go = __shfl_sync(kFull, st_go, lead);
+        st_len = __shfl_sync(kFull, st_len, lead);
+        st_src = __shfl_sync(kFull, st_src, lead);
+        uint32_t p0 = __shfl_sync(kFull, pos, lead);
+        if (st_go != 0u)
+            for (uint32_t i = gl; i < st_len; i += kInfLanes) dst[p0 + i] = src0[st_src + i];
+        __syncwarp();
+        if (leader && st_go != 0u) {
+            pos += st_len;
+            br_init(br, src0 + st_src + st_len, M.src_len - st_src - st_len, st_src + st_len);
+            if (last) finished = true;
         }
-        // ---- compressed block: lane 0 decodes up to the next match, the warp copies it ----
-        while (true) {
-            uint32_t mlen = 0, mdist = 0, done = 0;
-            if (lane == 0) {
-                while (true) {
-                    br_fill(br);
-                    uint32_t e = T.lit[br_peek(br, kLitBits)];
-                    uint32_t kind = (e >> 4) & 15u;
-                    int32_t s = -1;
-                    if (kind == kKindSlow) {                              // a code longer than the table width
-                        s = inf_slow(br, T.lit_sym, T.lit_count);
-                        if (s < 0) { err = 1u; break; }
-                    } else {
-                        if ((e & 15u) == 0u) { err = 1u; break; }
-                        br_skip(br, e & 15u);
-                    }
-                    uint32_t base, extra;
-                    if (kind == kKindLit || (s >= 0 && s < 256)) {
+        // ---- compressed blocks: the leader decodes up to its next match ----
+        uint32_t mlen = 0, mdist = 0;
+        if (leader && !done && in_block && err == 0u) {
+            while (true) {
+                br_fill(br);
+                uint32_t e = T.lit[br_peek(br, kLitBits)];
+                if ((e & 0xF0u) == 0u) {                                  // a literal (the common case)
+                    br_skip(br, e & 15u);
+                    if (pos >= cap) { err = 2u; break; }
+                    dst[pos++] = (uint8_t)(e >> 16);
+                    continue;
+                }
+                uint32_t kind = (e >> 4) & 15u;
+                uint32_t base, extra;
+                if (kind == kKindSlow) {                                  // a code longer than the table width
+                    const int32_t s = inf_slow(br, T.lit_sym, T.lit_count);
+                    if (s < 0 || s >= 286) { err = 1u; break; }
+                    if (s < 256) {
                         if (pos >= cap) { err = 2u; break; }
-                        dst[pos++] = (uint8_t)(s >= 0 ? (uint32_t)s : (e >> 16));
+                        dst[pos++] = (uint8_t)s;
                         continue;
                     }
-                    if (kind == kKindEob || s == 256) { done = 1u; break; }
-                    if (s >= 0) {
-                        if (s >= 286) { err = 1u; break; }
-                        base = kInfLenBase[s - 257]; extra = kInfLenExtra[s - 257];
-                    } else {
-                        base = e >> 16; extra = (e >> 8) & 255u;
-                    }
-                    mlen = base + br_take(br, extra);
-                    br_fill(br);
-                    e = T.dist[br_peek(br, kDistBits)];
-                    kind = (e >> 4) & 15u;
-                    if (kind == kKindSlow) {
-                        const int32_t d = inf_slow(br, T.dist_sym, T.dist_count);
-                        if (d < 0 || d >= 30) { err = 1u; break; }
-                        base = kInfDistBase[d]; extra = kInfDistExtra[d];
-                    } else {
-                        if ((e & 15u) == 0u) { err = 1u; break; }
-                        br_skip(br, e & 15u);
-                        base = e >> 16; extra = (e >> 8) & 255u;
-                    }
-                    br_fill(br);
-                    mdist = base + br_take(br, extra);
-                    if (mdist > pos || pos + mlen > cap) err = 2u;
+                    if (s == 256) { in_block = false; if (last) finished = true; break; }
+                    base = kInfLenBase[s - 257]; extra = kInfLenExtra[s - 257];
+                } else if (kind == kKindLen) {
+                    br_skip(br, e & 15u);
+                    base = e >> 16; extra = (e >> 8) & 255u;
+                } else if (kind == kKindEob) {
+                    br_skip(br, e & 15u);
+                    in_block = false;
+                    if (last) finished = true;
                     break;
+                } else { err = 1u; break; }
+                mlen = base + br_take(br, extra);
+                br_fill(br);
+                e = T.dist[br_peek(br, kDistBits)];
+                kind = (e >> 4) & 15u;
+                if (kind == kKindLen) {
+                    br_skip(br, e & 15u);
+                    base = e >> 16; extra = (e >> 8) & 255u;
+                } else if (kind == kKindSlow) {
+                    const int32_t d = inf_slow(br, T.dist_sym, T.dist_count);
+                    if (d < 0 || d >= 30) { err = 1u; mlen = 0; break; }
+                    base = kInfDistBase[d]; extra = kInfDistExtra[d];
+                } else { err = 1u; mlen = 0; break; }
+                br_fill(br);
+                mdist = base + br_take(br, extra);
+                if (mdist > pos || pos + mlen > cap) { err = 2u; mlen = 0; }
+                break;
+            }
+        }
+        mlen = __shfl_sync(kFull, mlen, lead);
+        mdist = __shfl_sync(kFull, mdist, lead);
+        p0 = __shfl_sync(kFull, pos, lead);
+        // the previous match's bytes were only LOADED when it was decoded (the decoder does not need them to go on):
+        // they are stored now, one decode run later, when the loads have long returned
+        if (pend_pos != 0xFFFFFFFFu) { dst[pend_pos] = pend_val; pend_pos = 0xFFFFFFFFu; }
+        __syncwarp();                                                 // ... and the leader's literal stores: visible to the group
+        if (mlen != 0u) {
+            const uint8_t* s = dst + p0 - mdist;
+            if (mlen <= (uint32_t)kInfLanes) {                         // one byte per lane: load now, store at the next sync point
+                if (gl < mlen) { pend_val = s[mdist >= mlen ? gl : gl % mdist]; pend_pos = p0 + gl; }
+            } else {
+                if (mdist >= mlen) {
+                    for (uint32_t i = gl; i < mlen; i += kInfLanes) dst[p0 + i] = s[i];
+                } else {
+                    for (uint32_t i = gl; i < mlen; i += kInfLanes) dst[p0 + i] = s[i % mdist];   // the pattern repeats
                 }
             }
-            err = __shfl_sync(0xFFFFFFFFu, err, 0);
-            done = __shfl_sync(0xFFFFFFFFu, done, 0);
-            if (err != 0u || done != 0u) break;
-            mlen = __shfl_sync(0xFFFFFFFFu, mlen, 0);
-            mdist = __shfl_sync(0xFFFFFFFFu, mdist, 0);
-            const uint32_t p0 = __shfl_sync(0xFFFFFFFFu, pos, 0);
-            __syncwarp();                                             // lane 0's literal stores are visible to the warp
-            const uint8_t* src = dst + p0 - mdist;
-            if (mdist >= mlen) {
-                for (uint32_t i = lane; i < mlen; i += 32u) dst[p0 + i] = src[i];
-            } else {
-                for (uint32_t i = lane; i < mlen; i += 32u) dst[p0 + i] = src[i % mdist];   // the pattern repeats
-            }
-            __syncwarp();
-            if (lane == 0) pos = p0 + mlen;
         }
-    }
-    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-    uint32_t over = 0;
-    if (lane == 0) over = br.consumed > (uint64_t)M.src_len * 8u ? 1u : 0u;
-    over = __shfl_sync(0xFFFFFFFFu, over, 0);
-    if (lane == 0) {
-        uint32_t st = err;
-        if (st == 0u && over) st = 3u;
-        if (st == 0u && pos != cap) st = 4u;
-        status[m] = st;
+        __syncwarp();                                                 // (outside every branch: groups differ in what they do)
+        if (leader && mlen != 0u) pos = p0 + mlen;
+        // a damaged stream must end the member, not spin: the reader never runs more than a few words past the payload
+        if (leader && br.wp > br.wend + 4) err = 3u;
+        // ---- members that are through ----
+        const uint32_t fin = __shfl_sync(kFull, (uint32_t)(finished || err != 0u), lead);
+        if (fin != 0u && !done) {
+            if (pend_pos != 0xFFFFFFFFu) { dst[pend_pos] = pend_val; pend_pos = 0xFFFFFFFFu; }
+            done = true;
+            if (leader) {
+                uint32_t st = err;
+                if (st == 0u && br_consumed(br) > (uint64_t)M.src_len * 8u) st = 3u;
+                if (st == 0u && pos != cap) st = 4u;
+                status[m] = st;
+            }
+        }
+        if (__all_sync(kFull, done)) break;
     }
 }
 
@@ -353,7 +385,8 @@ __device__ __forceinline__ uint32_t crc_xpow8n(uint32_t n) {               // x^
     }
     return r;
 }
-__global__ void __launch_bounds__(kInfWarps * 32) k_crc32_members(const uint8_t* __restrict__ out, const InflateMember* __restrict__ members,
+constexpr int kCrcWarps = 4;
+__global__ void __launch_bounds__(kCrcWarps * 32) k_crc32_members(const uint8_t* __restrict__ out, const InflateMember* __restrict__ members,
                                                                 uint32_t n_members, uint32_t* __restrict__ status) {
     __shared__ uint32_t tab[256];
     for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) {
@@ -363,7 +396,7 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_crc32_members(const uint8_t*
     }
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t m = blockIdx.x * kInfWarps + warp;
+    const uint32_t m = blockIdx.x * kCrcWarps + warp;
     if (m >= n_members) return;
     const InflateMember M = members[m];
     // lane 0 takes the first per + (n mod 32) bytes, every other lane `per` bytes: all right-hand operands of the
