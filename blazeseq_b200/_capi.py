@@ -26,6 +26,7 @@ SYMBOLS = [
     "bsq_last_timing", "bsq_compute_num_reads_for_size", "bsq_synth_size", "bsq_synth_device",
     "bsq_summarize_device", "bsq_shard_prefix", "bsq_stream_open", "bsq_stream_next", "bsq_stream_region",
     "bsq_stream_get_stats", "bsq_stream_close", "bsq_quality_sums", "bsq_soa_to_host", "bsq_stream_region_info",
+    "bsq_fasta_parse_device", "bsq_fasta_parse_host", "bsq_fasta_get", "bsq_fasta_to_host",
 ]
 
 
@@ -92,6 +93,15 @@ class StreamStats(C.Structure):
 SOURCE_PLAIN, SOURCE_GZIP, SOURCE_AUTO = 0, 1, 2
 
 
+class FastaResult(C.Structure):
+    _fields_ = [("n_records", C.c_int64), ("n_bases", C.c_int64), ("n_lines", C.c_int64), ("stop", Error)]
+
+
+class FastaView(C.Structure):
+    _fields_ = [("n_records", C.c_int64), ("sequence_bytes", C.c_int64), ("sequence", C.c_void_p), ("seq_starts", C.c_void_p),
+                ("id_start", C.c_void_p), ("id_len", C.c_void_p), ("input", C.c_void_p)]
+
+
 class ShardStart(C.Structure):
     _fields_ = [("newline_rank", C.c_int64), ("first_record", C.c_int64), ("skip_bytes", C.c_int64),
                 ("phase", C.c_int32), ("_pad", C.c_int32)]
@@ -151,6 +161,12 @@ def lib():
     L.bsq_stream_close.restype = None
     L.bsq_quality_sums.argtypes = [vp, i64, i64, vp, vp]
     L.bsq_soa_to_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.bsq_fasta_parse_device.argtypes = [vp, vp, u64, C.POINTER(FastaResult)]
+    L.bsq_fasta_parse_host.argtypes = [vp, vp, u64, C.POINTER(FastaResult)]
+    L.bsq_fasta_get.argtypes = [vp, C.POINTER(FastaView)]
+    L.bsq_fasta_to_host.argtypes = [vp, vp, vp, vp, vp]
+    for name in ("bsq_fasta_parse_device", "bsq_fasta_parse_host", "bsq_fasta_get", "bsq_fasta_to_host"):
+        getattr(L, name).restype = i32
     L.bsq_soa_to_host.restype = i32
     L.bsq_quality_sums.restype = i32
     for name in ("bsq_stream_open", "bsq_stream_next", "bsq_stream_get_stats", "bsq_create", "bsq_get_offsets", "bsq_get_batch", "bsq_get_soa", "bsq_batch_to_host",

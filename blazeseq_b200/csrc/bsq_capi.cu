@@ -27,6 +27,7 @@
 #include "bsq_aux.cuh"
 #include "bsq_device.cuh"
 #include "bsq_inflate.cuh"
+#include "bsq_fasta.cuh"
 
 using namespace bsq;
 
@@ -100,6 +101,13 @@ struct bsq_parser {
     float ms[5] = {0, 0, 0, 0, 0};
     int64_t n_launches = 0;
     std::string last_error;
+    // FASTA (bsq_fasta_*): line tables, record tables and the sequence arena of the last FASTA pass
+    DevBuf fa_hdr, fa_slen, fa_start, fa_len, fa_hcum, fa_soff, fa_seq, fa_seq_start, fa_id_start, fa_id_len, fa_hdr_line, fa_err;
+    Window fa_win;
+    bool fa_have = false;
+    int64_t fa_records = 0, fa_total_records = 0;
+    uint64_t fa_seq_bytes = 0;
+    const uint8_t* fa_input = nullptr;
 };
 
 namespace {
@@ -339,7 +347,9 @@ extern "C" void bsq_destroy(bsq_parser* p) {
     for (auto& w : p->win) { w.line_ends.release(); w.run_pre.release(); w.nl_count.release(); w.nl_list.release(); }
     DevBuf* bufs[] = {&p->run_sum, &p->scan_out, &p->err_word, &p->tail_out, &p->cub_tmp, &p->len_prefix,
                       &p->seq_out, &p->qual_out, &p->id_out, &p->ends, &p->id_ends, &p->ends_base,
-                      &p->id_ends_base, &p->id_spans, &p->host_input};
+                      &p->id_ends_base, &p->id_spans, &p->host_input, &p->fa_hdr, &p->fa_slen, &p->fa_start, &p->fa_len, &p->fa_hcum,
+                      &p->fa_soff, &p->fa_seq, &p->fa_seq_start, &p->fa_id_start, &p->fa_id_len, &p->fa_hdr_line, &p->fa_err};
+    p->fa_win.line_ends.release(); p->fa_win.run_pre.release(); p->fa_win.nl_count.release(); p->fa_win.nl_list.release();
     for (auto* b : bufs) b->release();
     for (auto& s : p->pinned_stage) if (s) cudaFreeHost(s);
     if (p->hm) cudaFreeHost(p->hm);
@@ -1512,6 +1522,220 @@ extern "C" bsq_status bsq_last_timing(const bsq_parser* p, float ms[5], int64_t*
     if (!p || !p->have_pass) return BSQ_E_STATE;
     if (ms) memcpy(ms, p->ms, sizeof p->ms);
     if (n_launches) *n_launches = p->n_launches;
+    return BSQ_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// FASTA
+// ------------------------------------------------------------------------------------------------
+
+namespace {
+
+// the table of every newline position of one window (the views() pass of the FASTQ path, its checks ignored)
+bsq_status materialize_line_ends(bsq_parser* p, Window& w) {
+    bsq_status st = summarize_window(p, w, false);
+    if (st != BSQ_OK) return st;
+    CK(w.line_ends.ensure(4ull * ((size_t)w.scan.totals.newlines + 2), 1 << 16));
+    CK(p->id_spans.ensure(8ull * ((size_t)w.scan.totals.records + 1), 1 << 20));
+    CK(p->err_word.ensure(32));
+    ResolveParams P{};
+    P.run_pre = w.run_pre.as<BsqPrefix>();
+    P.n_complete = w.scan.totals.records;
+    P.strip_flag = reinterpret_cast<uint32_t*>(p->err_word.as<uint8_t>() + 8);
+    P.bases = p->err_word.as<unsigned long long>() + 2;
+    P.line_ends = w.line_ends.as<uint32_t>();
+    P.id_spans = p->id_spans.as<uint32_t>();
+    P.batch_size = 4096;
+    P.rec_limit = 0xFFFFFFFFu;
+    P.err = p->err_word.as<unsigned long long>();   // (FASTQ structure reports land here and are ignored)
+    k_resolve<false, false, true, false><<<w.wp.n_runs, kThreads, smem_bytes(false, false), p->stream>>>(w.wp, P);
+    p->n_launches += 1;
+    CK(cudaGetLastError());
+    return BSQ_OK;
+}
+
+bsq_status fasta_pass(bsq_parser* p, const uint8_t* d, uint64_t n, bsq_fasta_result* out) {
+    memset(out, 0, sizeof *out);
+    p->fa_have = false;
+    p->have_pass = false;            // the FASTQ result views share buffers with this pass
+    p->fa_input = d;
+    if (n > kWindowMax) { p->last_error = "a FASTA pass is limited to one window (2 GiB - 1 MiB)"; return BSQ_E_ARG; }
+    set_plain_error(&out->stop, BSQ_EOF, "EOF");
+    if (n == 0) { p->fa_have = true; p->fa_records = p->fa_total_records = 0; p->fa_seq_bytes = 0; return BSQ_OK; }
+    Window& w = p->fa_win;
+    plan_window(p, w, d, n, false);
+    w.region_off = 0;
+    bsq_status st = materialize_line_ends(p, w);
+    if (st != BSQ_OK) return st;
+    const uint32_t nnl = w.scan.totals.newlines;
+    uint8_t last_byte = 0;
+    CK(cudaMemcpyAsync(&last_byte, d + n - 1, 1, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    const uint32_t L = nnl + (last_byte != '\n' ? 1u : 0u);
+    out->n_lines = L;
+    CK(p->fa_hdr.ensure(4ull * (L + 1), 1 << 16)); CK(p->fa_hcum.ensure(4ull * (L + 1), 1 << 16));
+    CK(p->fa_slen.ensure(8ull * (L + 1), 1 << 16)); CK(p->fa_soff.ensure(8ull * (L + 1), 1 << 16));
+    CK(p->fa_start.ensure(4ull * (L + 1), 1 << 16)); CK(p->fa_len.ensure(4ull * (L + 1), 1 << 16));
+    CK(p->fa_err.ensure(16));
+    CK(cudaMemsetAsync(p->fa_err.p, 0xFF, 16, p->stream));
+    FastaLines F{};
+    F.base = w.base; F.line_ends = w.line_ends.as<uint32_t>(); F.n_newlines = nnl; F.n_lines = L; F.end = w.wp.end;
+    F.hdr = p->fa_hdr.as<uint32_t>(); F.slen = p->fa_slen.as<unsigned long long>();
+    F.start = p->fa_start.as<uint32_t>(); F.len = p->fa_len.as<uint32_t>();
+    const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((L + 255) / 256, (uint32_t)p->sm_count * 32));
+    k_fa_lines<<<grid, 256, 0, p->stream>>>(F);
+    size_t t1 = 0, t2 = 0;
+    CK(cub::DeviceScan::InclusiveSum(nullptr, t1, F.hdr, p->fa_hcum.as<uint32_t>(), (int)L, p->stream));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, t2, F.slen, p->fa_soff.as<unsigned long long>(), (int)L, p->stream));
+    CK(p->cub_tmp.ensure(std::max(t1, t2) + 16));
+    t1 = t2 = p->cub_tmp.cap;
+    CK(cub::DeviceScan::InclusiveSum(p->cub_tmp.p, t1, F.hdr, p->fa_hcum.as<uint32_t>(), (int)L, p->stream));
+    CK(cub::DeviceScan::ExclusiveSum(p->cub_tmp.p, t2, F.slen, p->fa_soff.as<unsigned long long>(), (int)L, p->stream));
+    uint32_t n_rec = 0;
+    unsigned long long soff_last = 0, slen_last = 0;
+    CK(cudaMemcpyAsync(&n_rec, p->fa_hcum.as<uint32_t>() + (L - 1), 4, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(&soff_last, p->fa_soff.as<unsigned long long>() + (L - 1), 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(&slen_last, p->fa_slen.as<unsigned long long>() + (L - 1), 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    const unsigned long long total_seq = soff_last + slen_last;
+    CK(p->fa_seq.ensure(total_seq + 64, 1 << 20));
+    CK(p->fa_seq_start.ensure(8ull * (n_rec + 2), 1 << 12));
+    CK(p->fa_id_start.ensure(4ull * (n_rec + 1), 1 << 12)); CK(p->fa_id_len.ensure(4ull * (n_rec + 1), 1 << 12));
+    CK(p->fa_hdr_line.ensure(4ull * (n_rec + 1), 1 << 12));
+    FastaPack K{};
+    K.base = w.base; K.n_lines = L; K.n_records = n_rec; K.check_ascii = p->cfg.check_ascii ? 1u : 0u;
+    K.hdr = F.hdr; K.hcum = p->fa_hcum.as<uint32_t>(); K.soff = p->fa_soff.as<unsigned long long>();
+    K.start = F.start; K.len = F.len; K.seq_out = p->fa_seq.as<uint8_t>();
+    K.seq_start = p->fa_seq_start.as<unsigned long long>(); K.id_start = p->fa_id_start.as<uint32_t>();
+    K.id_len = p->fa_id_len.as<uint32_t>(); K.hdr_line = p->fa_hdr_line.as<uint32_t>();
+    K.total_seq = total_seq; K.err = p->fa_err.as<uint32_t>();
+    const int gridw = (int)std::max<uint32_t>(1, std::min<uint32_t>((L + 7) / 8, (uint32_t)p->sm_count * 64));
+    k_fa_pack<<<gridw, 256, 0, p->stream>>>(K);
+    if (n_rec)
+        k_fa_empty<<<std::max(1, std::min<int>((int)((n_rec + 255) / 256), p->sm_count * 8)), 256, 0, p->stream>>>(
+            K.seq_start, n_rec, K.err);
+    p->n_launches += 5;
+    CK(cudaGetLastError());
+    uint32_t herr[4];
+    CK(cudaMemcpyAsync(herr, p->fa_err.p, 16, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    // ---- the first stop, in the order the reference meets them ----
+    const uint32_t none = 0xFFFFFFFFu, begin = w.wp.begin;
+    auto line_start = [&](uint32_t line, int64_t* pos) -> bsq_status {   // stream offset of the first byte of a line
+        uint32_t le = 0;
+        CK(cudaMemcpy(&le, w.line_ends.as<uint32_t>() + line, 4, cudaMemcpyDeviceToHost));
+        *pos = (int64_t)(le + 1u) - (int64_t)begin;
+        return BSQ_OK;
+    };
+    int64_t good = n_rec;
+    if (herr[0] != none) {
+        // a non-blank line before the first header: _read_header_line, parser.mojo:193-197 (context: records so far = 0)
+        good = 0;
+        int64_t pos = 0;
+        st = line_start(herr[0], &pos);
+        if (st != BSQ_OK) return st;
+        memset(&out->stop, 0, sizeof out->stop);
+        out->stop.code = BSQ_OTHER; out->stop.line_number = (int64_t)herr[0] + 1; out->stop.file_position = pos;
+        Msg m{out->stop.message, sizeof out->stop.message, 0};
+        m.str("FASTA: sequence id line does not start with '>'");
+        m.str("\n  Line number: "); m.i64(out->stop.line_number);
+        if (pos > 0) { m.str("\n  File position: "); m.i64(pos); }
+    } else {
+        const uint32_t e_empty = herr[2], e_ascii = herr[1];
+        const uint32_t first = std::min(e_empty, e_ascii);
+        if (first != none) {
+            good = first;
+            memset(&out->stop, 0, sizeof out->stop);
+            Msg m{out->stop.message, sizeof out->stop.message, 0};
+            if (e_empty == first) {                       // parser.mojo:152-160
+                uint32_t hl[2] = {0, 0};
+                CK(cudaMemcpy(hl, p->fa_hdr_line.as<uint32_t>() + first, first + 1 < n_rec ? 8 : 4, cudaMemcpyDeviceToHost));
+                int64_t pos = (int64_t)n;                 // the line read last: the next header, or the end of the stream
+                if (first + 1 < n_rec) { st = line_start(hl[1], &pos); if (st != BSQ_OK) return st; }
+                out->stop.code = BSQ_OTHER; out->stop.record_number = (int64_t)first + 1;
+                out->stop.line_number = (int64_t)hl[0] + 2; out->stop.file_position = pos;
+                m.str("FASTA record has empty sequence");
+                m.str("\n  Record number: "); m.i64(out->stop.record_number);
+                m.str("\n  Line number: "); m.i64(out->stop.line_number);
+                if (pos > 0) { m.str("\n  File position: "); m.i64(pos); }
+            } else {                                      // parser.mojo:162-163, errors.mojo:223-234
+                out->stop.code = BSQ_ASCII_INVALID; out->stop.record_number = first;
+                m.str(code_message(BSQ_ASCII_INVALID));
+                if (first > 0) { m.str("\n  Record number: "); m.i64(first); }
+            }
+        }
+    }
+    p->fa_total_records = n_rec;
+    p->fa_records = good;
+    p->fa_seq_bytes = total_seq;
+    out->n_records = good;
+    if (good == (int64_t)n_rec && herr[0] == none) out->n_bases = (int64_t)total_seq;
+    else if (good > 0) {
+        unsigned long long v = 0;
+        CK(cudaMemcpy(&v, p->fa_seq_start.as<unsigned long long>() + good, 8, cudaMemcpyDeviceToHost));
+        out->n_bases = (int64_t)v;
+    }
+    p->fa_have = true;
+    return BSQ_OK;
+}
+
+}  // namespace
+
+extern "C" bsq_status bsq_fasta_parse_device(bsq_parser* p, const uint8_t* dev_bytes, uint64_t n, bsq_fasta_result* out) {
+    if (!p || !out || (!dev_bytes && n)) return BSQ_E_ARG;
+    CK(cudaSetDevice(p->cfg.device_id));
+    p->n_launches = 0;
+    return fasta_pass(p, dev_bytes, n, out);
+}
+
+extern "C" bsq_status bsq_fasta_parse_host(bsq_parser* p, const uint8_t* host_bytes, uint64_t n, bsq_fasta_result* out) {
+    if (!p || !out || (!host_bytes && n)) return BSQ_E_ARG;
+    CK(cudaSetDevice(p->cfg.device_id));
+    p->n_launches = 0;
+    CK(p->host_input.ensure(n + 256, 1 << 20));
+    if (n) CK(cudaMemcpyAsync(p->host_input.p, host_bytes, n, cudaMemcpyHostToDevice, p->stream));
+    return fasta_pass(p, p->host_input.as<uint8_t>(), n, out);
+}
+
+extern "C" bsq_status bsq_fasta_get(const bsq_parser* p, bsq_fasta_view* out) {
+    if (!p || !out) return BSQ_E_ARG;
+    if (!p->fa_have) return BSQ_E_STATE;
+    memset(out, 0, sizeof *out);
+    out->n_records = p->fa_records;
+    if (p->fa_total_records == 0) return BSQ_OK;
+    out->sequence = p->fa_seq.as<uint8_t>();
+    out->seq_starts = p->fa_seq_start.as<uint64_t>();
+    out->id_start = p->fa_id_start.as<uint32_t>();
+    out->id_len = p->fa_id_len.as<uint32_t>();
+    out->input = p->fa_win.base;
+    out->sequence_bytes = (int64_t)p->fa_seq_bytes;
+    return BSQ_OK;
+}
+
+extern "C" bsq_status bsq_fasta_to_host(bsq_parser* p, uint8_t* seq, uint64_t* seq_starts, uint8_t* ids, uint64_t* id_starts) {
+    bsq_fasta_view v;
+    bsq_status st = bsq_fasta_get(p, &v);
+    if (st != BSQ_OK) return st;
+    const int64_t n = v.n_records;
+    if (n == 0) { if (seq_starts) seq_starts[0] = 0; if (id_starts) id_starts[0] = 0; return BSQ_OK; }
+    CK(cudaSetDevice(p->cfg.device_id));
+    std::vector<uint64_t> ss(n + 1);
+    CK(cudaMemcpy(ss.data(), v.seq_starts, 8ull * (n + 1), cudaMemcpyDeviceToHost));
+    if (seq_starts) memcpy(seq_starts, ss.data(), 8ull * (n + 1));
+    if (seq && ss[n]) CK(cudaMemcpy(seq, v.sequence, ss[n], cudaMemcpyDeviceToHost));
+    if (ids || id_starts) {
+        std::vector<uint32_t> a(n), l(n);
+        CK(cudaMemcpy(a.data(), v.id_start, 4ull * n, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(l.data(), v.id_len, 4ull * n, cudaMemcpyDeviceToHost));
+        uint64_t off = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            if (id_starts) id_starts[i] = off;
+            if (ids && l[i]) CK(cudaMemcpy(ids + off, v.input + a[i], l[i], cudaMemcpyDeviceToHost));
+            off += l[i];
+        }
+        if (id_starts) id_starts[n] = off;
+    }
     return BSQ_OK;
 }
 

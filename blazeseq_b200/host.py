@@ -467,6 +467,45 @@ class GpuParser:
         capi.check(capi.lib().bsq_soa_to_host(self._h, p(seq), p(qual), p(idb), p(ends), p(id_ends)), self._h,
                    "bsq_soa_to_host")
 
+    def fasta_parse_host(self, data: np.ndarray) -> capi.FastaResult:
+        """bsq_fasta_parse_host: FastaParser.next_record in a loop over `data` (fasta/parser.mojo:60-200)."""
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        r = capi.FastaResult()
+        self.generation += 1
+        capi.check(capi.lib().bsq_fasta_parse_host(self._h, C.c_void_p(data.ctypes.data if data.size else 0), data.size,
+                                                   C.byref(r)), self._h, "bsq_fasta_parse_host")
+        return r
+
+    def fasta_parse_device(self, dev_ptr: int, n: int) -> capi.FastaResult:
+        r = capi.FastaResult()
+        self.generation += 1
+        capi.check(capi.lib().bsq_fasta_parse_device(self._h, C.c_void_p(dev_ptr), n, C.byref(r)), self._h,
+                   "bsq_fasta_parse_device")
+        return r
+
+    def fasta_view(self) -> capi.FastaView:
+        v = capi.FastaView()
+        capi.check(capi.lib().bsq_fasta_get(self._h, C.byref(v)), self._h, "bsq_fasta_get")
+        return v
+
+    def fasta_to_host(self):
+        """(sequence bytes, seq_starts[n+1], id bytes, id_starts[n+1]) of the last FASTA pass."""
+        v = self.fasta_view()
+        n = int(v.n_records)
+        seq = np.zeros(max(int(v.sequence_bytes), 1), np.uint8)
+        ss = np.zeros(n + 1, np.uint64)
+        # ids are at most as long as the input: size them from the device table
+        ids = np.zeros(1, np.uint8)
+        ist = np.zeros(n + 1, np.uint64)
+        if n:
+            capi.check(capi.lib().bsq_fasta_to_host(self._h, None, C.c_void_p(ss.ctypes.data), None, C.c_void_p(ist.ctypes.data)),
+                       self._h, "bsq_fasta_to_host")
+            ids = np.zeros(max(int(ist[n]), 1), np.uint8)
+            capi.check(capi.lib().bsq_fasta_to_host(self._h, C.c_void_p(seq.ctypes.data), C.c_void_p(ss.ctypes.data),
+                                                    C.c_void_p(ids.ctypes.data), C.c_void_p(ist.ctypes.data)), self._h,
+                       "bsq_fasta_to_host")
+        return seq, ss, ids, ist
+
     def quality_sums(self, first_record: int = 0, count: Optional[int] = None, out_device_ptr: int = 0) -> np.ndarray:
         """Per-record sum of Phred scores of the last batches() pass, computed on the device from the SoA
         (bsq_quality_sums): the parse -> consumer hand-off without a host round trip."""

@@ -260,6 +260,34 @@ bsq_status bsq_offsets_to_host(bsq_parser* p, int32_t window, uint32_t* line_end
 /* Device address of the input of the last pass (the staged copy for host passes). */
 const uint8_t* bsq_pass_device_input(const bsq_parser* p);
 
+/* ---- FASTA (blazeseq/fasta/parser.mojo:60-200) ---------------------------------------------------
+ * FastaParser.next_record in a loop over one region (<= 2 GiB - 1 MiB): every line is stripped of blanks at both
+ * ends, a line that then begins with '>' opens a record (id = the rest, stripped), every other line is sequence and
+ * is appended without its line break.  Results stay on the device: one contiguous sequence arena, n+1 offsets into
+ * it, and the span of every id in the input.  The stop is BSQ_EOF, or the reference's error with its context:
+ * BSQ_OTHER "FASTA: sequence id line does not start with '>'" / "FASTA record has empty sequence", or
+ * BSQ_ASCII_INVALID under cfg.check_ascii (fasta/parser.mojo:40-58). */
+typedef struct bsq_fasta_result {
+    int64_t n_records;             /* records before the stop */
+    int64_t n_bases;               /* sequence bytes of those records */
+    int64_t n_lines;
+    bsq_error stop;
+} bsq_fasta_result;
+typedef struct bsq_fasta_view {    /* DEVICE pointers, valid until the next pass */
+    int64_t n_records;
+    int64_t sequence_bytes;
+    const uint8_t* sequence;       /* record r: sequence[seq_starts[r] .. seq_starts[r+1]) */
+    const uint64_t* seq_starts;    /* n_records + 1 */
+    const uint32_t* id_start;      /* id of record r: input[id_start[r] .. + id_len[r]) */
+    const uint32_t* id_len;
+    const uint8_t* input;
+} bsq_fasta_view;
+bsq_status bsq_fasta_parse_device(bsq_parser* p, const uint8_t* dev_bytes, uint64_t n, bsq_fasta_result* out);
+bsq_status bsq_fasta_parse_host(bsq_parser* p, const uint8_t* host_bytes, uint64_t n, bsq_fasta_result* out);
+bsq_status bsq_fasta_get(const bsq_parser* p, bsq_fasta_view* out);
+/* Host copies: seq (sequence_bytes), seq_starts (n+1), the ids packed back to back (ids, with n+1 offsets). */
+bsq_status bsq_fasta_to_host(bsq_parser* p, uint8_t* seq, uint64_t* seq_starts, uint8_t* ids, uint64_t* id_starts);
+
 /* ---- measurement hooks ------------------------------------------------------------------------ */
 
 /* Device time (ms, CUDA events on the parser's stream) of the kernels of the last pass:

@@ -971,3 +971,114 @@ void ora_sha256(const uint8_t* data, size_t n, uint8_t out[32]) {
         out[4 * j + 2] = (uint8_t)(h[j] >> 8); out[4 * j + 3] = (uint8_t)h[j];
     }
 }
+
+/* ------------------------------------------------------------------------ */
+/* FASTA: blazeseq/fasta/parser.mojo:60-200 over LineIterator   */
+/* (io/buffered.mojo:600-638: lines without '\n', a trailing '\r' trimmed,   */
+/* the last line may lack its newline; line numbers count lines read; the    */
+/* file position is the stream offset at the start of the last next_line).   */
+/* ------------------------------------------------------------------------ */
+
+typedef struct { const uint8_t* d; int64_t n, pos, line_no, file_pos; } ora_lines;
+
+/* LineIterator.next_line: 1 and [*s, *e) on a line, 0 at EOF */
+static int ora_next_line(ora_lines* L, int64_t* s, int64_t* e) {
+    L->file_pos = L->pos;                                   /* buffered.mojo:606 */
+    if (L->pos >= L->n) return 0;                           /* :609-616 EOFError */
+    const uint8_t* q = (const uint8_t*)memchr(L->d + L->pos, ORA_NL, (size_t)(L->n - L->pos));
+    int64_t end = q ? q - L->d : L->n;
+    *s = L->pos;
+    *e = end;
+    if (*e > *s && L->d[*e - 1] == ORA_CR) --*e;            /* _trim_trailing_cr */
+    L->pos = q ? end + 1 : L->n;
+    L->line_no++;
+    return 1;
+}
+
+static void ora_strip_range(const uint8_t* d, int64_t* s, int64_t* e) {   /* _strip_spaces, utils.mojo:221-242 */
+    int64_t len = *e - *s;
+    ora_strip(d, s, &len);
+    *e = *s + len;
+}
+
+/* FastaParser.next_record in a loop (fasta/parser.mojo:123-172, _read_header_line :182-203).
+ * ids: (start, len) pairs per record; seq_off: n+1 cumulative offsets into seq (sequence r = seq[seq_off[r], seq_off[r+1]));
+ * returns the records delivered before the stop; *err = the stop (ORA_EOF on a clean end). */
+int64_t ora_fasta_parse(const uint8_t* data, size_t n_, int check_ascii, int64_t* ids, int64_t* seq_off, uint8_t* seq,
+                        int64_t cap_records, ora_error* err) {
+    ora_lines L = {data, (int64_t)n_, 0, 0, 0};
+    int64_t nrec = 0, nseq = 0;
+    int have_pending = 0;
+    int64_t pend_s = 0, pend_e = 0;
+    ora_err_clear(err, ORA_EOF);
+    if (err) strcpy(err->message, "EOF");
+    if (seq_off) seq_off[0] = 0;
+    for (;;) {
+        int64_t id_s, id_e, s, e;
+        /* has_more (:103-105) is `pending or lines.has_more()`; _read_header_line raises EOF itself when only blank lines remain */
+        if (have_pending) { id_s = pend_s; id_e = pend_e; have_pending = 0; }
+        else {
+            int got = 0;
+            while (ora_next_line(&L, &s, &e)) {                       /* :189-203 */
+                ora_strip_range(data, &s, &e);
+                if (e == s) continue;
+                if (data[s] != '>') {
+                    ora_err_clear(err, ORA_OTHER);
+                    err->record_number = nrec; err->line_number = L.line_no; err->file_position = L.file_pos;
+                    ora_sb b = {err->message, sizeof err->message, 0};
+                    sb_str(&b, "FASTA: sequence id line does not start with '>'");
+                    if (nrec > 0) { sb_str(&b, "\n  Record number: "); sb_i64(&b, nrec); }
+                    if (L.line_no > 0) { sb_str(&b, "\n  Line number: "); sb_i64(&b, L.line_no); }
+                    if (L.file_pos > 0) { sb_str(&b, "\n  File position: "); sb_i64(&b, L.file_pos); }
+                    return nrec;
+                }
+                id_s = s + 1; id_e = e;
+                ora_strip_range(data, &id_s, &id_e);
+                got = 1;
+                break;
+            }
+            if (!got) return nrec;                                   /* EOFError */
+        }
+        const int64_t seq_start_line = L.line_no + 1;                /* :134 */
+        const int64_t seq_begin = nseq;
+        while (ora_next_line(&L, &s, &e)) {                           /* :136-149 */
+            ora_strip_range(data, &s, &e);
+            if (e > s && data[s] == '>') {
+                pend_s = s + 1; pend_e = e;
+                ora_strip_range(data, &pend_s, &pend_e);
+                have_pending = 1;
+                break;
+            }
+            if (seq) memcpy(seq + nseq, data + s, (size_t)(e - s));
+            nseq += e - s;
+        }
+        if (nseq == seq_begin) {                                     /* :152-160 */
+            ora_err_clear(err, ORA_OTHER);
+            err->record_number = nrec + 1; err->line_number = seq_start_line; err->file_position = L.file_pos;
+            ora_sb b = {err->message, sizeof err->message, 0};
+            sb_str(&b, "FASTA record has empty sequence");
+            sb_str(&b, "\n  Record number: "); sb_i64(&b, nrec + 1);
+            sb_str(&b, "\n  Line number: "); sb_i64(&b, seq_start_line);
+            if (L.file_pos > 0) { sb_str(&b, "\n  File position: "); sb_i64(&b, L.file_pos); }
+            return nrec;
+        }
+        if (check_ascii) {                                           /* :162-163, Validator :40-58 */
+            int bad = 0;
+            for (int64_t i = id_s; i < id_e && !bad; ++i) bad = data[i] & 0x80;
+            for (int64_t i = seq_begin; i < nseq && !bad; ++i) bad = seq ? (seq[i] & 0x80) : 0;
+            if (bad) {
+                ora_err_clear(err, ORA_ASCII_INVALID);
+                err->record_number = nrec;
+                ora_sb b = {err->message, sizeof err->message, 0};
+                sb_str(&b, ora_code_message(ORA_ASCII_INVALID));
+                if (nrec > 0) { sb_str(&b, "\n  Record number: "); sb_i64(&b, nrec); }
+                return nrec;
+            }
+        }
+        if (nrec < cap_records) {
+            if (ids) { ids[2 * nrec] = id_s; ids[2 * nrec + 1] = id_e - id_s; }
+            if (seq_off) seq_off[nrec + 1] = nseq;
+        }
+        nrec++;
+    }
+}

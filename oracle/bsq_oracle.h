@@ -146,6 +146,13 @@ int64_t ora_synth_generate(int64_t num_reads, int64_t first, int64_t count,
                            int64_t max_phred, uint8_t q_lower, uint8_t q_upper,
                            uint8_t q_offset, int gc_slots, uint8_t* out);
 
+/* FASTA: FastaParser.next_record in a loop (blazeseq/fasta/parser.mojo:60-200).  ids: (start, len) pairs of the
+ * stripped id in `data`; seq_off: n+1 cumulative offsets into `seq` (all line breaks and surrounding blanks
+ * removed); `seq` must hold n bytes.  Returns the records delivered before the stop; *err = the stop reason
+ * (ORA_EOF on a clean end; ORA_OTHER with the reference's text for the two FASTA parse errors). */
+int64_t ora_fasta_parse(const uint8_t* data, size_t n, int check_ascii, int64_t* ids, int64_t* seq_off, uint8_t* seq,
+                        int64_t cap_records, ora_error* err);
+
 /* SHA-256 helper for generator known-answer tests. */
 void ora_sha256(const uint8_t* data, size_t n, uint8_t out[32]);
 

@@ -254,6 +254,23 @@ def synth(num_reads, mn, mx, min_phred, max_phred, schema_name="generic", first=
     return out[:w]
 
 
+def fasta_parse(data, check_ascii=False):
+    """FastaParser over the whole input.  Returns (ids [(bytes)], sequences [(bytes)], Error)."""
+    a = _as_u8(data)
+    cap = a.size // 2 + 2
+    ids = np.zeros(2 * cap, np.int64)
+    off = np.zeros(cap + 1, np.int64)
+    seq = np.zeros(max(a.size, 1), np.uint8)
+    err = Error()
+    L = lib()
+    L.ora_fasta_parse.restype = C.c_int64
+    L.ora_fasta_parse.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    n = L.ora_fasta_parse(_ptr(a), a.size, int(check_ascii), _ptr(ids), _ptr(off), _ptr(seq), cap, C.byref(err))
+    id_list = [bytes(a[ids[2 * i]: ids[2 * i] + ids[2 * i + 1]]) for i in range(n)]
+    seq_list = [bytes(seq[off[i]: off[i + 1]]) for i in range(n)]
+    return id_list, seq_list, err
+
+
 def sha256(data) -> str:
     a = _as_u8(data)
     out = np.zeros(32, np.uint8)

@@ -1,17 +1,27 @@
-# the committed evidence: bench line, launch list of the same command, one full capture per hot kernel
-set -x
+# the committed evidence of profiles/: ncu launch list of the bench command + one `ncu --set full` capture per hot kernel,
+# summarised on the box (the reports are ~10 MB each; gpurun brings back at most 64 MiB) -- gpurun -- 'bash scripts/gpu_profiles.sh'
 mkdir -p gpurun_out
-R=${ROUND_TAG:-r01}
-nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > gpurun_out/${R}_gpu.txt; lscpu | grep -E "Model name|^CPU\(s\)" >> gpurun_out/${R}_gpu.txt
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err; tail -c 600 gpurun_out/${R}_bench.json
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${R}_bench_reference.json 2>> gpurun_out/${R}_bench.err
-timeout 600 python bench.py --steps 5 --warmup 3 --mode views --no-cpu --no-e2e > gpurun_out/${R}_bench_views.json 2>> gpurun_out/${R}_bench.err
-timeout 600 python bench.py --steps 5 --warmup 3 --validate --no-cpu --no-e2e > gpurun_out/${R}_bench_validate.json 2>> gpurun_out/${R}_bench.err
-timeout 600 python bench.py --steps 5 --warmup 3 --mixed --no-cpu --no-e2e > gpurun_out/${R}_bench_mixed.json 2>> gpurun_out/${R}_bench.err
-BSQ_SINGLE_PASS=1 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/${R}_bench_single_pass.json 2>> gpurun_out/${R}_bench.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/${R}_ncu_launch.log 2>&1
-# launch 13 of k_resolve / k_summarize = window 0 of the first timed step (steps: 3 warm-up + ...; 6 windows per step)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_resolve -s 18 -c 1 -o gpurun_out/${R}_prof_resolve -f python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/${R}_ncu_resolve.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_summarize -s 18 -c 1 -o gpurun_out/${R}_prof_summarize -f python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e > gpurun_out/${R}_ncu_summarize.log 2>&1
-tail -2 gpurun_out/${R}_bench.err
-ls -la gpurun_out | tail -15
+R=${ROUND_TAG:-r02}
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > gpurun_out/${R}_gpu.txt; lscpu | grep -E "Model name|^CPU\(s\)|NUMA" >> gpurun_out/${R}_gpu.txt
+nvidia-smi topo -m >> gpurun_out/${R}_gpu.txt 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-sub > gpurun_out/${R}_ncu_launch.log 2>&1
+# one window of 1.9 GiB per pass: launches per pass = 1 k_summarize + 1 k_resolve; 3 warm-up passes, the 4th is captured
+N="ncu --set full --clock-control none --import-source on -s 3 -c 1 -f"
+P="python bench.py --gib 1.9 --steps 1 --warmup 3 --no-cpu --no-e2e --no-sub"
+cap() {  # name kernel-regex args...
+  name=$1; kern=$2; shift 2
+  timeout 300 $N -k regex:$kern -o gpurun_out/${R}_prof_$name $P "$@" > gpurun_out/ncu_$name.log 2>&1
+  timeout 120 python scripts/profile_summary.py gpurun_out/${R}_prof_$name.ncu-rep $kern > gpurun_out/${R}_$name.txt 2>&1
+}
+cap k_resolve k_resolve
+cap k_summarize k_summarize
+timeout 120 python scripts/traffic_from_ncu.py gpurun_out/${R}_prof_k_resolve.ncu-rep gpurun_out/${R}_prof_k_summarize.ncu-rep 6394930 > gpurun_out/traffic.json 2>> gpurun_out/ncu_k_resolve.log
+cap k_resolve_stride320 k_resolve --id-digits 9
+cap k_resolve_validate k_resolve --validate
+cap k_summarize_validate k_summarize --validate
+cap k_resolve_mixed k_resolve --mixed
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_inflate_members -s 2 -c 1 -f -o gpurun_out/${R}_prof_k_inflate python bench.py --gzip --gib 0.5 > gpurun_out/ncu_k_inflate.log 2>&1
+timeout 120 python scripts/profile_summary.py gpurun_out/${R}_prof_k_inflate.ncu-rep k_inflate > gpurun_out/${R}_k_inflate_members.txt 2>&1
+# keep two reports for reading source pages later; the rest stays on the box
+find gpurun_out -name "*.ncu-rep" ! -name "${R}_prof_k_resolve.ncu-rep" ! -name "${R}_prof_k_inflate.ncu-rep" -delete
+ls -la gpurun_out | tail -20; du -sh gpurun_out

@@ -354,3 +354,21 @@ def test_record_limit_of_the_canonical_parse_equals_the_streaming_model(oracle):
         assert (se.code, se.message) == (err.code, err.message), (trial, cap, growth, mx, se.message, err.message)
         hits += err.code in (8, 9)
     assert hits > 50   # the limit was exercised
+
+
+def test_fasta_oracle_against_the_reference_literals_and_corpus(oracle, golden_dir):
+    """ora_fasta_parse (fasta/parser.mojo:60-200) against every literal stream of tests/fasta/test_fasta_parser.mojo and
+    the Biopython files checked by tests/fasta/test_fasta_parser_correctness.mojo."""
+    from fasta_cases import CASES, CORPUS
+    for cite, data, check_ascii, recs, sub in CASES:
+        ids, seqs, err = oracle.fasta_parse(data, check_ascii)
+        assert list(zip(ids, seqs)) == recs, cite
+        assert sub in err.message.decode("latin-1"), (cite, err.message)
+    for name, count, checks in CORPUS:
+        data = open(os.path.join(golden_dir, "fasta_corpus", name), "rb").read()
+        ids, seqs, err = oracle.fasta_parse(data)
+        assert (len(ids) >= 1) if count is None else (len(ids) == count), name
+        assert err.code == oracle.EOF
+        for i, id_sub, seq_sub in checks:
+            assert id_sub in ids[i] and (seq_sub is None or seq_sub in seqs[i]), (name, i)
+        assert all(b"\n" not in s and b"\r" not in s for s in seqs)
