@@ -844,7 +844,9 @@ struct bsq_stream {
     gzFile gz = nullptr;
     uint64_t region_bytes = 0, carry_cap = 0;
     struct Buf { uint8_t* mem = nullptr; uint64_t n_new = 0; bool eof = false; int state = 0; /* 0 free, 1 ready, 2 in use */ };
-    Buf buf[2];
+    static constexpr int kMaxSlots = 3;
+    Buf buf[kMaxSlots];
+    int n_slots = 2;                 // pinned buffers the reader cycles through (3 when regions are inflated on the device)
     std::thread reader;
     std::mutex mu;
     std::condition_variable cv;
@@ -882,15 +884,30 @@ struct bsq_stream {
     // the caller asks for them (bsq_stream_region).
     bool gpu_inflate = false;
     struct ZBuf { uint8_t* mem = nullptr; uint64_t n = 0; std::vector<bsq::InflateMember> members; uint64_t out_bytes = 0; };
-    ZBuf zb[2];
+    ZBuf zb[kMaxSlots];
     uint64_t zcap = 0;                   // compressed bytes a pinned buffer holds
     std::vector<uint8_t> zcarry;         // compressed bytes read but not yet handed out (a partial member, or over budget)
     int64_t zfile_pos = 0;
-    DevBuf zdev, mdev, sdev, rdev[2];    // compressed bytes, member table, member status, inflated regions (ping-pong)
+    // Two regions are in flight: while the pass of region k runs on the parser's stream, the compressed bytes of region
+    // k+1 travel and are inflated on the copy stream (when the reader has them ready).
+    struct InfJob {
+        bool launched = false, eof = false;
+        int slot = -1;
+        uint32_t nm = 0;
+        uint64_t out_bytes = 0, z_bytes = 0, room = 0;   // room: bytes kept free in front of the inflated data for the carry
+        DevBuf zdev, mdev, sdev;
+        uint32_t* status = nullptr;      // pinned: the D2H copy must not hold the host up
+        size_t status_cap = 0;
+        cudaEvent_t e_start = nullptr, e_h2d = nullptr, e_done = nullptr;
+    };
+    InfJob job[2];
+    int jcur = 0;
+    cudaEvent_t e_carry = nullptr;
+    DevBuf rdev[2];                      // inflated regions (ping-pong): [room | inflated members]
     int rcur = 0;
-    uint64_t dev_carry_off = 0, dev_carry_len = 0;   // unconsumed tail of the region in rdev[rcur]
+    uint64_t region_dev_off = 0;         // offset of the current region in rdev[rcur]
+    uint64_t dev_carry_off = 0, dev_carry_len = 0;   // unconsumed tail of the region in rdev[rcur] (offset in the buffer)
     std::vector<uint8_t> region_host;    // the current region on the host, fetched on demand
-    std::vector<uint32_t> status_host;
     bool region_host_valid = false;
     uint64_t region_dev_n = 0;
 
@@ -1083,7 +1100,7 @@ struct bsq_stream {
                 b->n_new = got; b->eof = eof || err; b->state = 1;
                 if (err) read_error = true;
                 st.reader_busy_s += dt; st.bytes_read += got;
-                next_fill ^= 1;
+                next_fill = (next_fill + 1) % n_slots;
             }
             cv.notify_all();
             if (eof || err) return;
@@ -1145,6 +1162,11 @@ extern "C" bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t s
     s->carry_cap = std::max<uint64_t>(std::min<uint64_t>(s->region_bytes / 4, 64ull << 20), 4096);
     if (s->gpu_inflate) {
         s->zcap = std::max<uint64_t>(s->region_bytes / 2 + (1ull << 20), 256ull << 10);
+        s->n_slots = bsq_stream::kMaxSlots;
+        for (auto& j : s->job)
+            if (cudaEventCreate(&j.e_start) != cudaSuccess || cudaEventCreate(&j.e_h2d) != cudaSuccess ||
+                cudaEventCreate(&j.e_done) != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, cudaGetLastError(), "cudaEventCreate"); }
+        if (cudaEventCreateWithFlags(&s->e_carry, cudaEventDisableTiming) != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, cudaGetLastError(), "cudaEventCreate"); }
         for (auto& z : s->zb) {
             cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&z.mem), s->zcap + 64, cudaHostAllocDefault);
             if (e != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, e, "cudaHostAlloc(compressed region)"); }
@@ -1174,8 +1196,20 @@ extern "C" void bsq_stream_close(bsq_stream* s) {
     if (s->zfp) fclose(s->zfp);
     for (auto& b : s->buf) if (b.mem) cudaFreeHost(b.mem);
     for (auto& z : s->zb) if (z.mem) cudaFreeHost(z.mem);
-    if (s->p) cudaSetDevice(s->p->cfg.device_id);
-    s->zdev.release(); s->mdev.release(); s->sdev.release(); s->rdev[0].release(); s->rdev[1].release();
+    if (s->p) {
+        cudaSetDevice(s->p->cfg.device_id);
+        if (s->p->copy_stream) cudaStreamSynchronize(s->p->copy_stream);   // a prefetched region may still be inflating
+        if (s->p->stream) cudaStreamSynchronize(s->p->stream);
+    }
+    for (auto& j : s->job) {
+        j.zdev.release(); j.mdev.release(); j.sdev.release();
+        if (j.status) cudaFreeHost(j.status);
+        if (j.e_start) cudaEventDestroy(j.e_start);
+        if (j.e_h2d) cudaEventDestroy(j.e_h2d);
+        if (j.e_done) cudaEventDestroy(j.e_done);
+    }
+    if (s->e_carry) cudaEventDestroy(s->e_carry);
+    s->rdev[0].release(); s->rdev[1].release();
     delete s;
 }
 
@@ -1201,11 +1235,153 @@ static bsq_status trim_to_whole_batches(bsq_parser* p, uint32_t want, bool is_la
     return BSQ_OK;
 }
 
+// ---- BGZF regions inflated on the device, two in flight ----------------------------------------------------------
+// H2D of the compressed members + k_inflate_members + k_crc32_members of one region, on the copy stream
+static bsq_status launch_inflate(bsq_stream* s, bsq_stream::InfJob& J, int slot, int rbuf) {
+    bsq_parser* p = s->p;
+    bsq_stream::ZBuf& z = s->zb[slot];
+    J.slot = slot; J.eof = s->buf[slot].eof; J.nm = (uint32_t)z.members.size(); J.out_bytes = z.out_bytes; J.z_bytes = z.n;
+    // room for the carry of the region before it: generous (device memory is not the constraint), grown with what was seen
+    J.room = std::max<uint64_t>(32ull << 20, 2 * s->dev_carry_len + (1ull << 20));
+    J.room = (J.room + 255) & ~255ull;
+    CK(s->rdev[rbuf].ensure(J.room + J.out_bytes + 256, 1 << 20));
+    CK(cudaEventRecord(J.e_start, p->copy_stream));
+    if (J.nm) {
+        CK(J.zdev.ensure(z.n + 64, 1 << 20));
+        CK(J.mdev.ensure(sizeof(InflateMember) * J.nm, 1 << 16));
+        CK(J.sdev.ensure(4ull * J.nm, 1 << 12));
+        CK(cudaMemcpyAsync(J.zdev.p, z.mem, z.n, cudaMemcpyHostToDevice, p->copy_stream));
+        CK(cudaMemcpyAsync(J.mdev.p, z.members.data(), sizeof(InflateMember) * J.nm, cudaMemcpyHostToDevice, p->copy_stream));
+    }
+    CK(cudaEventRecord(J.e_h2d, p->copy_stream));
+    if (J.nm) {
+        uint8_t* dst = s->rdev[rbuf].as<uint8_t>() + J.room;
+        k_inflate_members<<<(J.nm + kInfPerCta - 1) / kInfPerCta, kInfWarps * 32, sizeof(InflateTables) * kInfPerCta, p->copy_stream>>>(
+            J.zdev.as<uint8_t>(), dst, J.mdev.as<InflateMember>(), J.nm, J.sdev.as<uint32_t>());
+        k_crc32_members<<<(J.nm + kCrcWarps - 1) / kCrcWarps, kCrcWarps * 32, 0, p->copy_stream>>>(
+            dst, J.mdev.as<InflateMember>(), J.nm, J.sdev.as<uint32_t>());
+        CK(cudaGetLastError());
+        if (J.nm > J.status_cap) {
+            if (J.status) cudaFreeHost(J.status);
+            J.status = nullptr; J.status_cap = 0;
+            CK(cudaHostAlloc(reinterpret_cast<void**>(&J.status), 4ull * (J.nm + 1024), cudaHostAllocDefault));
+            J.status_cap = J.nm + 1024;
+        }
+        CK(cudaMemcpyAsync(J.status, J.sdev.p, 4ull * J.nm, cudaMemcpyDeviceToHost, p->copy_stream));
+    }
+    CK(cudaEventRecord(J.e_done, p->copy_stream));
+    J.launched = true;
+    return BSQ_OK;
+}
+
+static bsq_status stream_next_device_inflate(bsq_stream* s, uint32_t want, bsq_pass_result* out) {
+    bsq_parser* p = s->p;
+    bsq_stream::InfJob& J = s->job[s->jcur];
+    bsq_stream::InfJob& N = s->job[s->jcur ^ 1];
+    const int rb = s->jcur, rb_prev = s->jcur ^ 1;           // region buffers: this region / the previous (and the next) one
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!J.launched) {                                       // the first region, or the reader was not ahead
+        int slot;
+        {
+            std::unique_lock<std::mutex> lk(s->mu);
+            s->cv.wait(lk, [&] { return s->buf[s->next_take].state == 1; });
+            slot = s->next_take;
+            s->buf[slot].state = 2;
+            s->next_take = (s->next_take + 1) % s->n_slots;
+        }
+        if (s->read_error) { p->last_error = "read error / malformed BGZF member"; s->finished = true; return BSQ_E_IO; }
+        bsq_status st = launch_inflate(s, J, slot, rb);
+        if (st != BSQ_OK) { s->finished = true; return st; }
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    s->st.wait_reader_s += std::chrono::duration<double>(t1 - t0).count();
+    s->cur = J.slot;
+    // the unconsumed tail of the previous region goes in front of this one, device to device
+    uint64_t region_off = J.room - s->dev_carry_len;
+    if (s->dev_carry_len > J.room) {
+        // (a carry larger than the room left for it: wait for this region, then rebuild it in a larger buffer)
+        CK(cudaEventSynchronize(J.e_done));
+        DevBuf big;
+        CK(big.ensure(s->dev_carry_len + J.out_bytes + 512, 1 << 20));
+        CK(cudaMemcpyAsync(big.as<uint8_t>() + s->dev_carry_len, s->rdev[rb].as<uint8_t>() + J.room, J.out_bytes, cudaMemcpyDeviceToDevice, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        std::swap(big, s->rdev[rb]);
+        big.release();
+        J.room = s->dev_carry_len;
+        region_off = 0;
+    }
+    if (s->dev_carry_len)
+        CK(cudaMemcpyAsync(s->rdev[rb].as<uint8_t>() + region_off, s->rdev[rb_prev].as<uint8_t>() + s->dev_carry_off, s->dev_carry_len,
+                           cudaMemcpyDeviceToDevice, p->stream));
+    CK(cudaEventRecord(s->e_carry, p->stream));
+    // the next region, if the reader has it: its compressed bytes travel and inflate while this region is parsed
+    if (!J.eof && !N.launched) {
+        int slot = -1;
+        {
+            std::lock_guard<std::mutex> lk(s->mu);
+            if (s->buf[s->next_take].state == 1 && !s->read_error) {
+                slot = s->next_take;
+                s->buf[slot].state = 2;
+                s->next_take = (s->next_take + 1) % s->n_slots;
+            }
+        }
+        if (slot >= 0) {
+            CK(cudaStreamWaitEvent(p->copy_stream, s->e_carry, 0));   // it overwrites the buffer the carry was just read from
+            bsq_status st = launch_inflate(s, N, slot, rb_prev);
+            if (st != BSQ_OK) { s->finished = true; return st; }
+        }
+    }
+    // this region: inflated?
+    CK(cudaEventSynchronize(J.e_done));
+    float ms_copy = 0.f, ms_inf = 0.f;
+    cudaEventElapsedTime(&ms_copy, J.e_start, J.e_h2d);
+    cudaEventElapsedTime(&ms_inf, J.e_h2d, J.e_done);
+    s->st.h2d_s += ms_copy * 1e-3; s->st.inflate_s += ms_inf * 1e-3; s->st.compressed_bytes += J.z_bytes;
+    for (uint32_t i = 0; i < J.nm; ++i)
+        if (J.status[i] != 0u) {
+            char t[128];
+            snprintf(t, sizeof t, "BGZF member %u of the region does not inflate (status %u)", i, J.status[i]);
+            p->last_error = t; s->finished = true;
+            return BSQ_E_IO;
+        }
+    const uint64_t n = s->dev_carry_len + J.out_bytes;
+    uint8_t* region = s->rdev[rb].as<uint8_t>() + region_off;
+    const bool is_last = J.eof;
+    const uint32_t m = (uint32_t)p->cfg.batch_size;
+    uint32_t w = want;
+    if (!is_last && (want & BSQ_WANT_BATCHES)) w |= BSQ_WANT_OFFSETS;   // the cut between regions needs offsets
+    InputFeed none;
+    bsq_status rc = run_pass(p, region, n, s->stream_pos, s->records_done, is_last ? 1 : 0, w, kWindowMax, none, out);
+    if (rc != BSQ_OK) { s->finished = true; return rc; }
+    rc = trim_to_whole_batches(p, want, is_last, m, out);
+    if (rc != BSQ_OK) { s->finished = true; return rc; }
+    s->rcur = rb; s->region_dev_off = region_off;
+    s->region_dev_n = n; s->region_host_valid = false;
+    s->region_ptr = nullptr; s->region_n = n;
+    s->st.parse_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+    s->st.regions += 1;
+    const uint64_t consumed = (uint64_t)out->bytes_consumed;
+    s->dev_carry_off = region_off + consumed; s->dev_carry_len = n - consumed;
+    s->stream_pos += (int64_t)consumed;
+    s->records_done += out->n_records;
+    if (out->stop.code != BSQ_OK) s->finished = true;
+    // the compressed bytes of this region are on the device: its pinned buffer goes back to the reader
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        s->buf[J.slot].state = 0;
+    }
+    s->cv.notify_all();
+    J.launched = false;
+    s->jcur ^= 1;
+    return BSQ_OK;
+}
+
 extern "C" bsq_status bsq_stream_next(bsq_stream* s, uint32_t want, bsq_pass_result* out) {
     if (!s || !out) return BSQ_E_ARG;
     bsq_parser* p = s->p;
     CK(cudaSetDevice(p->cfg.device_id));
     if (s->finished) { p->last_error = "stream already finished"; return BSQ_E_STATE; }
+    if (s->gpu_inflate) return stream_next_device_inflate(s, want, out);
     // the previous region's buffer goes back to the reader
     if (s->cur >= 0) {
         {
@@ -1223,71 +1399,11 @@ extern "C" bsq_status bsq_stream_next(bsq_stream* s, uint32_t want, bsq_pass_res
         b = &s->buf[s->next_take];
         b->state = 2;
         s->cur = s->next_take;
-        s->next_take ^= 1;
+        s->next_take = (s->next_take + 1) % s->n_slots;
     }
     const auto t1 = std::chrono::steady_clock::now();
     s->st.wait_reader_s += std::chrono::duration<double>(t1 - t0).count();
     if (s->read_error) { p->last_error = "read / inflate error"; s->finished = true; return BSQ_E_IO; }
-    if (s->gpu_inflate) {
-        // ---- compressed members -> device -> k_inflate_members -> pass over the device region ----
-        bsq_stream::ZBuf& z = s->zb[s->cur];
-        const int nxt = s->rcur ^ 1;
-        const uint64_t n = s->dev_carry_len + z.out_bytes;
-        CK(s->rdev[nxt].ensure(n + 256, 1 << 20));
-        uint8_t* region = s->rdev[nxt].as<uint8_t>();
-        if (s->dev_carry_len)   // the unconsumed tail of the previous region, device to device
-            CK(cudaMemcpyAsync(region, s->rdev[s->rcur].as<uint8_t>() + s->dev_carry_off, s->dev_carry_len, cudaMemcpyDeviceToDevice, p->stream));
-        const uint32_t nm = (uint32_t)z.members.size();
-        if (nm) {
-            CK(s->zdev.ensure(z.n + 64, 1 << 20));
-            CK(s->mdev.ensure(sizeof(InflateMember) * nm, 1 << 16));
-            CK(s->sdev.ensure(4ull * nm, 1 << 12));
-            CK(cudaEventRecord(p->ev[0], p->stream));
-            CK(cudaMemcpyAsync(s->zdev.p, z.mem, z.n, cudaMemcpyHostToDevice, p->stream));
-            CK(cudaMemcpyAsync(s->mdev.p, z.members.data(), sizeof(InflateMember) * nm, cudaMemcpyHostToDevice, p->stream));
-            CK(cudaEventRecord(p->ev[1], p->stream));
-            k_inflate_members<<<(nm + kInfPerCta - 1) / kInfPerCta, kInfWarps * 32, sizeof(InflateTables) * kInfPerCta, p->stream>>>(
-                s->zdev.as<uint8_t>(), region + s->dev_carry_len, s->mdev.as<InflateMember>(), nm, s->sdev.as<uint32_t>());
-            k_crc32_members<<<(nm + kCrcWarps - 1) / kCrcWarps, kCrcWarps * 32, 0, p->stream>>>(
-                region + s->dev_carry_len, s->mdev.as<InflateMember>(), nm, s->sdev.as<uint32_t>());
-            CK(cudaGetLastError());
-            CK(cudaEventRecord(p->ev[2], p->stream));
-            s->status_host.resize(nm);
-            CK(cudaMemcpyAsync(s->status_host.data(), s->sdev.p, 4ull * nm, cudaMemcpyDeviceToHost, p->stream));
-            CK(cudaStreamSynchronize(p->stream));
-            float ms_copy = 0.f, ms_inf = 0.f;
-            cudaEventElapsedTime(&ms_copy, p->ev[0], p->ev[1]);
-            cudaEventElapsedTime(&ms_inf, p->ev[1], p->ev[2]);
-            s->st.h2d_s += ms_copy * 1e-3; s->st.inflate_s += ms_inf * 1e-3; s->st.compressed_bytes += z.n;
-            for (uint32_t i = 0; i < nm; ++i)
-                if (s->status_host[i] != 0u) {
-                    char t[128];
-                    snprintf(t, sizeof t, "BGZF member %u of the region does not inflate (status %u)", i, s->status_host[i]);
-                    p->last_error = t; s->finished = true;
-                    return BSQ_E_IO;
-                }
-        }
-        const bool is_last = b->eof;
-        const uint32_t m = (uint32_t)p->cfg.batch_size;
-        uint32_t w = want;
-        if (!is_last && (want & BSQ_WANT_BATCHES)) w |= BSQ_WANT_OFFSETS;   // the cut between regions needs offsets
-        InputFeed none;
-        bsq_status rc = run_pass(p, region, n, s->stream_pos, s->records_done, is_last ? 1 : 0, w, kWindowMax, none, out);
-        if (rc != BSQ_OK) { s->finished = true; return rc; }
-        rc = trim_to_whole_batches(p, want, is_last, m, out);
-        if (rc != BSQ_OK) { s->finished = true; return rc; }
-        s->rcur = nxt;
-        s->region_dev_n = n; s->region_host_valid = false;
-        s->region_ptr = nullptr; s->region_n = n;
-        s->st.parse_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
-        s->st.regions += 1;
-        const uint64_t consumed = (uint64_t)out->bytes_consumed;
-        s->dev_carry_off = consumed; s->dev_carry_len = n - consumed;
-        s->stream_pos += (int64_t)consumed;
-        s->records_done += out->n_records;
-        if (out->stop.code != BSQ_OK) s->finished = true;
-        return BSQ_OK;
-    }
     uint8_t* region;
     if (s->carry.size() <= s->carry_cap) {
         region = b->mem + s->carry_cap - s->carry.size();
@@ -1344,7 +1460,7 @@ extern "C" const uint8_t* bsq_stream_region(const bsq_stream* cs, uint64_t* n, i
             s->region_host.resize(s->region_dev_n ? s->region_dev_n : 1);
             cudaSetDevice(s->p->cfg.device_id);
             if (s->region_dev_n &&
-                cudaMemcpy(s->region_host.data(), s->rdev[s->rcur].p, s->region_dev_n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                cudaMemcpy(s->region_host.data(), s->rdev[s->rcur].as<uint8_t>() + s->region_dev_off, s->region_dev_n, cudaMemcpyDeviceToHost) != cudaSuccess) {
                 cudaGetLastError();
                 return nullptr;
             }

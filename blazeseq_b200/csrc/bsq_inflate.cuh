@@ -71,6 +71,7 @@ struct BitReader {
     const uint32_t* wp;                    // next word to fetch
     const uint32_t* wend;                  // one past the last word that holds payload bytes
     const uint32_t* w0;                    // first word
+    uint32_t overrun;                      // the reader ran words past the payload (a damaged stream)
     uint64_t buf;
     uint32_t cnt;                          // valid bits in buf
     uint32_t nextw;                        // prefetched word
@@ -90,6 +91,7 @@ __device__ __forceinline__ void br_init(BitReader& b, const uint8_t* p, uint32_t
     b.nextw = b.wp < b.wend ? __ldg(b.wp) : 0u;
     ++b.wp;
     b.base_bytes = base_bytes;
+    b.overrun = 0;
 }
 // payload bits consumed so far (the prefetched word is not in buf yet)
 __device__ __forceinline__ uint64_t br_consumed(const BitReader& b) {
@@ -100,7 +102,8 @@ __device__ __forceinline__ void br_fill(BitReader& b) {
     if (b.cnt <= 32u) {
         b.buf |= (uint64_t)b.nextw << b.cnt;
         b.cnt += 32u;
-        b.nextw = b.wp < b.wend ? __ldg(b.wp) : 0u;   // (past the end: zeros; the overrun is caught by br_consumed)
+        b.nextw = b.wp < b.wend ? __ldg(b.wp) : 0u;   // (past the end: zeros)
+        if (b.wp > b.wend + 4) b.overrun = 1u;        // a damaged stream must end the member, not spin on zeros
         ++b.wp;
     }
 }
@@ -194,13 +197,16 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members(const uint8_
     int tables = 0;                        // 0 none, 1 fixed, 2 dynamic (leader)
     if (leader) br_init(br, src0, M.src_len, 0u);
     bool done = !valid;                    // (whole group)
+    if (__all_sync(0xFFFFFFFFu, done)) return;   // a warp without members
     uint32_t pend_pos = 0xFFFFFFFFu;       // a match byte loaded but not yet stored (every lane)
     uint8_t pend_val = 0;
 
     while (true) {
         // ---- block headers: the leaders that stand between two blocks ----
         uint32_t st_len = 0, st_src = 0, st_go = 0;
-        if (leader && !done && !in_block && !finished && err == 0u) {
+        const bool at_header = leader && !done && !in_block && !finished && err == 0u;
+        if (__any_sync(kFull, at_header)) {                    // (rare: a few blocks per member)
+        if (at_header) {
             br_fill(br);
             last = br_take(br, 1) != 0u;
             const uint32_t btype = br_take(br, 2);
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members(const uint8_
         st_go = __shfl_sync(kFull, st_go, lead);
         st_len = __shfl_sync(kFull, st_len, lead);
         st_src = __shfl_sync(kFull, st_src, lead);
-        uint32_t p0 = __shfl_sync(kFull, pos, lead);
+        const uint32_t p0 = __shfl_sync(kFull, pos, lead);
         if (st_go != 0u)
             for (uint32_t i = gl; i < st_len; i += kInfLanes) dst[p0 + i] = src0[st_src + i];
         __syncwarp();
@@ -274,6 +280,7 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members(const uint8_
             pos += st_len;
             br_init(br, src0 + st_src + st_len, M.src_len - st_src - st_len, st_src + st_len);
             if (last) finished = true;
+        }
         }
         // ---- compressed blocks: the leader decodes up to its next match ----
         uint32_t mlen = 0, mdist = 0;
@@ -322,13 +329,13 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members(const uint8_
                 } else { err = 1u; mlen = 0; break; }
                 br_fill(br);
                 mdist = base + br_take(br, extra);
-                if (mdist > pos || pos + mlen > cap) { err = 2u; mlen = 0; }
+                if (mdist > pos || pos + mlen > cap || mdist > 32768u) { err = 2u; mlen = 0; }
                 break;
             }
         }
-        mlen = __shfl_sync(kFull, mlen, lead);
-        mdist = __shfl_sync(kFull, mdist, lead);
-        p0 = __shfl_sync(kFull, pos, lead);
+        const uint32_t mm = __shfl_sync(kFull, mlen | (mdist << 16), lead);   // (mlen <= 258, mdist <= 32768)
+        mlen = mm & 0xFFFFu; mdist = mm >> 16;
+        const uint32_t p0 = __shfl_sync(kFull, pos, lead);
         // the previous match's bytes were only LOADED when it was decoded (the decoder does not need them to go on):
         // they are stored now, one decode run later, when the loads have long returned
         if (pend_pos != 0xFFFFFFFFu) { dst[pend_pos] = pend_val; pend_pos = 0xFFFFFFFFu; }
@@ -347,21 +354,22 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members(const uint8_
         }
         __syncwarp();                                                 // (outside every branch: groups differ in what they do)
         if (leader && mlen != 0u) pos = p0 + mlen;
-        // a damaged stream must end the member, not spin: the reader never runs more than a few words past the payload
-        if (leader && br.wp > br.wend + 4) err = 3u;
         // ---- members that are through ----
-        const uint32_t fin = __shfl_sync(kFull, (uint32_t)(finished || err != 0u), lead);
-        if (fin != 0u && !done) {
-            if (pend_pos != 0xFFFFFFFFu) { dst[pend_pos] = pend_val; pend_pos = 0xFFFFFFFFu; }
-            done = true;
-            if (leader) {
-                uint32_t st = err;
-                if (st == 0u && br_consumed(br) > (uint64_t)M.src_len * 8u) st = 3u;
-                if (st == 0u && pos != cap) st = 4u;
-                status[m] = st;
+        if (leader && br.overrun) err = 3u;
+        if (__any_sync(kFull, leader && !done && (finished || err != 0u))) {   // (rare: somebody is through)
+            const uint32_t fin = __shfl_sync(kFull, (uint32_t)(finished || err != 0u), lead);
+            if (fin != 0u && !done) {
+                if (pend_pos != 0xFFFFFFFFu) { dst[pend_pos] = pend_val; pend_pos = 0xFFFFFFFFu; }
+                done = true;
+                if (leader) {
+                    uint32_t st = err;
+                    if (st == 0u && br_consumed(br) > (uint64_t)M.src_len * 8u) st = 3u;
+                    if (st == 0u && pos != cap) st = 4u;
+                    status[m] = st;
+                }
             }
+            if (__all_sync(kFull, done)) break;
         }
-        if (__all_sync(kFull, done)) break;
     }
 }
 
