@@ -214,6 +214,35 @@ def reference_arm(args):
     }))
 
 
+def pin_to_gpu_numa_node(index: int) -> dict:
+    """Binds this process to the CPUs of the NUMA node the GPU hangs off (PCI sysfs), so that its pinned buffers and
+    reader threads are local to the GPU's root port.  Returns what it found (reported in the e2e object)."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]                      # sysfs uses a 4-digit PCI domain
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(f"{base}/numa_node").read())
+        cpulist = open(f"{base}/local_cpulist").read().strip()
+        info["numa_node"] = node
+        info["cpus"] = cpulist
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        if cpus and node >= 0:
+            os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or cpus)
+            info["bound"] = True
+    except Exception as e:   # (no sysfs entry, a container without the topology): nothing to bind to
+        info["note"] = repr(e)[:120]
+    return info
+
+
 class _DevPtr:
     """A device address as a torch-importable array (zero copy)."""
 
@@ -262,6 +291,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    host_info = pin_to_gpu_numa_node(local)   # before any pinned allocation: first touch decides where it lives
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -668,7 +698,7 @@ def main():
         d2h = 8 * (int(r.n_batches) + 1) * 2 + 8 + 16 + 168   # batch directory + error word + scan totals
         e2e = {"value": total_reads / dt, "unit": "reads/s", "h2d_bytes_per_step": size,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
-               "result": "DeviceFastqBatch SoA left on the device + host batch directory"}
+               "result": "DeviceFastqBatch SoA left on the device + host batch directory", "host": host_info}
         if args.mode == "batches":
             # ... and with the reference's HOST product: the whole FastqBatch SoA copied back to pinned memory
             v = gpu.soa_view()
