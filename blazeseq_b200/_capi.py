@@ -27,6 +27,7 @@ SYMBOLS = [
     "bsq_summarize_device", "bsq_shard_prefix", "bsq_stream_open", "bsq_stream_next", "bsq_stream_region",
     "bsq_stream_get_stats", "bsq_stream_close", "bsq_quality_sums", "bsq_soa_to_host", "bsq_stream_region_info",
     "bsq_fasta_parse_device", "bsq_fasta_parse_host", "bsq_fasta_get", "bsq_fasta_to_host",
+    "bsq_gzip_open", "bsq_gzip_read", "bsq_gzip_error", "bsq_gzip_close",
 ]
 
 
@@ -169,6 +170,14 @@ def lib():
         getattr(L, name).restype = i32
     L.bsq_soa_to_host.restype = i32
     L.bsq_quality_sums.restype = i32
+    L.bsq_gzip_open.argtypes = [C.c_char_p, i32, u64, C.POINTER(vp)]
+    L.bsq_gzip_open.restype = i32
+    L.bsq_gzip_read.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.bsq_gzip_read.restype = i32
+    L.bsq_gzip_error.argtypes = [vp]
+    L.bsq_gzip_error.restype = C.c_char_p
+    L.bsq_gzip_close.argtypes = [vp]
+    L.bsq_gzip_close.restype = None
     for name in ("bsq_stream_open", "bsq_stream_next", "bsq_stream_get_stats", "bsq_create", "bsq_get_offsets", "bsq_get_batch", "bsq_get_soa", "bsq_batch_to_host",
                  "bsq_offsets_to_host", "bsq_last_timing", "bsq_synth_device", "bsq_summarize_device",
                  "bsq_shard_prefix"):

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libblazeseq_gpu.so")
 SOURCES = [os.path.join(SRC, "bsq_capi.cu")]
-DEPS = SOURCES + [os.path.join(SRC, f) for f in ("bsq_device.cuh", "bsq_aux.cuh", "tile_math.h")] + [
+DEPS = SOURCES + [os.path.join(SRC, f) for f in ("bsq_device.cuh", "bsq_aux.cuh", "bsq_inflate.cuh", "bsq_fasta.cuh", "bsq_pgzip.h", "tile_math.h")] + [
     os.path.join(HERE, "..", "include", "blazeseq_gpu.h")]
 
 NVCC_FLAGS = [

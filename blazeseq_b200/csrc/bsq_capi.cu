@@ -14,6 +14,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdarg>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <cstdio>
@@ -28,6 +29,7 @@
 #include "bsq_device.cuh"
 #include "bsq_inflate.cuh"
 #include "bsq_fasta.cuh"
+#include "bsq_pgzip.h"
 
 using namespace bsq;
 
@@ -842,6 +844,7 @@ struct bsq_stream {
     int kind = BSQ_SOURCE_PLAIN;
     FILE* fp = nullptr;
     gzFile gz = nullptr;
+    std::unique_ptr<bsq_pgz::Reader> pgz;   // ordinary gzip, decoded by host threads (bsq_pgzip.h)
     uint64_t region_bytes = 0, carry_cap = 0;
     struct Buf { uint8_t* mem = nullptr; uint64_t n_new = 0; bool eof = false; int state = 0; /* 0 free, 1 ready, 2 in use */ };
     static constexpr int kMaxSlots = 3;
@@ -1088,7 +1091,8 @@ struct bsq_stream {
             while (got < region_bytes) {
                 const size_t ask = (size_t)std::min<uint64_t>(region_bytes - got, 1u << 30);
                 long k;
-                if (kind == BSQ_SOURCE_GZIP) k = gzread(gz, dst + got, (unsigned)std::min<size_t>(ask, 1u << 30));
+                if (pgz) k = (long)pgz->read(dst + got, ask);
+                else if (kind == BSQ_SOURCE_GZIP) k = gzread(gz, dst + got, (unsigned)std::min<size_t>(ask, 1u << 30));
                 else k = (long)fread(dst + got, 1, ask, fp);
                 if (k < 0) { err = true; break; }
                 if (k == 0) { eof = true; break; }
@@ -1107,6 +1111,34 @@ struct bsq_stream {
         }
     }
 };
+
+// ------------------------------------------------------------------------------------------------
+// RapidgzipReader: the parallel gzip decoder on its own (host only)
+// ------------------------------------------------------------------------------------------------
+
+struct bsq_gzip { bsq_pgz::Reader r; std::string err; };
+
+extern "C" bsq_status bsq_gzip_open(const char* path, int32_t parallelism, uint64_t chunk_bytes, bsq_gzip** out) {
+    if (!path || !out) return BSQ_E_ARG;
+    *out = nullptr;
+    bsq_gzip* g = new (std::nothrow) bsq_gzip();
+    if (!g) return BSQ_E_NOMEM;
+    if (!g->r.open(path, parallelism, chunk_bytes ? (size_t)chunk_bytes : (2u << 20))) { delete g; return BSQ_E_IO; }
+    *out = g;
+    return BSQ_OK;
+}
+
+extern "C" bsq_status bsq_gzip_read(bsq_gzip* g, uint8_t* dst, uint64_t n, uint64_t* got) {
+    if (!g || (!dst && n) || !got) return BSQ_E_ARG;
+    const int64_t k = g->r.read(dst, (size_t)n);
+    if (k < 0) { *got = 0; return BSQ_E_IO; }
+    *got = (uint64_t)k;
+    return BSQ_OK;
+}
+
+extern "C" const char* bsq_gzip_error(const bsq_gzip* g) { return g ? g->r.error().c_str() : ""; }
+
+extern "C" void bsq_gzip_close(bsq_gzip* g) { delete g; }
 
 extern "C" bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t source_kind, uint64_t region_bytes,
                                       bsq_stream** out) {
@@ -1141,9 +1173,18 @@ extern "C" bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t s
                 s->io_threads = std::min(nt, 8);
             }
         } else {
+            // an ordinary gzip stream: `inflate_threads` host threads decode it speculatively in parallel
+            // (RapidgzipReader(parallelism), readers.mojo:380-443); one thread = zlib's gzread
+            const bool is_gzip = f && h[0] == 0x1f && h[1] == 0x8b;
             if (f) fclose(f);
-            s->gz = gzopen(path, "rb");
-            if (s->gz) gzbuffer(s->gz, 1 << 20);
+            if (is_gzip && p->cfg.inflate_threads != 1) {
+                s->pgz.reset(new bsq_pgz::Reader());
+                if (!s->pgz->open(path, p->cfg.inflate_threads)) s->pgz.reset();
+            }
+            if (!s->pgz) {
+                s->gz = gzopen(path, "rb");
+                if (s->gz) gzbuffer(s->gz, 1 << 20);
+            }
         }
     } else {
         s->fp = fopen(path, "rb");
@@ -1155,7 +1196,7 @@ extern "C" bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t s
             s->io_threads = std::min(nt, 8);
         }
     }
-    if (!s->gz && !s->fp && !s->zfp) { p->last_error = std::string("cannot open ") + path; delete s; return BSQ_E_ARG; }
+    if (!s->gz && !s->fp && !s->zfp && !s->pgz) { p->last_error = std::string("cannot open ") + path; delete s; return BSQ_E_ARG; }
     s->region_bytes = region_bytes ? region_bytes : (256ull << 20);
     // room in front of every pinned region for the previous region's unconsumed tail (a larger tail takes the
     // `big` path of bsq_stream_next)

@@ -153,14 +153,65 @@ class GZFile(Reader):
         return k
 
 
-class RapidgzipReader(GZFile):
-    """readers.mojo:380-443.  rapidgzip is not in this image; zlib inflates the same bytes.  Through the
-    native pipeline (FastqParser with native_io) `parallelism` host threads inflate the members of a BGZF
-    file block-parallel (0 = all cores); any other gzip stream is inflated sequentially."""
+class RapidgzipReader(Reader):
+    """readers.mojo:380-443: parallel gzip decompression, `parallelism` worker threads (0 = all cores).
 
-    def __init__(self, path, parallelism: int = 0):
-        super().__init__(path)
-        self.parallelism = parallelism
+    rapidgzip is not in this image; the native library carries its own two-stage speculative decoder
+    (csrc/bsq_pgzip.h, `bsq_gzip_*`): chunks of the compressed file are inflated in parallel from the first
+    deflate block found in each, references into the unknown window are resolved when the chunks are stitched,
+    every member's CRC-32 is verified.  Through FastqParser's native pipeline a BGZF file is inflated on the
+    device instead (k_inflate_members)."""
+
+    def __init__(self, path, parallelism: int = 0, *, chunk_bytes: int = 0):
+        self.path = os.fspath(path)
+        self.parallelism = int(parallelism)
+        self.chunk_bytes = int(chunk_bytes)       # compressed bytes per speculative chunk (0 = 2 MiB)
+        self._h = C.c_void_p()
+        self._closed = False
+        with open(self.path, "rb"):      # "Raises: Error: If the file cannot be opened" (readers.mojo:405-407)
+            pass
+
+    def _open(self):
+        # the decoder threads start on the first read: a FastqParser that takes the file through the library's own
+        # stream pipeline never needs this handle
+        st = capi.lib().bsq_gzip_open(self.path.encode(), self.parallelism, self.chunk_bytes, C.byref(self._h))
+        if st != 0:
+            raise OSError(f"RapidgzipReader: cannot open {self.path} as gzip")
+
+    def read_to_buffer(self, buf, amt, pos=0):
+        self._check(buf, amt, pos)
+        if amt == 0:
+            return 0
+        if self._closed:
+            raise ValueError("RapidgzipReader is closed")
+        if not self._h:
+            self._open()
+        view = buf[pos:pos + amt]
+        if not (isinstance(view, np.ndarray) and view.dtype == np.uint8 and view.flags["C_CONTIGUOUS"]):
+            tmp = np.empty(amt, dtype=np.uint8)
+            k = self._read(tmp)
+            buf[pos:pos + k] = tmp[:k]
+            return k
+        return self._read(view)
+
+    def _read(self, arr: np.ndarray) -> int:
+        got = C.c_uint64(0)
+        st = capi.lib().bsq_gzip_read(self._h, arr.ctypes.data_as(C.c_void_p), arr.size, C.byref(got))
+        if st != 0:
+            raise BlazeSeqError("Error reading from gzip file: " + capi.lib().bsq_gzip_error(self._h).decode("latin-1"))
+        return int(got.value)
+
+    def close(self):
+        self._closed = True
+        if getattr(self, "_h", None):
+            capi.lib().bsq_gzip_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ------------------------------------------------------------------------------------------------
@@ -649,7 +700,8 @@ class FastqParser:
                               self._batch_size, device_id, self.config.buffer_capacity,
                               self.config.buffer_max_capacity, self.config.buffer_growth_enabled,
                               force_id_slow_path=_force_id_slow_path,
-                              inflate_threads=int(getattr(reader, "parallelism", 0) or 0), host_inflate=host_inflate)
+                              inflate_threads=(1 if type(reader) is GZFile else int(getattr(reader, "parallelism", 0) or 0)),
+                              host_inflate=host_inflate)
         self._carry = np.zeros(0, np.uint8)   # unconsumed tail of the previous region
         self._stream_pos = 0                  # stream offset of _carry[0]
         self._records_done = 0                # records of finished regions

@@ -197,8 +197,9 @@ bsq_status bsq_parse_host(bsq_parser* p, const uint8_t* host_bytes, uint64_t n,
 typedef struct bsq_stream bsq_stream;
 #define BSQ_SOURCE_PLAIN 0
 #define BSQ_SOURCE_GZIP 1          /* gzip: BGZF members are inflated on the device, one warp per member (or block-parallel by
-                                      cfg.inflate_threads host threads with cfg.host_inflate); any other gzip stream goes
-                                      through zlib on the reader thread */
+                                      cfg.inflate_threads host threads with cfg.host_inflate); any other gzip stream is
+                                      decoded by cfg.inflate_threads host threads with the two-stage speculative decoder
+                                      of bsq_gzip_* below (one zlib thread when inflate_threads == 1) */
 #define BSQ_SOURCE_AUTO 2          /* by suffix: .gz / .bgz -> gzip (python/blazeseq_parser.mojo:100-114) */
 
 typedef struct bsq_stream_stats {
@@ -226,6 +227,20 @@ const uint8_t* bsq_stream_region(const bsq_stream* s, uint64_t* n, int64_t* stre
 void bsq_stream_region_info(const bsq_stream* s, uint64_t* n, int64_t* stream_offset, int64_t* first_record);
 bsq_status bsq_stream_get_stats(const bsq_stream* s, bsq_stream_stats* out);
 void bsq_stream_close(bsq_stream* s);
+
+/* ---- RapidgzipReader (blazeseq/io/readers.mojo:380-443) ------------------------------------ */
+
+/* Parallel decoder for ordinary gzip files on host threads -- `RapidgzipReader(path, parallelism)`: the compressed file
+ * is cut into chunks, every chunk is inflated speculatively from the first deflate block found in it (references into
+ * the unknown 32 KiB window are kept as markers), chunks are stitched in order, markers resolved and every member's
+ * CRC-32 / ISIZE verified.  Host-only: it needs no parser and no device.  parallelism 0 = all cores.
+ * bsq_gzip_read is `Reader.read_to_buffer` (readers.mojo:421-443) / gzread: *got = bytes written, 0 at the end. */
+typedef struct bsq_gzip bsq_gzip;
+/* chunk_bytes: compressed bytes per speculative chunk (0 = 2 MiB, at least 64 KiB) */
+bsq_status bsq_gzip_open(const char* path, int32_t parallelism, uint64_t chunk_bytes, bsq_gzip** out);
+bsq_status bsq_gzip_read(bsq_gzip* g, uint8_t* dst, uint64_t n, uint64_t* got);
+const char* bsq_gzip_error(const bsq_gzip* g);
+void bsq_gzip_close(bsq_gzip* g);
 
 /* ---- results of the last pass -------------------------------------------------------------- */
 
