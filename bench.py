@@ -385,10 +385,11 @@ def main():
     # configs[4]: a .fastq.gz through the native stream pipeline (bsq_stream_*), file -> results
     # ------------------------------------------------------------------------------------------------
     def gzip_leg(gib, region_mib=256):
-        """Writes `gib` of the 150 bp stream as a plain file, as BGZF (gzip level 6, 64 KiB members) and as ordinary
-        multi-member gzip, and streams each through bsq_stream_next(WANT_BATCHES).  BGZF: the compressed members
-        cross PCIe and are inflated on the device (k_inflate_members); ordinary gzip goes through zlib on the reader
-        thread.  The CPU arm beside it: zlib on every host thread (BGZF members) feeding nothing (inflate only)."""
+        """Writes `gib` of the 150 bp stream as a plain file, as BGZF (gzip level 6, 64 KiB members) and as an ordinary
+        single-member gzip file, and streams each through bsq_stream_next(WANT_BATCHES).  BGZF: the compressed members
+        cross PCIe and are inflated on the device (k_inflate_members); ordinary gzip is decoded speculatively in parallel
+        by the host threads (bsq_pgzip.h), and by one zlib thread for comparison.  The CPU arm beside it: zlib on every
+        host thread (BGZF members) feeding nothing (inflate only)."""
         import gzip as gz
         import shutil
         import zlib
@@ -408,12 +409,22 @@ def main():
         try:
             plain, gzp, bgz = (os.path.join(tmp, n) for n in ("x.fastq", "x.fastq.gz", "x.fastq.bgz"))
             host.tofile(plain)
-            step = 32 << 20     # ordinary gzip, written by all cores as 32 MiB members (gzread concatenates them)
+            # ordinary gzip: ONE member (what `gzip` / `pigz` write; no member boundaries to split at), deflated by all
+            # cores the way pigz does it: 32 MiB pieces of raw deflate ending in a sync flush, the last one finished
+            step = 32 << 20
+            starts = list(range(0, nbytes, step))
+
+            def deflate_piece(i):
+                co = zlib.compressobj(6, zlib.DEFLATED, -15)
+                z = co.compress(host[i:i + step].tobytes())
+                return z + co.flush(zlib.Z_FINISH if i == starts[-1] else zlib.Z_SYNC_FLUSH)
             with ThreadPoolExecutor(cores) as ex:
-                parts = list(ex.map(lambda i: gz.compress(host[i:i + step].tobytes(), compresslevel=6), range(0, nbytes, step)))
+                parts = list(ex.map(deflate_piece, starts))
             with open(gzp, "wb") as f:
+                f.write(b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03")
                 for part in parts:
                     f.write(part)
+                f.write(int(zlib.crc32(host) & 0xFFFFFFFF).to_bytes(4, "little") + int(nbytes & 0xFFFFFFFF).to_bytes(4, "little"))
             del parts
             blob = bgzf.compress(host, 6, threads=cores)
             with open(bgz, "wb") as f:
@@ -442,7 +453,14 @@ def main():
             run(g, plain)                     # warm the page cache and the arenas
             run(g, bgz)
             out = {"bgzf_device_inflate": run(g, bgz), "bgzf_host_threads": run(gh, bgz), "plain_file": run(g, plain)}
-            out["gzip_zlib_reader_thread"] = run(g, gzp) if gib <= 1.0 else None     # 0.26 GB/s: only on small inputs
+            # ordinary gzip: decoded speculatively in parallel by every host thread (bsq_pgzip.h), and by one zlib thread
+            out["gzip_parallel_host_threads"] = run(g, gzp)
+            if gib <= 1.0:                                                             # 0.26 GB/s: only on small inputs
+                g1 = B.GpuParser(False, False, schema, 4096, device_id=local, inflate_threads=1)
+                out["gzip_zlib_reader_thread"] = run(g1, gzp)
+                g1.close()
+            else:
+                out["gzip_zlib_reader_thread"] = None
             # CPU arm: zlib over the same BGZF members on every host thread (what the reference's parallel reader does)
             offs, pos = [], 0
             while pos < len(blob):
@@ -670,6 +688,7 @@ def main():
                                                  "bsq_stream_next(batches 4096)", "unit": "GB/s of FASTQ text",
                                      "bgzf_device_inflate": gl["bgzf_device_inflate"]["uncompressed_gb_per_s"],
                                      "bgzf_host_threads": gl["bgzf_host_threads"]["uncompressed_gb_per_s"],
+                                     "gzip_parallel_host_threads": gl["gzip_parallel_host_threads"]["uncompressed_gb_per_s"],
                                      "gzip_zlib_reader_thread": (gl["gzip_zlib_reader_thread"] or {}).get("uncompressed_gb_per_s"),
                                      "plain_file": gl["plain_file"]["uncompressed_gb_per_s"],
                                      "cpu_zlib_all_threads_inflate_only": gl["cpu_zlib_all_threads_inflate_only"]["uncompressed_gb_per_s"],
@@ -718,6 +737,30 @@ def main():
             e2e["host_batch"] = {"value": total_reads / dth, "unit": "reads/s", "ms_per_step": dth * 1e3,
                                  "h2d_bytes_per_step": size, "d2h_bytes_per_step": back + d2h,
                                  "result": "host FastqBatch SoA (five arrays, pinned) via bsq_soa_to_host after the pass"}
+            # ... and the same product with both PCIe directions busy: two parser handles alternate 1 GiB regions, the
+            # SoA of region k travels back while region k+1 travels in (blazeseq_b200/pipeline.py)
+            try:
+                pipe = B.HostBatchPipeline(lambda: B.GpuParser(args.validate, args.validate, schema, 4096, device_id=local),
+                                           region_bytes=1 << 30)
+                got = pipe.run(harr, *outs, stream_offset=lo_off, first_record=rank * M)     # warm-up: arenas, staging
+                assert got[0] == M and pipe.stop.code == capi.EOF, (got, pipe.stop.text)
+                ref_ends = torch.as_tensor(_DevPtr(v.ends, M, "<i8"), device=dev).cpu()
+                assert torch.equal(outs[3], ref_ends), "pipelined ends differ from the one-pass SoA"
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    got = pipe.run(harr, *outs, stream_offset=lo_off, first_record=rank * M)
+                barrier()
+                (dtp,) = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+                assert got == (M, int(v.sequence_bytes), int(v.seq_len), int(v.total_id_bytes)), got
+                e2e["host_batch_pipelined"] = {
+                    "value": total_reads / dtp, "unit": "reads/s", "ms_per_step": dtp * 1e3, "h2d_bytes_per_step": size,
+                    "d2h_bytes_per_step": back, "region_bytes": 1 << 30,
+                    "result": "host FastqBatch SoA (five arrays, pinned); two parser handles alternate 1 GiB regions so that "
+                              "D2H of region k overlaps H2D + passes of region k+1 (HostBatchPipeline)"}
+                pipe.close()
+            except Exception as e:   # the headline does not depend on it
+                e2e["host_batch_pipelined"] = {"skipped": repr(e)[:300]}
             del outs
         del host, harr
 

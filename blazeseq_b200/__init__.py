@@ -11,12 +11,13 @@ from .host import (DEFAULT_BATCH_SIZE, DEFAULT_CAPACITY, EOF, MAX_CAPACITY, Blaz
                      FastqView, FileReader, GpuParser, GZFile, MemoryReader, ParserConfig,
                      QualitySchema, RapidgzipReader, Reader, create_parser, parse_schema, parser, shard_prefix)
 from .fasta import FastaParser, FastaParserConfig, FastaRecord
+from .pipeline import HostBatchPipeline
 
 __all__ = [
     "DEFAULT_BATCH_SIZE", "DEFAULT_CAPACITY", "EOF", "MAX_CAPACITY", "BlazeSeqError",
     "DeviceFastqBatch", "EOFError", "FastqBatch", "FastqGZParser", "FastqParser", "FastqRecord",
     "FastqView", "FileReader", "GpuParser", "GZFile", "MemoryReader", "ParserConfig",
     "QualitySchema", "RapidgzipReader", "Reader", "create_parser", "parse_schema", "parser", "shard_prefix",
-    "FastaParser", "FastaParserConfig", "FastaRecord",
+    "FastaParser", "FastaParserConfig", "FastaRecord", "HostBatchPipeline",
 ]
 __version__ = "0.1.0"

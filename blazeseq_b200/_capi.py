@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("BSQ_LIB") or os.path.join(HERE, "lib", "libblazeseq_g
 OK, ID_NO_AT, SEP_NO_PLUS, SEQ_QUAL_LEN_MISMATCH, ASCII_INVALID, QUALITY_OUT_OF_RANGE = range(6)
 EOF, UNEXPECTED_EOF, BUFFER_EXCEEDED, BUFFER_AT_MAX, OTHER, EMPTY_ERROR = range(6, 12)
 E_CUDA, E_ARG, E_NO_DEVICE, E_NOMEM, E_STATE, E_IO = -1, -2, -3, -4, -5, -6
-WANT_OFFSETS, WANT_BATCHES = 1, 2
+WANT_OFFSETS, WANT_BATCHES, WANT_WHOLE_BATCHES = 1, 2, 4
 
 # every symbol include/blazeseq_gpu.h declares (tests check the library exports exactly these)
 SYMBOLS = [

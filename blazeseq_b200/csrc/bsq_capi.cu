@@ -803,12 +803,24 @@ struct HostFeed : InputFeed {
 
 }  // namespace
 
+static bsq_status trim_to_whole_batches(bsq_parser* p, uint32_t want, bool is_last, uint32_t m, bsq_pass_result* out);
+
+// BSQ_WANT_WHOLE_BATCHES: a region that does not end the stream keeps its trailing partial batch unconsumed (the cut
+// between two records needs the offsets table, so such a pass also fills it)
+static inline uint32_t pass_want(uint32_t want, int32_t is_last) {
+    uint32_t w = want & (BSQ_WANT_OFFSETS | BSQ_WANT_BATCHES);
+    if ((want & BSQ_WANT_WHOLE_BATCHES) && (want & BSQ_WANT_BATCHES) && !is_last) w |= BSQ_WANT_OFFSETS;
+    return w;
+}
+
 extern "C" bsq_status bsq_parse_device(bsq_parser* p, const uint8_t* dev_bytes, uint64_t n, int64_t stream_offset,
                                        int64_t first_record, int32_t is_last, uint32_t want, bsq_pass_result* out) {
     if (!p || (!dev_bytes && n)) return BSQ_E_ARG;
     CK(cudaSetDevice(p->cfg.device_id));
     InputFeed none;
-    return run_pass(p, dev_bytes, n, stream_offset, first_record, is_last, want, kWindowMax, none, out);
+    bsq_status st = run_pass(p, dev_bytes, n, stream_offset, first_record, is_last, pass_want(want, is_last), kWindowMax, none, out);
+    if (st == BSQ_OK && (want & BSQ_WANT_WHOLE_BATCHES)) st = trim_to_whole_batches(p, want, is_last != 0, (uint32_t)p->cfg.batch_size, out);
+    return st;
 }
 
 extern "C" bsq_status bsq_parse_host(bsq_parser* p, const uint8_t* host_bytes, uint64_t n, int64_t stream_offset,
@@ -831,13 +843,22 @@ extern "C" bsq_status bsq_parse_host(bsq_parser* p, const uint8_t* host_bytes, u
     }
     const uint64_t window = std::min<uint64_t>(kWindowMax, std::max<uint64_t>(kHostWindow, (uint64_t)p->cfg.h2d_chunk_bytes));
     feed.ahead = window;
-    bsq_status st = run_pass(p, feed.d, n, stream_offset, first_record, is_last, want, window, feed, out);
+    bsq_status st = run_pass(p, feed.d, n, stream_offset, first_record, is_last, pass_want(want, is_last), window, feed, out);
+    if (st == BSQ_OK && (want & BSQ_WANT_WHOLE_BATCHES)) st = trim_to_whole_batches(p, want, is_last != 0, (uint32_t)p->cfg.batch_size, out);
     return st;
 }
 
 // ------------------------------------------------------------------------------------------------
 // streaming from a file: reader thread -> pinned regions -> passes
 // ------------------------------------------------------------------------------------------------
+
+// the inflate kernel of the build: every lane decodes (one warp per member), or the leader-lane form for the tuning
+// builds with several members per warp (BSQ_INF_LANES < 32)
+#if BSQ_INF_UNIFORM && BSQ_INF_LANES == 32
+static constexpr auto kInflateKernel = k_inflate_members_uniform;
+#else
+static constexpr auto kInflateKernel = k_inflate_members;
+#endif
 
 struct bsq_stream {
     bsq_parser* p = nullptr;
@@ -901,8 +922,9 @@ struct bsq_stream {
         DevBuf zdev, mdev, sdev;
         uint32_t* status = nullptr;      // pinned: the D2H copy must not hold the host up
         size_t status_cap = 0;
-        cudaEvent_t e_start = nullptr, e_h2d = nullptr, e_done = nullptr;
+        cudaEvent_t e_start = nullptr, e_h2d = nullptr, e_k0 = nullptr, e_done = nullptr;
     };
+    cudaStream_t h2d_stream = nullptr;   // compressed bytes of region k+1 travel while region k is still inflating
     InfJob job[2];
     int jcur = 0;
     cudaEvent_t e_carry = nullptr;
@@ -1206,13 +1228,15 @@ extern "C" bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t s
         s->n_slots = bsq_stream::kMaxSlots;
         for (auto& j : s->job)
             if (cudaEventCreate(&j.e_start) != cudaSuccess || cudaEventCreate(&j.e_h2d) != cudaSuccess ||
+                cudaEventCreate(&j.e_k0) != cudaSuccess ||
                 cudaEventCreate(&j.e_done) != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, cudaGetLastError(), "cudaEventCreate"); }
+        if (cudaStreamCreateWithFlags(&s->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, cudaGetLastError(), "cudaStreamCreate"); }
         if (cudaEventCreateWithFlags(&s->e_carry, cudaEventDisableTiming) != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, cudaGetLastError(), "cudaEventCreate"); }
         for (auto& z : s->zb) {
             cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&z.mem), s->zcap + 64, cudaHostAllocDefault);
             if (e != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, e, "cudaHostAlloc(compressed region)"); }
         }
-        cudaError_t e = opt_in_smem(k_inflate_members, sizeof(InflateTables) * kInfPerCta);
+        cudaError_t e = opt_in_smem(kInflateKernel, sizeof(InflateTables) * kInfPerCta);
         if (e != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, e, "k_inflate_members shared memory"); }
     } else
     for (auto& b : s->buf) {
@@ -1239,6 +1263,7 @@ extern "C" void bsq_stream_close(bsq_stream* s) {
     for (auto& z : s->zb) if (z.mem) cudaFreeHost(z.mem);
     if (s->p) {
         cudaSetDevice(s->p->cfg.device_id);
+        if (s->h2d_stream) cudaStreamSynchronize(s->h2d_stream);
         if (s->p->copy_stream) cudaStreamSynchronize(s->p->copy_stream);   // a prefetched region may still be inflating
         if (s->p->stream) cudaStreamSynchronize(s->p->stream);
     }
@@ -1247,9 +1272,11 @@ extern "C" void bsq_stream_close(bsq_stream* s) {
         if (j.status) cudaFreeHost(j.status);
         if (j.e_start) cudaEventDestroy(j.e_start);
         if (j.e_h2d) cudaEventDestroy(j.e_h2d);
+        if (j.e_k0) cudaEventDestroy(j.e_k0);
         if (j.e_done) cudaEventDestroy(j.e_done);
     }
     if (s->e_carry) cudaEventDestroy(s->e_carry);
+    if (s->h2d_stream) cudaStreamDestroy(s->h2d_stream);
     s->rdev[0].release(); s->rdev[1].release();
     delete s;
 }
@@ -1286,18 +1313,22 @@ static bsq_status launch_inflate(bsq_stream* s, bsq_stream::InfJob& J, int slot,
     J.room = std::max<uint64_t>(32ull << 20, 2 * s->dev_carry_len + (1ull << 20));
     J.room = (J.room + 255) & ~255ull;
     CK(s->rdev[rbuf].ensure(J.room + J.out_bytes + 256, 1 << 20));
-    CK(cudaEventRecord(J.e_start, p->copy_stream));
+    // the compressed bytes travel on their own stream (the job's buffers were last read by the inflate two regions ago, whose
+    // end the caller has waited for), so the copy runs while the previous region is still inflating on the copy stream
+    CK(cudaEventRecord(J.e_start, s->h2d_stream));
     if (J.nm) {
         CK(J.zdev.ensure(z.n + 64, 1 << 20));
         CK(J.mdev.ensure(sizeof(InflateMember) * J.nm, 1 << 16));
         CK(J.sdev.ensure(4ull * J.nm, 1 << 12));
-        CK(cudaMemcpyAsync(J.zdev.p, z.mem, z.n, cudaMemcpyHostToDevice, p->copy_stream));
-        CK(cudaMemcpyAsync(J.mdev.p, z.members.data(), sizeof(InflateMember) * J.nm, cudaMemcpyHostToDevice, p->copy_stream));
+        CK(cudaMemcpyAsync(J.zdev.p, z.mem, z.n, cudaMemcpyHostToDevice, s->h2d_stream));
+        CK(cudaMemcpyAsync(J.mdev.p, z.members.data(), sizeof(InflateMember) * J.nm, cudaMemcpyHostToDevice, s->h2d_stream));
     }
-    CK(cudaEventRecord(J.e_h2d, p->copy_stream));
+    CK(cudaEventRecord(J.e_h2d, s->h2d_stream));
+    CK(cudaStreamWaitEvent(p->copy_stream, J.e_h2d, 0));
+    CK(cudaEventRecord(J.e_k0, p->copy_stream));
     if (J.nm) {
         uint8_t* dst = s->rdev[rbuf].as<uint8_t>() + J.room;
-        k_inflate_members<<<(J.nm + kInfPerCta - 1) / kInfPerCta, kInfWarps * 32, sizeof(InflateTables) * kInfPerCta, p->copy_stream>>>(
+        kInflateKernel<<<(J.nm + kInfPerCta - 1) / kInfPerCta, kInfWarps * 32, sizeof(InflateTables) * kInfPerCta, p->copy_stream>>>(
             J.zdev.as<uint8_t>(), dst, J.mdev.as<InflateMember>(), J.nm, J.sdev.as<uint32_t>());
         k_crc32_members<<<(J.nm + kCrcWarps - 1) / kCrcWarps, kCrcWarps * 32, 0, p->copy_stream>>>(
             dst, J.mdev.as<InflateMember>(), J.nm, J.sdev.as<uint32_t>());
@@ -1376,7 +1407,7 @@ static bsq_status stream_next_device_inflate(bsq_stream* s, uint32_t want, bsq_p
     CK(cudaEventSynchronize(J.e_done));
     float ms_copy = 0.f, ms_inf = 0.f;
     cudaEventElapsedTime(&ms_copy, J.e_start, J.e_h2d);
-    cudaEventElapsedTime(&ms_inf, J.e_h2d, J.e_done);
+    cudaEventElapsedTime(&ms_inf, J.e_k0, J.e_done);
     s->st.h2d_s += ms_copy * 1e-3; s->st.inflate_s += ms_inf * 1e-3; s->st.compressed_bytes += J.z_bytes;
     for (uint32_t i = 0; i < J.nm; ++i)
         if (J.status[i] != 0u) {

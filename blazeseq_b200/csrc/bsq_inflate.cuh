@@ -373,6 +373,197 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members(const uint8_
     }
 }
 
+#ifndef BSQ_INF_UNIFORM
+#define BSQ_INF_UNIFORM 1
+#endif
+// The shipped form (one warp per member, kInfLanes == 32): EVERY lane runs the decode loop on identical state -- the
+// same input words (one broadcast load), the same table lookups (one shared-memory broadcast) -- so the warp never
+// leaves the loop: no leader hand-off, no shuffles, no votes.  A redundant lane costs nothing on a SIMT machine (the
+// warp instruction issues once either way), and every lane already knows (position, length, distance) when a match
+// comes up: lane i copies byte i.  Literals are stored by lane 0.  Only the block headers (a few per member) are
+// parsed by lane 0 alone and the reader state is broadcast afterwards.  As before, a match's bytes are loaded when it is
+// decoded and stored at the next match (the decoder never waits for them).
+__global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members_uniform(const uint8_t* __restrict__ zbuf, uint8_t* __restrict__ out,
+                                                                          const InflateMember* __restrict__ members, uint32_t n_members,
+                                                                          uint32_t* __restrict__ status) {
+    extern __shared__ __align__(16) uint8_t inf_smem[];
+    constexpr uint32_t kFull = 0xFFFFFFFFu, kNone = 0xFFFFFFFFu;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t m = blockIdx.x * kInfWarps + warp;
+    if (m >= n_members) return;                       // (whole warp)
+    InflateTables& T = reinterpret_cast<InflateTables*>(inf_smem)[warp];
+    const InflateMember M = members[m];
+    uint8_t* const dst = out + M.dst;
+    const uint8_t* const src0 = zbuf + M.src;
+    const uint32_t cap = M.isize;
+    BitReader br{};
+    br_init(br, src0, M.src_len, 0u);
+    uint32_t pos = 0, err = 0;
+    bool last = false, finished = false;
+    int tables = 0;                                   // 0 none, 1 fixed, 2 dynamic (lane 0 keeps the tables)
+    uint32_t pend_pos = kNone;                        // a match byte loaded but not yet stored (per lane)
+    uint8_t pend_val = 0;
+
+    while (!finished && err == 0u) {
+        // ---- block header: every lane reads the three header bits; lane 0 alone sets the tables up ----
+        br_fill(br);
+        last = br_take(br, 1) != 0u;
+        const uint32_t btype = br_take(br, 2);
+        if (btype == 0u) {
+            br_skip(br, br.cnt & 7u);                                     // to the byte boundary
+            br_fill(br);
+            const uint32_t len = br_take(br, 16);
+            br_fill(br);
+            const uint32_t nlen = br_take(br, 16);
+            const uint32_t st_src = (uint32_t)(br_consumed(br) >> 3);     // payload offset of the raw bytes
+            if ((len ^ nlen) != 0xFFFFu) { err = 1u; break; }
+            if (pos + len > cap) { err = 2u; break; }
+            if (st_src + len > M.src_len) { err = 3u; break; }
+            if (pend_pos != kNone) { dst[pend_pos] = pend_val; pend_pos = kNone; }
+            for (uint32_t i = lane; i < len; i += 32u) dst[pos + i] = src0[st_src + i];
+            pos += len;
+            br_init(br, src0 + st_src + len, M.src_len - st_src - len, st_src + len);
+            if (last) finished = true;
+            continue;
+        }
+        if (btype == 3u) { err = 1u; break; }
+        {
+            // lane 0 parses the rest of the header and builds the tables; its reader state and verdict are broadcast
+            uint32_t herr = 0;
+            if (lane == 0u) {
+                if (btype == 1u) {
+                    if (tables != 1) {
+                        for (int s = 0; s < 144; ++s) T.lens[s] = 8;
+                        for (int s = 144; s < 256; ++s) T.lens[s] = 9;
+                        for (int s = 256; s < 280; ++s) T.lens[s] = 7;
+                        for (int s = 280; s < 288; ++s) T.lens[s] = 8;
+                        inf_build(T.lens, 288, T.lit, kLitBits, T.lit_sym, T.lit_count, false);
+                        for (int s = 0; s < 30; ++s) T.lens[s] = 5;
+                        inf_build(T.lens, 30, T.dist, kDistBits, T.dist_sym, T.dist_count, true);
+                    }
+                } else {
+                    const uint32_t hlit = br_take(br, 5) + 257u, hdist = br_take(br, 5) + 1u, hclen = br_take(br, 4) + 4u;
+                    if (hlit > 286u || hdist > 30u) herr = 1u;
+                    uint8_t* cl = T.lens + 300;                             // 19 code-length code lengths
+                    for (int i = 0; i < 19; ++i) cl[i] = 0;
+                    for (uint32_t i = 0; i < hclen && herr == 0u; ++i) { br_fill(br); cl[kInfClOrder[i]] = (uint8_t)br_take(br, 3); }
+                    // the code-length code borrows the distance table's storage (7-bit lookup)
+                    if (herr == 0u && !inf_build(cl, 19, T.dist, 7, T.dist_sym, T.dist_count, false)) herr = 1u;
+                    uint32_t i = 0;
+                    while (i < hlit + hdist && herr == 0u) {
+                        br_fill(br);
+                        const uint32_t e = T.dist[br_peek(br, 7)];
+                        if ((e & 0xF0u) != 0u) { herr = 1u; break; }        // not a (valid) symbol of the code-length code
+                        br_skip(br, e & 15u);
+                        const uint32_t s = e >> 16;
+                        if (s < 16u) { T.lens[i++] = (uint8_t)s; continue; }
+                        uint32_t rep, val = 0;
+                        if (s == 16u) { if (i == 0u) { herr = 1u; break; } val = T.lens[i - 1]; rep = 3u + br_take(br, 2); }
+                        else if (s == 17u) rep = 3u + br_take(br, 3);
+                        else rep = 11u + br_take(br, 7);
+                        if (i + rep > hlit + hdist) { herr = 1u; break; }
+                        while (rep--) T.lens[i++] = (uint8_t)val;
+                    }
+                    if (herr == 0u && T.lens[256] == 0) herr = 1u;            // no end-of-block code
+                    if (herr == 0u) {
+                        for (uint32_t k = 0; k < 32u; ++k) T.dl[k] = k < hdist ? T.lens[hlit + k] : 0;
+                        if (!inf_build(T.lens, hlit, T.lit, kLitBits, T.lit_sym, T.lit_count, false)) herr = 1u;
+                        if (herr == 0u && !inf_build(T.dl, hdist, T.dist, kDistBits, T.dist_sym, T.dist_count, true)) herr = 1u;
+                    }
+                }
+            }
+            tables = (int)btype;
+            __syncwarp();                                                 // the tables are in shared memory for every lane
+            herr = __shfl_sync(kFull, herr, 0);
+            if (btype == 2u) {
+                // the reader moved in lane 0 only
+                const uint32_t adv = __shfl_sync(kFull, (uint32_t)(br.wp - br.w0), 0);
+                br.wp = br.w0 + adv;
+                br.buf = ((uint64_t)__shfl_sync(kFull, (uint32_t)(br.buf >> 32), 0) << 32) | __shfl_sync(kFull, (uint32_t)br.buf, 0);
+                br.cnt = __shfl_sync(kFull, br.cnt, 0);
+                br.nextw = __shfl_sync(kFull, br.nextw, 0);
+                br.overrun = __shfl_sync(kFull, br.overrun, 0);
+            }
+            if (herr != 0u) { err = herr; break; }
+        }
+        // ---- the block's symbols: every lane decodes, lane 0 stores literals, lane i copies byte i of a match ----
+        while (true) {
+            br_fill(br);
+            uint32_t e = T.lit[br_peek(br, kLitBits)];
+            if ((e & 0xF0u) == 0u) {                                  // a literal (the common case)
+                br_skip(br, e & 15u);
+                if (pos >= cap) { err = 2u; break; }
+                if (lane == 0u) dst[pos] = (uint8_t)(e >> 16);
+                ++pos;
+                continue;
+            }
+            uint32_t kind = (e >> 4) & 15u;
+            uint32_t base, extra;
+            if (kind == kKindLen) {
+                br_skip(br, e & 15u);
+                base = e >> 16; extra = (e >> 8) & 255u;
+            } else if (kind == kKindEob) {
+                br_skip(br, e & 15u);
+                if (last) finished = true;
+                break;
+            } else if (kind == kKindSlow) {                           // a code longer than the table width
+                const int32_t s = inf_slow(br, T.lit_sym, T.lit_count);
+                if (s < 0 || s >= 286) { err = 1u; break; }
+                if (s < 256) {
+                    if (pos >= cap) { err = 2u; break; }
+                    if (lane == 0u) dst[pos] = (uint8_t)s;
+                    ++pos;
+                    continue;
+                }
+                if (s == 256) { if (last) finished = true; break; }
+                base = kInfLenBase[s - 257]; extra = kInfLenExtra[s - 257];
+            } else { err = 1u; break; }
+            const uint32_t mlen = base + br_take(br, extra);
+            br_fill(br);
+            e = T.dist[br_peek(br, kDistBits)];
+            kind = (e >> 4) & 15u;
+            if (kind == kKindLen) {
+                br_skip(br, e & 15u);
+                base = e >> 16; extra = (e >> 8) & 255u;
+            } else if (kind == kKindSlow) {
+                const int32_t d = inf_slow(br, T.dist_sym, T.dist_count);
+                if (d < 0 || d >= 30) { err = 1u; break; }
+                base = kInfDistBase[d]; extra = kInfDistExtra[d];
+            } else { err = 1u; break; }
+            br_fill(br);
+            const uint32_t mdist = base + br_take(br, extra);
+            if (mdist > pos || pos + mlen > cap || mdist > 32768u) { err = 2u; break; }
+            // the previous match's bytes were only LOADED when it was decoded: they are stored now, when the loads have long
+            // returned; then lane 0's literal stores and these become visible to the warp
+            if (pend_pos != kNone) { dst[pend_pos] = pend_val; pend_pos = kNone; }
+            __syncwarp();
+            const uint8_t* s = dst + pos - mdist;
+            if (mlen <= 32u) {                                         // one byte per lane: load now, store at the next match
+                if (lane < mlen) {
+                    uint32_t i = lane;
+                    if (mdist < mlen) i = lane % mdist;               // the pattern repeats
+                    pend_val = s[i];
+                    pend_pos = pos + lane;
+                }
+            } else if (mdist >= mlen) {
+                for (uint32_t i = lane; i < mlen; i += 32u) dst[pos + i] = s[i];
+            } else {
+                for (uint32_t i = lane; i < mlen; i += 32u) dst[pos + i] = s[i % mdist];
+            }
+            pos += mlen;
+        }
+        if (br.overrun) err = 3u;
+    }
+    if (pend_pos != kNone) dst[pend_pos] = pend_val;
+    if (lane == 0u) {
+        uint32_t st = err;
+        if (st == 0u && br.overrun) st = 3u;
+        if (st == 0u && br_consumed(br) > (uint64_t)M.src_len * 8u) st = 3u;
+        if (st == 0u && pos != cap) st = 4u;
+        status[m] = st;
+    }
+}
+
 // CRC-32 (gzip, reflected 0xEDB88320) of every member's inflated bytes: one warp per member, each lane a
 // contiguous slice, the slices' CRCs combined with x^(8 n) mod P multiplications.
 __device__ __forceinline__ uint32_t crc_mul(uint32_t a, uint32_t b) {      // a * b mod P, bit-reflected operands

@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
@@ -278,9 +279,11 @@ inline bool read_dynamic_header(BitReader& br, Tables& T) {
 
 // ---- block finder -----------------------------------------------------------------------------------------------
 // First bit offset in [from, to) at which a non-final dynamic block header parses; UINT64_MAX when none.
-inline uint64_t find_block(const uint8_t* z, size_t n, uint64_t from, uint64_t to, Tables& scratch) {
+inline uint64_t find_block(const uint8_t* z, size_t n, uint64_t from, uint64_t to, Tables& scratch,
+                           const std::atomic<bool>* cancel = nullptr) {
     const uint64_t last = (uint64_t)n * 8;
     for (uint64_t o = from; o < to; ++o) {
+        if (cancel && (o & 0xFFFFu) == 0 && cancel->load(std::memory_order_relaxed)) return UINT64_MAX;
         if (o + 64 > last) {
             // near the end of the input: go through the bit reader for every offset
             BitReader br;
@@ -344,48 +347,85 @@ inline int read_gzip_header(BitReader& br) {
 enum BlockResult { BR_EOB = 0, BR_ERR = 1 };
 
 // One compressed block's symbols into out[pos...]; T = uint16_t (marker mode) or uint8_t.  `grow` makes room.
+// The reader's state and the output cursor live in locals for the duration of the block (byte stores may alias anything).
 template <class T, class Grow>
 inline BlockResult inflate_codes(BitReader& br, const Tables& tb, T*& out, size_t& pos, size_t& cap, Grow grow) {
-    const Entry* lit = tb.lit;
-    const Entry* dist = tb.dist;
+    const Entry* const lit = tb.lit;
+    const Entry* const dist = tb.dist;
+    const bool have_dist = tb.have_dist;
+    constexpr uint64_t LM = (1u << kLitBits) - 1, DM = (1u << kDistBits) - 1;
+    constexpr uint32_t W = 16 / sizeof(T);   // elements per 16-byte move (the buffer keeps 320 slack elements)
+    uint64_t buf = br.buf;
+    uint32_t cnt = br.cnt, over = br.over;
+    const uint8_t* ip = br.ip;
+    const uint8_t* const end = br.end;
+    T* obase = out;
+    T* o = out + pos;
+    T* olimit = out + cap - 320;
+    BlockResult res = BR_ERR;
     for (;;) {
-        if (pos + 320 > cap) grow();
-        br.refill();
-        Entry e = lit[br.buf & ((1u << kLitBits) - 1)];
-        if (e.kx == K_SUB) e = lit[e.val + ((br.buf >> kLitBits) & ((1u << e.len) - 1))];
+        if (o > olimit) {
+            pos = (size_t)(o - obase);
+            grow();
+            obase = out; o = out + pos; olimit = out + cap - 320;
+        }
+        if (ip + 8 <= end) {
+            uint64_t w;
+            memcpy(&w, ip, 8);
+            buf |= w << cnt;
+            ip += (63 - cnt) >> 3;
+            cnt |= 56;
+        } else {
+            while (cnt <= 56) {
+                if (ip < end) buf |= (uint64_t)*ip++ << cnt; else over += 8;
+                cnt += 8;
+            }
+        }
+        Entry e = lit[buf & LM];
         if (e.kx == K_LIT) {
-            br.drop(e.len);
-            out[pos++] = (T)e.val;
-            // a second and third literal on the bits already loaded (<= 33 more bits)
-            e = lit[br.buf & ((1u << kLitBits) - 1)];
+            // up to three literals on the bits already loaded (<= 45 of >= 56)
+            buf >>= e.len; cnt -= e.len;
+            *o++ = (T)e.val;
+            e = lit[buf & LM];
             if (e.kx == K_LIT) {
-                br.drop(e.len);
-                out[pos++] = (T)e.val;
-                e = lit[br.buf & ((1u << kLitBits) - 1)];
+                buf >>= e.len; cnt -= e.len;
+                *o++ = (T)e.val;
+                e = lit[buf & LM];
                 if (e.kx == K_LIT) {
-                    br.drop(e.len);
-                    out[pos++] = (T)e.val;
+                    buf >>= e.len; cnt -= e.len;
+                    *o++ = (T)e.val;
                 }
             }
             continue;
         }
+        if (e.kx == K_SUB) {
+            e = lit[e.val + ((buf >> kLitBits) & ((1u << e.len) - 1))];
+            if (e.kx == K_LIT) { buf >>= e.len; cnt -= e.len; *o++ = (T)e.val; continue; }
+        }
         if ((e.kx & 15) == K_LEN) {
-            br.drop(e.len);
-            uint32_t len = e.val + br.take(e.kx >> 4);
-            if (!tb.have_dist) return BR_ERR;
-            Entry d = dist[br.buf & ((1u << kDistBits) - 1)];
-            if (d.kx == K_SUB) d = dist[d.val + ((br.buf >> kDistBits) & ((1u << d.len) - 1))];
-            if ((d.kx & 15) != K_LEN) return BR_ERR;
-            br.drop(d.len);
-            const uint32_t dd = d.val + br.take(d.kx >> 4);
-            if (br.overrun()) return BR_ERR;
-            if (dd > kWin || dd > pos) return BR_ERR;
-            T* dst = out + pos;
-            const T* src = dst - dd;
-            pos += len;
-            constexpr uint32_t W = 16 / sizeof(T);   // elements per 16-byte move (the buffer has 320 slack elements)
+            buf >>= e.len; cnt -= e.len;
+            const uint32_t xl = e.kx >> 4;
+            const uint32_t len = e.val + (uint32_t)(buf & ((1u << xl) - 1));
+            buf >>= xl; cnt -= xl;
+            if (!have_dist) break;
+            Entry d = dist[buf & DM];
+            if (d.kx == K_SUB) d = dist[d.val + ((buf >> kDistBits) & ((1u << d.len) - 1))];
+            if ((d.kx & 15) != K_LEN) break;
+            buf >>= d.len; cnt -= d.len;
+            const uint32_t xd = d.kx >> 4;
+            const uint32_t dd = d.val + (uint32_t)(buf & ((1u << xd) - 1));
+            buf >>= xd; cnt -= xd;
+            if (over > cnt) break;
+            if (dd > kWin || dd > (size_t)(o - obase)) break;
+            const T* src = o - dd;
+            T* dst = o;
+            o += len;
             if (dd >= W) {
-                for (uint32_t k = 0; k < len; k += W) memcpy(dst + k, src + k, 16);
+                memcpy(dst, src, 16);
+                if (len > W) {
+                    memcpy(dst + W, src + W, 16);
+                    for (uint32_t k = 2 * W; k < len; k += W) memcpy(dst + k, src + k, 16);
+                }
             } else if (dd == 1) {
                 const T v = *src;
                 for (uint32_t k = 0; k < len; ++k) dst[k] = v;
@@ -394,9 +434,12 @@ inline BlockResult inflate_codes(BitReader& br, const Tables& tb, T*& out, size_
             }
             continue;
         }
-        if (e.kx == K_EOB) { br.drop(e.len); return br.overrun() ? BR_ERR : BR_EOB; }
-        return BR_ERR;
+        if (e.kx == K_EOB) { buf >>= e.len; cnt -= e.len; res = over > cnt ? BR_ERR : BR_EOB; }
+        break;
     }
+    br.buf = buf; br.cnt = cnt; br.ip = ip; br.over = over;
+    pos = (size_t)(o - obase);
+    return res;
 }
 
 // Decodes blocks from the reader's position until (a) a block boundary at or after `stop_bit` where a non-final
@@ -576,6 +619,9 @@ class Reader {
         int state = 0;       // 0 queued, 1 stage 1 running, 2 stage 1 done, 3 accepted (stage 2 queued/running), 4 ready
         uint8_t window[kWin];
         bool have_window = false, skipped = false;
+        bool found = false;                 // stage 1 has a block start and is inflating from it
+        std::atomic<bool> abandon{false};   // the sequencer got here first and decodes the chunk itself
+        bool taken = false;
         std::vector<uint8_t> head;          // resolved m16
         std::vector<uint32_t> seg_crc;      // crc of [segment start, member end) pieces, then the open tail
         std::vector<uint64_t> seg_len;
@@ -624,7 +670,8 @@ class Reader {
             if (what == 1) stage1(*c, *tb); else stage2(*c);
             {
                 std::lock_guard<std::mutex> lk(mu_);
-                c->state = what == 1 ? 2 : 4;
+                if (what == 2) c->state = 4;
+                else if (!c->taken) c->state = 2;
             }
             cv_done_.notify_all();
         }
@@ -636,12 +683,22 @@ class Reader {
         if (c.idx == 0) { inflate_chunk(z_, n_, 0, stop, nullptr, true, c.out, tb); return; }
         uint64_t from = c.nominal_begin;
         for (int tries = 0; tries < 64; ++tries) {
-            const uint64_t o = find_block(z_, n_, from, c.nominal_end, tb);
+            const uint64_t o = find_block(z_, n_, from, c.nominal_end, tb, &c.abandon);
             if (o == UINT64_MAX) break;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (c.abandon.load()) return;        // (the sequencer owns c.out from here on)
+                c.found = true;
+            }
             inflate_chunk(z_, n_, o, stop, nullptr, false, c.out, tb);
             if (c.out.ok) return;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                c.found = false;
+            }
             from = o + 1;      // a false positive of the finder: the data after it does not decode
         }
+        if (c.abandon.load()) return;
         c.out.ok = false;
         c.out.start_bit = UINT64_MAX;
     }
@@ -700,17 +757,30 @@ class Reader {
             bool progressed = false;
             while (!finished_ && next_seq_ < chunks_base_ + chunks_.size()) {
                 std::shared_ptr<Chunk> c = chunks_[next_seq_ - chunks_base_];
-                if (c->state < 2) break;
                 if (c->state >= 3) { ++next_seq_; continue; }
-                progressed = true;
                 if (c->nominal_end <= expect_bit_) {
-                    // the predecessor ran through this whole chunk: nothing of it is needed
-                    c->out = ChunkOut(); c->out.ok = true; c->head.clear(); c->seg_crc.clear(); c->seg_len.clear();
+                    // the predecessor ran through this whole chunk: nothing of it is needed (a worker still busy with it
+                    // keeps its own reference and finds `taken`)
+                    progressed = true;
+                    c->abandon.store(true);
+                    c->taken = true;
+                    c->head.clear(); c->seg_crc.clear(); c->seg_len.clear();
                     c->state = 4; c->skipped = true;
                     if (c->idx + 1 == n_chunks_) { finished_ = true; final_idx_ = c->idx; }
                     ++next_seq_;
                     continue;
                 }
+                if (c->state < 2) {
+                    // still searching for a block start (a stream of stored / fixed blocks has none): rather than wait for
+                    // the search to run through the whole chunk, take the chunk over -- the start is known here
+                    if (c->state == 1 && !c->found && c->idx != 0 && c->nominal_end > expect_bit_ && waited_) {
+                        c->abandon.store(true);
+                        c->taken = true;
+                        c->out = ChunkOut();
+                        c->state = 2;
+                    } else break;
+                }
+                progressed = true;
                 if (!c->out.ok || c->out.start_bit != expect_bit_) {
                     // not where the predecessor stopped (or nothing found): decode it here, window known
                     lk.unlock();
@@ -752,9 +822,10 @@ class Reader {
                     return c;
                 }
             }
-            if (progressed) continue;
+            if (progressed) { waited_ = false; continue; }
             cv_work_.notify_all();
-            cv_done_.wait(lk);
+            // (a short timed wait first: a worker that is merely finishing its chunk gets the chance to)
+            waited_ = cv_done_.wait_for(lk, std::chrono::milliseconds(waited_ ? 50 : 3)) == std::cv_status::timeout;
         }
     }
 
@@ -796,6 +867,7 @@ class Reader {
     uLong crc_ = 0;
     uint64_t member_len_ = 0;
     size_t final_idx_ = 0;
+    bool waited_ = false;                  // the sequencer's last wait timed out with nothing done
     std::shared_ptr<Chunk> cur_;
     size_t cur_off_ = 0;
     std::string err_;

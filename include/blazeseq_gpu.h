@@ -56,6 +56,9 @@ enum {
 /* what a pass materialises */
 #define BSQ_WANT_OFFSETS 1u    /* views(): line-end table + stripped id spans */
 #define BSQ_WANT_BATCHES 2u    /* batches(): FastqBatch SoA */
+#define BSQ_WANT_WHOLE_BATCHES 4u /* with BSQ_WANT_BATCHES on a region that does not end the stream (is_last = 0): the
+                                  records of a trailing partial batch stay unconsumed (bytes_consumed ends at the last whole
+                                  batch), so that batches(m) cut region by region are the batches of the whole stream */
 
 /* ParserConfig (parser.mojo:33-74) + the resolved QualitySchema (quality_schema.mojo:9-31).
  * check_ascii / check_quality select the kernel instantiation (the reference's comptime

@@ -556,6 +556,60 @@ def test_scale_two_windows(B, oracle):
     gpu.close()
 
 
+def test_whole_batches_regions_and_the_host_batch_pipeline(B, oracle):
+    """BSQ_WANT_WHOLE_BATCHES: a region that does not end the stream leaves its trailing partial batch unconsumed, so
+    batches cut region by region are the batches of the whole stream; HostBatchPipeline (two parser handles alternating
+    regions, D2H of one overlapping H2D + passes of the other) fills the same five arrays as one pass over everything."""
+    from blazeseq_b200 import _capi as capi
+    data = oracle.synth(30000, 60, 260, 2, 40, "sanger")
+    views, bases, err = oracle.parse_all(data)
+    m = 700
+    exp = [oracle.build_batch(data, views[a:a + m]) for a in range(0, len(views), m)]   # (id, seq, qual, id_ends, ends)
+    gpu = B.GpuParser(True, True, B.parse_schema("sanger"), m)
+    pos = rec = 0
+    region = 900_000
+    while True:
+        end = min(data.size, pos + region)
+        last = end == data.size
+        r = gpu.parse_host(data[pos:end], pos, rec, last, capi.WANT_BATCHES | capi.WANT_WHOLE_BATCHES)
+        n = int(r.n_records)
+        assert last or (n % m == 0 and n > 0 and r.stop.code == capi.OK)
+        assert pos + int(r.bytes_consumed) == (int(views[rec + n]["header_start"]) if rec + n < len(views) else data.size)
+        for b in range(int(r.n_batches)):
+            got = gpu.batch_to_host(b)
+            e = exp[rec // m + b]
+            for g, x in zip(got, (e[1], e[2], e[0], e[4], e[3])):
+                assert np.array_equal(g, x)
+        pos += int(r.bytes_consumed)
+        rec += n
+        if last:
+            assert r.stop.code == capi.EOF
+            break
+    assert rec == len(views)
+    gpu.close()
+
+    total = {k: sum(e[i].size for e in exp) for k, i in (("id", 0), ("seq", 1), ("qual", 2))}
+    for region in (700_000, 2_000_000, 1 << 30):
+        pipe = B.HostBatchPipeline(lambda: B.GpuParser(True, True, B.parse_schema("sanger"), m), region_bytes=region)
+        seq = np.zeros(total["seq"], np.uint8); qual = np.zeros(total["qual"], np.uint8); idb = np.zeros(total["id"], np.uint8)
+        ends = np.zeros(len(views), np.int64); id_ends = np.zeros(len(views), np.int64)
+        for _ in range(2):     # the handles are reusable
+            got = pipe.run(data, seq, qual, idb, ends, id_ends)
+            assert got == (len(views), total["seq"], total["qual"], total["id"]) and pipe.stop.code == capi.EOF
+            assert np.array_equal(seq, np.concatenate([e[1] for e in exp])) and np.array_equal(qual, np.concatenate([e[2] for e in exp]))
+            assert np.array_equal(idb, np.concatenate([e[0] for e in exp]))
+            assert np.array_equal(ends, np.concatenate([e[4] for e in exp])) and np.array_equal(id_ends, np.concatenate([e[3] for e in exp]))
+        pipe.close()
+    # an error stops the pipeline with the reference's context
+    bad = data.copy()
+    bad[int(views[20000]["seq_start"]) + 5] = 0x80
+    pipe = B.HostBatchPipeline(lambda: B.GpuParser(True, True, B.parse_schema("sanger"), m), region_bytes=700_000)
+    got = pipe.run(bad, None, None, None, None, None)
+    _, _, oerr = oracle.parse_all(bad, oracle.config(True, True, "sanger"))
+    assert got[0] == 20000 and pipe.stop.code == 4 and pipe.stop.message == oerr.message
+    pipe.close()
+
+
 def test_shard_summaries_locate_record_starts(B, oracle):
     """Multi-GPU stitching: summaries of arbitrary byte shards (device) -> where each shard's first
     own record starts (host arithmetic) must match the oracle's record table."""
@@ -830,6 +884,50 @@ def test_bgzf_parallel_inflate(B, oracle, tmp_path, golden_dir):
                     break
         gpu.stream_close(st)
         gpu.close()
+
+
+def test_plain_gzip_parallel_decode_feeds_the_passes(B, oracle, tmp_path):
+    """An ordinary (non-BGZF) .gz through the stream pipeline: `parallelism` host threads decode it speculatively
+    (bsq_pgzip.h; 1 = zlib's gzread), regions / carries / batches as for any other source; a damaged stream is
+    reported as a read failure, never parsed."""
+    import gzip
+    from blazeseq_b200 import _capi as capi
+    data = oracle.synth(40000, 100, 250, 2, 40, "sanger")          # ~7 MB compressed: several 2 MiB chunks
+    views, bases, err = oracle.parse_all(data)
+    path = tmp_path / "q.fastq.gz"
+    blob = gzip.compress(data.tobytes(), 6)
+    path.write_bytes(blob)
+    for threads in (1, 2, 0):
+        p = B.FastqParser(B.RapidgzipReader(str(path), threads), "sanger", region_bytes=3 << 20,
+                          config=B.ParserConfig(check_ascii=True, check_quality=True))
+        n = nb = 0
+        first_ids = []
+        for batch in p.batches(1000):
+            if n == 0:
+                first_ids = [batch.get_record(i).id for i in range(3)]
+            n += len(batch)
+            nb += batch.seq_len()
+        assert (n, nb) == (len(views), bases)
+        assert first_ids == [bytes(data[int(v["id_start"]):int(v["id_start"]) + int(v["id_len"])]).decode() for v in views[:3]]
+    bad = bytearray(blob)
+    bad[len(bad) // 2] ^= 0x55
+    path.write_bytes(bytes(bad))
+    # (a streaming decoder hands bytes on before the member's CRC-32 is known, as gzread does: the damage surfaces either
+    #  as a read failure or, earlier, as a parse error on the garbage -- never as a clean end of the stream)
+    gpu = B.GpuParser(False, False, B.parse_schema("sanger"), 512)
+    st = gpu.stream_open(str(path), capi.SOURCE_AUTO, 1 << 20)
+    outcome = None
+    try:
+        while True:
+            res, region, off, first = gpu.stream_next(st, capi.WANT_OFFSETS)
+            if res.stop.code != capi.OK:
+                outcome = res.stop.code
+                break
+    except Exception:
+        outcome = "raised"
+    assert outcome == "raised" or outcome not in (capi.OK, capi.EOF), outcome
+    gpu.stream_close(st)
+    gpu.close()
 
 
 def test_device_inflate_is_bit_exact_zlib(B, tmp_path, golden_dir):
