@@ -449,7 +449,8 @@ def main():
                 return {"wall_s": wall, "reads_per_s": reads / wall, "uncompressed_gb_per_s": nbytes / wall / 1e9,
                         "reader_busy_s": s_.reader_busy_s, "gpu_pass_s": s_.parse_s, "caller_wait_reader_s": s_.wait_reader_s,
                         "regions": int(s_.regions), "h2d_compressed_s": s_.h2d_s, "inflate_kernels_s": s_.inflate_s,
-                        "compressed_bytes_over_pcie": int(s_.compressed_bytes)}
+                        "compressed_bytes_over_pcie": int(s_.compressed_bytes), "launch_s": s_.launch_s,
+                        "wait_inflate_s": s_.wait_inflate_s}
             run(g, plain)                     # warm the page cache and the arenas
             run(g, bgz)
             out = {"bgzf_device_inflate": run(g, bgz), "bgzf_host_threads": run(gh, bgz), "plain_file": run(g, plain)}
@@ -737,28 +738,34 @@ def main():
             e2e["host_batch"] = {"value": total_reads / dth, "unit": "reads/s", "ms_per_step": dth * 1e3,
                                  "h2d_bytes_per_step": size, "d2h_bytes_per_step": back + d2h,
                                  "result": "host FastqBatch SoA (five arrays, pinned) via bsq_soa_to_host after the pass"}
-            # ... and the same product with both PCIe directions busy: two parser handles alternate 1 GiB regions, the
-            # SoA of region k travels back while region k+1 travels in (blazeseq_b200/pipeline.py)
+            # ... and the same product with both PCIe directions busy: two parser handles alternate regions, the SoA of
+            # region k travels back while region k+1 travels in (blazeseq_b200/pipeline.py)
             try:
-                pipe = B.HostBatchPipeline(lambda: B.GpuParser(args.validate, args.validate, schema, 4096, device_id=local),
-                                           region_bytes=1 << 30)
-                got = pipe.run(harr, *outs, stream_offset=lo_off, first_record=rank * M)     # warm-up: arenas, staging
-                assert got[0] == M and pipe.stop.code == capi.EOF, (got, pipe.stop.text)
                 ref_ends = torch.as_tensor(_DevPtr(v.ends, M, "<i8"), device=dev).cpu()
-                assert torch.equal(outs[3], ref_ends), "pipelined ends differ from the one-pass SoA"
-                barrier()
-                t0 = time.perf_counter()
-                for _ in range(args.e2e_steps):
-                    got = pipe.run(harr, *outs, stream_offset=lo_off, first_record=rank * M)
-                barrier()
-                (dtp,) = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
-                assert got == (M, int(v.sequence_bytes), int(v.seq_len), int(v.total_id_bytes)), got
+                tried = {}
+                for region in (256 << 20, 1 << 30):
+                    pipe = B.HostBatchPipeline(lambda: B.GpuParser(args.validate, args.validate, schema, 4096, device_id=local),
+                                               region_bytes=region)
+                    outs[3].zero_()
+                    got = pipe.run(harr, *outs, stream_offset=lo_off, first_record=rank * M)     # warm-up: arenas, staging
+                    assert got[0] == M and pipe.stop.code == capi.EOF, (got, pipe.stop.text)
+                    assert torch.equal(outs[3], ref_ends), "pipelined ends differ from the one-pass SoA"
+                    barrier()
+                    t0 = time.perf_counter()
+                    for _ in range(args.e2e_steps):
+                        got = pipe.run(harr, *outs, stream_offset=lo_off, first_record=rank * M)
+                    barrier()
+                    (dtp,) = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+                    assert got == (M, int(v.sequence_bytes), int(v.seq_len), int(v.total_id_bytes)), got
+                    tried[region] = dtp
+                    pipe.close()
+                region, dtp = min(tried.items(), key=lambda kv: kv[1])
                 e2e["host_batch_pipelined"] = {
                     "value": total_reads / dtp, "unit": "reads/s", "ms_per_step": dtp * 1e3, "h2d_bytes_per_step": size,
-                    "d2h_bytes_per_step": back, "region_bytes": 1 << 30,
-                    "result": "host FastqBatch SoA (five arrays, pinned); two parser handles alternate 1 GiB regions so that "
-                              "D2H of region k overlaps H2D + passes of region k+1 (HostBatchPipeline)"}
-                pipe.close()
+                    "d2h_bytes_per_step": back, "region_bytes": region,
+                    "ms_per_step_by_region_mib": {str(r >> 20): t * 1e3 for r, t in tried.items()},
+                    "result": "host FastqBatch SoA (five arrays, pinned); two parser handles alternate regions so that D2H of "
+                              "region k overlaps H2D + passes of region k+1 (HostBatchPipeline)"}
             except Exception as e:   # the headline does not depend on it
                 e2e["host_batch_pipelined"] = {"skipped": repr(e)[:300]}
             del outs

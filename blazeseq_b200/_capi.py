@@ -27,7 +27,7 @@ SYMBOLS = [
     "bsq_summarize_device", "bsq_shard_prefix", "bsq_stream_open", "bsq_stream_next", "bsq_stream_region",
     "bsq_stream_get_stats", "bsq_stream_close", "bsq_quality_sums", "bsq_soa_to_host", "bsq_stream_region_info",
     "bsq_fasta_parse_device", "bsq_fasta_parse_host", "bsq_fasta_get", "bsq_fasta_to_host",
-    "bsq_gzip_open", "bsq_gzip_read", "bsq_gzip_error", "bsq_gzip_close",
+    "bsq_gzip_open", "bsq_gzip_read", "bsq_gzip_error", "bsq_gzip_close", "bsq_write_records",
 ]
 
 
@@ -88,7 +88,7 @@ class Summary(C.Structure):
 class StreamStats(C.Structure):
     _fields_ = [("bytes_read", C.c_uint64), ("regions", C.c_uint64), ("reader_busy_s", C.c_double),
                 ("parse_s", C.c_double), ("wait_reader_s", C.c_double), ("h2d_s", C.c_double), ("inflate_s", C.c_double),
-                ("compressed_bytes", C.c_uint64)]
+                ("compressed_bytes", C.c_uint64), ("launch_s", C.c_double), ("wait_inflate_s", C.c_double)]
 
 
 SOURCE_PLAIN, SOURCE_GZIP, SOURCE_AUTO = 0, 1, 2
@@ -170,6 +170,8 @@ def lib():
         getattr(L, name).restype = i32
     L.bsq_soa_to_host.restype = i32
     L.bsq_quality_sums.restype = i32
+    L.bsq_write_records.argtypes = [vp, i64, i64, vp, u64, vp, vp, C.POINTER(u64)]
+    L.bsq_write_records.restype = i32
     L.bsq_gzip_open.argtypes = [C.c_char_p, i32, u64, C.POINTER(vp)]
     L.bsq_gzip_open.restype = i32
     L.bsq_gzip_read.argtypes = [vp, vp, u64, C.POINTER(u64)]

@@ -158,6 +158,55 @@ __global__ void __launch_bounds__(256) k_quality_sums(const uint8_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// FastqRecord.write (fastq/record.mojo:390-402, byte_len :384-388) over the device SoA: records [first, first + count)
+// serialised back to four-line FASTQ text on the device -- '@' id '\n' sequence '\n' '+' '\n' quality '\n'.
+// k_write_sizes: byte_len of every record; (exclusive scan by the caller); k_write_records: one warp per record.
+// ------------------------------------------------------------------------------------------------
+
+struct WriteParams {
+    const uint8_t* seq; const uint8_t* qual; const uint8_t* id;
+    const int64_t* ends; const int64_t* id_ends; const int64_t* ends_base; const int64_t* id_ends_base;
+    int64_t first, count;
+    int32_t batch_size;
+};
+
+__device__ __forceinline__ void write_span(const WriteParams& W, int64_t k, int64_t& lo, int64_t& hi, int64_t& id_lo, int64_t& id_hi) {
+    const int64_t b = k / W.batch_size;
+    const bool head = k % W.batch_size == 0;
+    const int64_t base = W.ends_base[b], id_base = W.id_ends_base[b];
+    lo = base + (head ? 0 : W.ends[k - 1]); hi = base + W.ends[k];
+    id_lo = id_base + (head ? 0 : W.id_ends[k - 1]); id_hi = id_base + W.id_ends[k];
+}
+
+__global__ void __launch_bounds__(256) k_write_sizes(const WriteParams W, unsigned long long* __restrict__ sizes) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= W.count; r += stride) {
+        if (r == W.count) { sizes[r] = 0ull; continue; }           // (the scan leaves the total here)
+        int64_t lo, hi, id_lo, id_hi;
+        write_span(W, W.first + r, lo, hi, id_lo, id_hi);
+        sizes[r] = (unsigned long long)(1 + (id_hi - id_lo) + 2 * (hi - lo) + 5);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_write_records(const WriteParams W, const unsigned long long* __restrict__ offs,
+                                                       uint8_t* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < W.count; r += warps) {
+        int64_t lo, hi, id_lo, id_hi;
+        write_span(W, W.first + r, lo, hi, id_lo, id_hi);
+        const int64_t n = hi - lo, ni = id_hi - id_lo;
+        uint8_t* o = out + offs[r];
+        // [ '@' | id | '\n' | seq | '\n' '+' '\n' | qual | '\n' ]
+        if (lane == 0) { o[0] = '@'; o[1 + ni] = '\n'; o[2 + ni + n] = '\n'; o[3 + ni + n] = '+'; o[4 + ni + n] = '\n'; o[5 + ni + 2 * n] = '\n'; }
+        for (int64_t i = lane; i < ni; i += 32) o[1 + i] = W.id[id_lo + i];
+        uint8_t* os = o + 2 + ni;
+        uint8_t* oq = o + 5 + ni + n;
+        for (int64_t i = lane; i < n; i += 32) { os[i] = W.seq[lo + i]; oq[i] = W.qual[lo + i]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // id strip pipeline (taken only when some header needs _strip_spaces, e.g. CRLF input)
 // ------------------------------------------------------------------------------------------------
 

@@ -85,6 +85,12 @@ struct bsq_parser {
     DevBuf run_sum, scan_out, err_word, tail_out, cub_tmp, len_prefix;   // err_word: [0] error key, [1] strip flag
     DevBuf seq_out, qual_out, id_out, ends, id_ends, ends_base, id_ends_base, id_spans;
     DevBuf host_input;               // device copy of a host pass
+    DevBuf write_offs, write_buf;    // bsq_write_records: record offsets, text when the caller gives no device buffer
+    // buffers of the last device-inflating stream (inflated regions, compressed bytes, member tables, pinned status): the next
+    // stream of this parser takes them over instead of allocating its own
+    DevBuf inf_rdev[2], inf_zdev[2], inf_mdev[2], inf_sdev[2];
+    uint32_t* inf_status[2] = {nullptr, nullptr};
+    size_t inf_status_cap[2] = {0, 0};
     void* pinned_stage[2] = {nullptr, nullptr};
     size_t pinned_stage_bytes = 0;
     HostMirror* hm = nullptr;        // pinned
@@ -349,10 +355,14 @@ extern "C" void bsq_destroy(bsq_parser* p) {
     for (auto& w : p->win) { w.line_ends.release(); w.run_pre.release(); w.nl_count.release(); w.nl_list.release(); }
     DevBuf* bufs[] = {&p->run_sum, &p->scan_out, &p->err_word, &p->tail_out, &p->cub_tmp, &p->len_prefix,
                       &p->seq_out, &p->qual_out, &p->id_out, &p->ends, &p->id_ends, &p->ends_base,
-                      &p->id_ends_base, &p->id_spans, &p->host_input, &p->fa_hdr, &p->fa_slen, &p->fa_start, &p->fa_len, &p->fa_hcum,
+                      &p->id_ends_base, &p->id_spans, &p->host_input, &p->write_offs, &p->write_buf, &p->fa_hdr, &p->fa_slen, &p->fa_start, &p->fa_len, &p->fa_hcum,
                       &p->fa_soff, &p->fa_seq, &p->fa_seq_start, &p->fa_id_start, &p->fa_id_len, &p->fa_hdr_line, &p->fa_err};
     p->fa_win.line_ends.release(); p->fa_win.run_pre.release(); p->fa_win.nl_count.release(); p->fa_win.nl_list.release();
     for (auto* b : bufs) b->release();
+    for (int i = 0; i < 2; ++i) {
+        p->inf_rdev[i].release(); p->inf_zdev[i].release(); p->inf_mdev[i].release(); p->inf_sdev[i].release();
+        if (p->inf_status[i]) cudaFreeHost(p->inf_status[i]);
+    }
     for (auto& s : p->pinned_stage) if (s) cudaFreeHost(s);
     if (p->hm) cudaFreeHost(p->hm);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
@@ -910,6 +920,7 @@ struct bsq_stream {
     struct ZBuf { uint8_t* mem = nullptr; uint64_t n = 0; std::vector<bsq::InflateMember> members; uint64_t out_bytes = 0; };
     ZBuf zb[kMaxSlots];
     uint64_t zcap = 0;                   // compressed bytes a pinned buffer holds
+    int regions_filled = 0;
     std::vector<uint8_t> zcarry;         // compressed bytes read but not yet handed out (a partial member, or over budget)
     int64_t zfile_pos = 0;
     // Two regions are in flight: while the pass of region k runs on the parser's stream, the compressed bytes of region
@@ -939,11 +950,17 @@ struct bsq_stream {
     // fills zb[which] with whole members: at most region_bytes of output, at most zcap compressed bytes
     bool fill_bgzf_raw(ZBuf& z, bool* eof) {
         z.members.clear(); z.n = 0; z.out_bytes = 0;
+        // the first regions are short (1/8, 1/4, 1/2 of a region): the read -> copy -> inflate -> parse pipeline has nothing to
+        // overlap with until its first stages have run once, so it is filled with small pieces
+        const int shift = regions_filled < 3 ? 3 - regions_filled : 0;
+        ++regions_filled;
+        const uint64_t out_limit = std::max<uint64_t>(region_bytes >> shift, std::min<uint64_t>(region_bytes, 1ull << 20));
+        const uint64_t z_limit = std::max<uint64_t>(zcap >> shift, std::min<uint64_t>(zcap, 1ull << 20));
         uint64_t have = zcarry.size();
         if (have) memcpy(z.mem, zcarry.data(), have);
         zcarry.clear();
         // parallel pread of the next compressed bytes
-        const uint64_t want = (uint64_t)std::min<int64_t>((int64_t)(zcap - have), file_size - zfile_pos);
+        const uint64_t want = have >= z_limit ? 0 : (uint64_t)std::min<int64_t>((int64_t)(z_limit - have), file_size - zfile_pos);
         if (want > 0) {
             const int nt = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)io_threads, want >> 22));
             const uint64_t slice = (want + (uint64_t)nt - 1) / (uint64_t)nt;
@@ -978,12 +995,12 @@ struct bsq_stream {
             const uint32_t crc = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
             const uint32_t isz = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
             if (isz > (1u << 16)) return false;
-            if (z.out_bytes + isz > region_bytes && !z.members.empty()) break;   // belongs to the next region
+            if (z.out_bytes + isz > out_limit && !z.members.empty()) break;      // belongs to the next region
             if (isz > 0) z.members.push_back(bsq::InflateMember{pos + 18, total - 18u - 8u, isz, z.out_bytes, crc, 0u});
             z.out_bytes += isz;
             pos += total;
         }
-        if (pos == 0 && have > 0 && (have >= zcap || zfile_pos >= file_size)) return false;   // a member that never completes
+        if (pos == 0 && have > 0 && (have >= z_limit || zfile_pos >= file_size)) return false;   // a member that never completes
         z.n = pos;
         zcarry.assign(z.mem + pos, z.mem + have);
         *eof = zfile_pos >= file_size && zcarry.empty();
@@ -1236,6 +1253,12 @@ extern "C" bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t s
             cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&z.mem), s->zcap + 64, cudaHostAllocDefault);
             if (e != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, e, "cudaHostAlloc(compressed region)"); }
         }
+        for (int i = 0; i < 2; ++i) {            // the buffers of the parser's previous device-inflating stream
+            s->job[i].zdev = p->inf_zdev[i]; s->job[i].mdev = p->inf_mdev[i]; s->job[i].sdev = p->inf_sdev[i]; s->rdev[i] = p->inf_rdev[i];
+            s->job[i].status = p->inf_status[i]; s->job[i].status_cap = p->inf_status_cap[i];
+            p->inf_zdev[i] = DevBuf(); p->inf_mdev[i] = DevBuf(); p->inf_sdev[i] = DevBuf(); p->inf_rdev[i] = DevBuf();
+            p->inf_status[i] = nullptr; p->inf_status_cap[i] = 0;
+        }
         cudaError_t e = opt_in_smem(kInflateKernel, sizeof(InflateTables) * kInfPerCta);
         if (e != cudaSuccess) { bsq_stream_close(s); return fail_cuda(p, e, "k_inflate_members shared memory"); }
     } else
@@ -1267,7 +1290,16 @@ extern "C" void bsq_stream_close(bsq_stream* s) {
         if (s->p->copy_stream) cudaStreamSynchronize(s->p->copy_stream);   // a prefetched region may still be inflating
         if (s->p->stream) cudaStreamSynchronize(s->p->stream);
     }
-    for (auto& j : s->job) {
+    for (int i = 0; i < 2; ++i) {
+        auto& j = s->job[i];
+        if (s->p && s->gpu_inflate) {          // kept for the parser's next stream
+            bsq_parser* p = s->p;
+            p->inf_zdev[i].release(); p->inf_mdev[i].release(); p->inf_sdev[i].release(); p->inf_rdev[i].release();
+            if (p->inf_status[i]) cudaFreeHost(p->inf_status[i]);
+            p->inf_zdev[i] = j.zdev; p->inf_mdev[i] = j.mdev; p->inf_sdev[i] = j.sdev; p->inf_rdev[i] = s->rdev[i];
+            p->inf_status[i] = j.status; p->inf_status_cap[i] = j.status_cap;
+            j.zdev = DevBuf(); j.mdev = DevBuf(); j.sdev = DevBuf(); s->rdev[i] = DevBuf(); j.status = nullptr; j.status_cap = 0;
+        }
         j.zdev.release(); j.mdev.release(); j.sdev.release();
         if (j.status) cudaFreeHost(j.status);
         if (j.e_start) cudaEventDestroy(j.e_start);
@@ -1404,7 +1436,10 @@ static bsq_status stream_next_device_inflate(bsq_stream* s, uint32_t want, bsq_p
         }
     }
     // this region: inflated?
+    const auto tw0 = std::chrono::steady_clock::now();
+    s->st.launch_s += std::chrono::duration<double>(tw0 - t1).count();
     CK(cudaEventSynchronize(J.e_done));
+    s->st.wait_inflate_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw0).count();
     float ms_copy = 0.f, ms_inf = 0.f;
     cudaEventElapsedTime(&ms_copy, J.e_start, J.e_h2d);
     cudaEventElapsedTime(&ms_inf, J.e_k0, J.e_done);
@@ -1669,6 +1704,46 @@ extern "C" bsq_status bsq_soa_to_host(bsq_parser* p, uint8_t* seq, uint8_t* qual
     if (id_ends) CK(cudaMemcpyAsync(id_ends, v.id_ends, 8 * v.num_records, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->copy_stream));
     CK(cudaStreamSynchronize(p->stream));
+    return BSQ_OK;
+}
+
+extern "C" bsq_status bsq_write_records(bsq_parser* p, int64_t first_record, int64_t count, uint8_t* out_device, uint64_t capacity,
+                                        uint8_t* out_host, uint64_t* offsets_host, uint64_t* bytes_written) {
+    if (!p || first_record < 0 || count < 0 || !bytes_written) return BSQ_E_ARG;
+    if (!p->have_pass || !(p->want & BSQ_WANT_BATCHES)) return BSQ_E_STATE;
+    if (first_record + count > p->res.n_records) return BSQ_E_ARG;
+    *bytes_written = 0;
+    if (count == 0) { if (offsets_host) offsets_host[0] = 0; return BSQ_OK; }
+    CK(cudaSetDevice(p->cfg.device_id));
+    WriteParams W{};
+    W.seq = p->seq_out.as<uint8_t>(); W.qual = p->qual_out.as<uint8_t>(); W.id = p->id_out.as<uint8_t>();
+    W.ends = p->ends.as<int64_t>(); W.id_ends = p->id_ends.as<int64_t>();
+    W.ends_base = p->ends_base.as<int64_t>(); W.id_ends_base = p->id_ends_base.as<int64_t>();
+    W.first = first_record; W.count = count; W.batch_size = p->cfg.batch_size;
+    CK(p->write_offs.ensure(8ull * (size_t)(count + 1), 1 << 16));
+    unsigned long long* offs = p->write_offs.as<unsigned long long>();
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)p->sm_count * 8, (count + 256) / 256));
+    k_write_sizes<<<grid, 256, 0, p->stream>>>(W, offs);
+    size_t tmp = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, offs, offs, (int)(count + 1), p->stream));
+    CK(p->cub_tmp.ensure(tmp + 16));
+    CK(cub::DeviceScan::ExclusiveSum(p->cub_tmp.p, tmp, offs, offs, (int)(count + 1), p->stream));
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, offs + count, 8, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    *bytes_written = total;
+    if (offsets_host) CK(cudaMemcpyAsync(offsets_host, offs, 8ull * (size_t)(count + 1), cudaMemcpyDeviceToHost, p->stream));
+    if (out_device || out_host) {
+        uint8_t* dst = out_device;
+        if (dst) { if (capacity < total) return BSQ_E_ARG; }
+        else { CK(p->write_buf.ensure((size_t)total + 16, 1 << 20)); dst = p->write_buf.as<uint8_t>(); }
+        const int gridw = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)p->sm_count * 8, (count + 7) / 8));
+        k_write_records<<<gridw, 256, 0, p->stream>>>(W, offs, dst);
+        CK(cudaGetLastError());
+        if (out_host) CK(cudaMemcpyAsync(out_host, dst, (size_t)total, cudaMemcpyDeviceToHost, p->stream));
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    p->n_launches += 3;
     return BSQ_OK;
 }
 

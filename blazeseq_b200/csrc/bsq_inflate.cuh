@@ -34,7 +34,7 @@ struct InflateMember {
 #define BSQ_INF_LANES 32
 #endif
 #ifndef BSQ_INF_WARPS
-#define BSQ_INF_WARPS 4
+#define BSQ_INF_WARPS 8
 #endif
 constexpr int kInfWarps = BSQ_INF_WARPS;   // warps per CTA
 constexpr int kInfLanes = BSQ_INF_LANES;   // lanes per member: one decodes, all copy
@@ -376,13 +376,81 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members(const uint8_
 #ifndef BSQ_INF_UNIFORM
 #define BSQ_INF_UNIFORM 1
 #endif
+
+// ---- bit reader of the shipped kernel: a 64-bit window (lo, hi) of the payload and a bit offset into it.  One funnel shift
+// yields the next 32 bits; consuming bits is an add to the offset.  br32_fill() moves the window on by a word once 32 bits are
+// used up, so after it `off < 32` and br32_window() holds 32 valid bits -- enough for a literal/length code with its extra bits
+// (<= 20) or a distance code with its extra bits (<= 28).  The word after the window is prefetched.
+struct Br32 {
+    const uint32_t* wp;                    // next word to fetch
+    const uint32_t* wend;                  // one past the last word that holds payload bytes
+    const uint32_t* w0;                    // first word
+    uint32_t lo, hi, next;                 // window and the prefetched word
+    uint32_t off;                          // bits of (lo, hi) already consumed (< 64)
+    uint32_t lead;                         // bits of the first word that precede the payload (8 x misalignment)
+    uint32_t base_bytes;                   // payload bytes before w0's payload start (after a stored block)
+    uint32_t overrun;                      // the reader ran words past the payload (a damaged stream)
+};
+__device__ __forceinline__ uint32_t br32_word(Br32& b) {
+    const uint32_t v = b.wp < b.wend ? __ldg(b.wp) : 0u;          // (past the end: zeros)
+    ++b.wp;
+    return v;
+}
+__device__ __forceinline__ void br32_init(Br32& b, const uint8_t* p, uint32_t nbytes, uint32_t base_bytes) {
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+    b.w0 = b.wp = reinterpret_cast<const uint32_t*>(p - a);
+    b.wend = b.w0 + ((a + nbytes + 3u) >> 2);
+    b.lo = br32_word(b); b.hi = br32_word(b); b.next = br32_word(b);
+    b.off = 8u * a; b.lead = 8u * a;
+    b.base_bytes = base_bytes;
+    b.overrun = 0;
+}
+__device__ __forceinline__ void br32_fill(Br32& b) {
+    if (b.off >= 32u) {
+        b.lo = b.hi; b.hi = b.next;
+        if (b.wp > b.wend + 4) b.overrun = 1u;                    // a damaged stream must end the member, not spin on zeros
+        b.next = br32_word(b);
+        b.off -= 32u;
+    }
+}
+__device__ __forceinline__ uint32_t br32_window(const Br32& b) { return __funnelshift_r(b.lo, b.hi, b.off); }
+// payload bits consumed so far
+__device__ __forceinline__ uint64_t br32_consumed(const Br32& b) {
+    return (uint64_t)b.base_bytes * 8u + (uint64_t)(b.wp - b.w0 - 3) * 32u + b.off - b.lead;
+}
+// n <= 16 bits (block headers)
+__device__ __forceinline__ uint32_t br32_take(Br32& b, uint32_t n) {
+    br32_fill(b);
+    const uint32_t v = br32_window(b) & ((1u << n) - 1u);
+    b.off += n;
+    return v;
+}
+__device__ __forceinline__ uint32_t inf_lds(uint32_t addr) {          // one table entry (32-bit shared-memory address)
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// canonical decode of a code longer than the lookup width from the window's bits; returns the symbol or -1
+__device__ int32_t inf_slow32(uint32_t w, const uint16_t* sym, const uint16_t* count, uint32_t& used) {
+    int32_t code = 0, first = 0, index = 0;
+    for (int l = 1; l < 16; ++l) {
+        code |= (int32_t)(w & 1u);
+        w >>= 1;
+        const int32_t c = count[l];
+        if (code - c < first) { used = (uint32_t)l; return sym[index + (code - first)]; }
+        index += c; first += c; first <<= 1; code <<= 1;
+    }
+    used = 15u;
+    return -1;
+}
+
 // The shipped form (one warp per member, kInfLanes == 32): EVERY lane runs the decode loop on identical state -- the
 // same input words (one broadcast load), the same table lookups (one shared-memory broadcast) -- so the warp never
 // leaves the loop: no leader hand-off, no shuffles, no votes.  A redundant lane costs nothing on a SIMT machine (the
 // warp instruction issues once either way), and every lane already knows (position, length, distance) when a match
-// comes up: lane i copies byte i.  Literals are stored by lane 0.  Only the block headers (a few per member) are
-// parsed by lane 0 alone and the reader state is broadcast afterwards.  As before, a match's bytes are loaded when it is
-// decoded and stored at the next match (the decoder never waits for them).
+// comes up: lane i copies byte i.  A literal is stored by every lane (one address, one value: one transaction).  Only the
+// block headers (a few per member) are parsed by lane 0 alone and the reader state is broadcast afterwards.  As before, a
+// match's bytes are loaded when it is decoded and stored at the next match (the decoder never waits for them).
 __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members_uniform(const uint8_t* __restrict__ zbuf, uint8_t* __restrict__ out,
                                                                           const InflateMember* __restrict__ members, uint32_t n_members,
                                                                           uint32_t* __restrict__ status) {
@@ -396,33 +464,34 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members_uniform(cons
     uint8_t* const dst = out + M.dst;
     const uint8_t* const src0 = zbuf + M.src;
     const uint32_t cap = M.isize;
-    BitReader br{};
-    br_init(br, src0, M.src_len, 0u);
+    // shared-memory addresses of the two lookup tables, kept in registers (opaque to the compiler, which otherwise rebuilds
+    // them from the thread index in front of every lookup)
+    uint32_t lit_base = (uint32_t)__cvta_generic_to_shared(T.lit), dist_base = (uint32_t)__cvta_generic_to_shared(T.dist);
+    asm volatile("" : "+r"(lit_base), "+r"(dist_base));
+    Br32 br{};
+    br32_init(br, src0, M.src_len, 0u);
     uint32_t pos = 0, err = 0;
     bool last = false, finished = false;
-    int tables = 0;                                   // 0 none, 1 fixed, 2 dynamic (lane 0 keeps the tables)
+    int tables = 0;                                   // 0 none, 1 fixed, 2 dynamic
     uint32_t pend_pos = kNone;                        // a match byte loaded but not yet stored (per lane)
-    uint8_t pend_val = 0;
+    uint32_t pend_val = 0;
 
     while (!finished && err == 0u) {
         // ---- block header: every lane reads the three header bits; lane 0 alone sets the tables up ----
-        br_fill(br);
-        last = br_take(br, 1) != 0u;
-        const uint32_t btype = br_take(br, 2);
+        last = br32_take(br, 1) != 0u;
+        const uint32_t btype = br32_take(br, 2);
         if (btype == 0u) {
-            br_skip(br, br.cnt & 7u);                                     // to the byte boundary
-            br_fill(br);
-            const uint32_t len = br_take(br, 16);
-            br_fill(br);
-            const uint32_t nlen = br_take(br, 16);
-            const uint32_t st_src = (uint32_t)(br_consumed(br) >> 3);     // payload offset of the raw bytes
+            br.off = (br.off + 7u) & ~7u;                                 // to the byte boundary
+            const uint32_t len = br32_take(br, 16);
+            const uint32_t nlen = br32_take(br, 16);
+            const uint32_t st_src = (uint32_t)(br32_consumed(br) >> 3);   // payload offset of the raw bytes
             if ((len ^ nlen) != 0xFFFFu) { err = 1u; break; }
             if (pos + len > cap) { err = 2u; break; }
             if (st_src + len > M.src_len) { err = 3u; break; }
-            if (pend_pos != kNone) { dst[pend_pos] = pend_val; pend_pos = kNone; }
+            if (pend_pos != kNone) { dst[pend_pos] = (uint8_t)pend_val; pend_pos = kNone; }
             for (uint32_t i = lane; i < len; i += 32u) dst[pos + i] = src0[st_src + i];
             pos += len;
-            br_init(br, src0 + st_src + len, M.src_len - st_src - len, st_src + len);
+            br32_init(br, src0 + st_src + len, M.src_len - st_src - len, st_src + len);
             if (last) finished = true;
             continue;
         }
@@ -442,25 +511,25 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members_uniform(cons
                         inf_build(T.lens, 30, T.dist, kDistBits, T.dist_sym, T.dist_count, true);
                     }
                 } else {
-                    const uint32_t hlit = br_take(br, 5) + 257u, hdist = br_take(br, 5) + 1u, hclen = br_take(br, 4) + 4u;
+                    const uint32_t hlit = br32_take(br, 5) + 257u, hdist = br32_take(br, 5) + 1u, hclen = br32_take(br, 4) + 4u;
                     if (hlit > 286u || hdist > 30u) herr = 1u;
                     uint8_t* cl = T.lens + 300;                             // 19 code-length code lengths
                     for (int i = 0; i < 19; ++i) cl[i] = 0;
-                    for (uint32_t i = 0; i < hclen && herr == 0u; ++i) { br_fill(br); cl[kInfClOrder[i]] = (uint8_t)br_take(br, 3); }
+                    for (uint32_t i = 0; i < hclen && herr == 0u; ++i) cl[kInfClOrder[i]] = (uint8_t)br32_take(br, 3);
                     // the code-length code borrows the distance table's storage (7-bit lookup)
                     if (herr == 0u && !inf_build(cl, 19, T.dist, 7, T.dist_sym, T.dist_count, false)) herr = 1u;
                     uint32_t i = 0;
                     while (i < hlit + hdist && herr == 0u) {
-                        br_fill(br);
-                        const uint32_t e = T.dist[br_peek(br, 7)];
+                        br32_fill(br);
+                        const uint32_t e = T.dist[br32_window(br) & 127u];
                         if ((e & 0xF0u) != 0u) { herr = 1u; break; }        // not a (valid) symbol of the code-length code
-                        br_skip(br, e & 15u);
+                        br.off += e & 15u;
                         const uint32_t s = e >> 16;
                         if (s < 16u) { T.lens[i++] = (uint8_t)s; continue; }
                         uint32_t rep, val = 0;
-                        if (s == 16u) { if (i == 0u) { herr = 1u; break; } val = T.lens[i - 1]; rep = 3u + br_take(br, 2); }
-                        else if (s == 17u) rep = 3u + br_take(br, 3);
-                        else rep = 11u + br_take(br, 7);
+                        if (s == 16u) { if (i == 0u) { herr = 1u; break; } val = T.lens[i - 1]; rep = 3u + br32_take(br, 2); }
+                        else if (s == 17u) rep = 3u + br32_take(br, 3);
+                        else rep = 11u + br32_take(br, 7);
                         if (i + rep > hlit + hdist) { herr = 1u; break; }
                         while (rep--) T.lens[i++] = (uint8_t)val;
                     }
@@ -479,63 +548,66 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members_uniform(cons
                 // the reader moved in lane 0 only
                 const uint32_t adv = __shfl_sync(kFull, (uint32_t)(br.wp - br.w0), 0);
                 br.wp = br.w0 + adv;
-                br.buf = ((uint64_t)__shfl_sync(kFull, (uint32_t)(br.buf >> 32), 0) << 32) | __shfl_sync(kFull, (uint32_t)br.buf, 0);
-                br.cnt = __shfl_sync(kFull, br.cnt, 0);
-                br.nextw = __shfl_sync(kFull, br.nextw, 0);
+                br.lo = __shfl_sync(kFull, br.lo, 0);
+                br.hi = __shfl_sync(kFull, br.hi, 0);
+                br.next = __shfl_sync(kFull, br.next, 0);
+                br.off = __shfl_sync(kFull, br.off, 0);
                 br.overrun = __shfl_sync(kFull, br.overrun, 0);
             }
             if (herr != 0u) { err = herr; break; }
         }
-        // ---- the block's symbols: every lane decodes, lane 0 stores literals, lane i copies byte i of a match ----
+        // ---- the block's symbols: every lane decodes, every lane stores the literal, lane i copies byte i of a match ----
         while (true) {
-            br_fill(br);
-            uint32_t e = T.lit[br_peek(br, kLitBits)];
+            br32_fill(br);
+            uint32_t w = br32_window(br);
+            uint32_t e = inf_lds(lit_base + ((w & ((1u << kLitBits) - 1u)) << 2));
             if ((e & 0xF0u) == 0u) {                                  // a literal (the common case)
-                br_skip(br, e & 15u);
+                br.off += e & 15u;
                 if (pos >= cap) { err = 2u; break; }
-                if (lane == 0u) dst[pos] = (uint8_t)(e >> 16);
+                dst[pos] = (uint8_t)(e >> 16);
                 ++pos;
                 continue;
             }
             uint32_t kind = (e >> 4) & 15u;
-            uint32_t base, extra;
+            uint32_t base, extra, used;
             if (kind == kKindLen) {
-                br_skip(br, e & 15u);
-                base = e >> 16; extra = (e >> 8) & 255u;
+                used = e & 15u; base = e >> 16; extra = (e >> 8) & 255u;
             } else if (kind == kKindEob) {
-                br_skip(br, e & 15u);
+                br.off += e & 15u;
                 if (last) finished = true;
                 break;
             } else if (kind == kKindSlow) {                           // a code longer than the table width
-                const int32_t s = inf_slow(br, T.lit_sym, T.lit_count);
+                const int32_t s = inf_slow32(w, T.lit_sym, T.lit_count, used);
                 if (s < 0 || s >= 286) { err = 1u; break; }
                 if (s < 256) {
+                    br.off += used;
                     if (pos >= cap) { err = 2u; break; }
-                    if (lane == 0u) dst[pos] = (uint8_t)s;
+                    dst[pos] = (uint8_t)s;
                     ++pos;
                     continue;
                 }
-                if (s == 256) { if (last) finished = true; break; }
+                if (s == 256) { br.off += used; if (last) finished = true; break; }
                 base = kInfLenBase[s - 257]; extra = kInfLenExtra[s - 257];
             } else { err = 1u; break; }
-            const uint32_t mlen = base + br_take(br, extra);
-            br_fill(br);
-            e = T.dist[br_peek(br, kDistBits)];
+            const uint32_t mlen = base + ((w >> used) & ((1u << extra) - 1u));
+            br.off += used + extra;                                   // <= 20 bits of the window
+            br32_fill(br);
+            w = br32_window(br);
+            e = inf_lds(dist_base + ((w & ((1u << kDistBits) - 1u)) << 2));
             kind = (e >> 4) & 15u;
             if (kind == kKindLen) {
-                br_skip(br, e & 15u);
-                base = e >> 16; extra = (e >> 8) & 255u;
+                used = e & 15u; base = e >> 16; extra = (e >> 8) & 255u;
             } else if (kind == kKindSlow) {
-                const int32_t d = inf_slow(br, T.dist_sym, T.dist_count);
+                const int32_t d = inf_slow32(w, T.dist_sym, T.dist_count, used);
                 if (d < 0 || d >= 30) { err = 1u; break; }
                 base = kInfDistBase[d]; extra = kInfDistExtra[d];
             } else { err = 1u; break; }
-            br_fill(br);
-            const uint32_t mdist = base + br_take(br, extra);
+            const uint32_t mdist = base + ((w >> used) & ((1u << extra) - 1u));
+            br.off += used + extra;                                   // <= 28 bits of the window
             if (mdist > pos || pos + mlen > cap || mdist > 32768u) { err = 2u; break; }
             // the previous match's bytes were only LOADED when it was decoded: they are stored now, when the loads have long
-            // returned; then lane 0's literal stores and these become visible to the warp
-            if (pend_pos != kNone) { dst[pend_pos] = pend_val; pend_pos = kNone; }
+            // returned; then the literal stores and these are visible to the whole warp
+            if (pend_pos != kNone) { dst[pend_pos] = (uint8_t)pend_val; pend_pos = kNone; }
             __syncwarp();
             const uint8_t* s = dst + pos - mdist;
             if (mlen <= 32u) {                                         // one byte per lane: load now, store at the next match
@@ -554,11 +626,11 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members_uniform(cons
         }
         if (br.overrun) err = 3u;
     }
-    if (pend_pos != kNone) dst[pend_pos] = pend_val;
+    if (pend_pos != kNone) dst[pend_pos] = (uint8_t)pend_val;
     if (lane == 0u) {
         uint32_t st = err;
         if (st == 0u && br.overrun) st = 3u;
-        if (st == 0u && br_consumed(br) > (uint64_t)M.src_len * 8u) st = 3u;
+        if (st == 0u && br32_consumed(br) > (uint64_t)M.src_len * 8u) st = 3u;
         if (st == 0u && pos != cap) st = 4u;
         status[m] = st;
     }

@@ -326,6 +326,13 @@ class DeviceFastqBatch:
         self._check()
         return FastqBatch._from_arrays(*self._gpu.batch_to_host(self._index), quality_offset=self.quality_offset)
 
+    def write(self) -> bytes:
+        """The batch's records as four-line FASTQ text (FastqRecord.write, record.mojo:390-402), serialised on the device."""
+        self._check()
+        m = self._gpu.cfg.batch_size
+        text, _ = self._gpu.write_records(self._index * m, self.num_records)
+        return text.tobytes()
+
 
 class FastqBatch:
     """record_batch.mojo:19-207: five arrays, Int64 inclusive cumulative ends restarting per batch."""
@@ -556,6 +563,26 @@ class GpuParser:
                                                     C.c_void_p(ids.ctypes.data), C.c_void_p(ist.ctypes.data)), self._h,
                        "bsq_fasta_to_host")
         return seq, ss, ids, ist
+
+    def write_records(self, first_record: int = 0, count: Optional[int] = None, out_device_ptr: int = 0, capacity: int = 0,
+                      to_host: bool = True, want_offsets: bool = False):
+        """bsq_write_records: records [first_record, first_record + count) of the last batches() pass as FASTQ text, written by
+        the device.  Returns (text as np.uint8 or None, offsets as np.uint64[count + 1] or None); with out_device_ptr the
+        text also (or only, to_host=False) lands in the caller's device buffer."""
+        if count is None:
+            count = int(self.result.n_records) - first_record
+        n = C.c_uint64(0)
+        offs = np.zeros(count + 1, np.uint64) if want_offsets else None
+        op = C.c_void_p(offs.ctypes.data) if offs is not None else C.c_void_p(0)
+        # size first, then the text
+        capi.check(capi.lib().bsq_write_records(self._h, first_record, count, C.c_void_p(0), 0, C.c_void_p(0), op, C.byref(n)),
+                   self._h, "bsq_write_records")
+        text = np.empty(int(n.value), np.uint8) if to_host else None
+        if to_host or out_device_ptr:
+            capi.check(capi.lib().bsq_write_records(
+                self._h, first_record, count, C.c_void_p(out_device_ptr), capacity,
+                C.c_void_p(text.ctypes.data if (text is not None and text.size) else 0), op, C.byref(n)), self._h, "bsq_write_records")
+        return text, offs
 
     def quality_sums(self, first_record: int = 0, count: Optional[int] = None, out_device_ptr: int = 0) -> np.ndarray:
         """Per-record sum of Phred scores of the last batches() pass, computed on the device from the SoA

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BSQ_ABI_VERSION 2
+#define BSQ_ABI_VERSION 3
 
 /* >= 0: FastxErrorCode, identical to blazeseq/errors.mojo:43-56.  < 0: library failures. */
 typedef int32_t bsq_status;
@@ -214,6 +214,8 @@ typedef struct bsq_stream_stats {
     double h2d_s;                  /* device-inflated BGZF: device time of the compressed bytes' H2D copies ... */
     double inflate_s;              /* ... and of k_inflate_members + k_crc32_members (CUDA events) */
     uint64_t compressed_bytes;     /* ... and the compressed bytes that crossed PCIe */
+    double launch_s;               /* ... caller: time spent enqueueing copies / kernels (incl. buffer growth) */
+    double wait_inflate_s;         /* ... caller: time blocked until a region was inflated */
 } bsq_stream_stats;
 
 bsq_status bsq_stream_open(bsq_parser* p, const char* path, int32_t source_kind, uint64_t region_bytes,
@@ -254,6 +256,14 @@ void bsq_gzip_close(bsq_gzip* g);
  * per-batch `ends`.  The int32 results go to out_device (device pointer, may be NULL: a library buffer is
  * used) and, if out_host is not NULL, are copied there.  The parsed bytes never visit the host. */
 bsq_status bsq_quality_sums(bsq_parser* p, int64_t first_record, int64_t count, int32_t* out_device, int32_t* out_host);
+
+/* FastqRecord.write / byte_len (fastq/record.mojo:384-402) over the device SoA of the last batches() pass: records
+ * [first_record, first_record + count) serialised back to four-line FASTQ text ('@' id '\n' sequence '\n' '+' '\n' quality '\n')
+ * by one warp per record -- the device side of records() and of the writer round trip (tests/fastq/test_fastq_integration.mojo).
+ * out_device (capacity bytes) and / or out_host receive the text; both NULL: only *bytes_written (the size to allocate) and the
+ * offsets are computed.  offsets_host (optional, count + 1 entries): byte offset of every record in the text. */
+bsq_status bsq_write_records(bsq_parser* p, int64_t first_record, int64_t count, uint8_t* out_device, uint64_t capacity,
+                             uint8_t* out_host, uint64_t* offsets_host, uint64_t* bytes_written);
 
 bsq_status bsq_get_offsets(const bsq_parser* p, int32_t window, bsq_offsets_view* out);
 /* FastqParser.next_batch(max_records) restricted to the pass: batch b holds records

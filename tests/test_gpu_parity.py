@@ -610,6 +610,64 @@ def test_whole_batches_regions_and_the_host_batch_pipeline(B, oracle):
     pipe.close()
 
 
+def test_device_writer_round_trip(B, oracle):
+    """bsq_write_records (FastqRecord.write over the device SoA, record.mojo:384-402): the text the device writes is the
+    records' canonical four-line form -- equal to the input when the input is canonical, the '\r'-free / bare-'+' form
+    otherwise -- its offsets are the running byte_len, and parsing it again gives the same batches
+    (tests/fastq/test_fastq_integration.mojo round trips)."""
+    import torch
+    from blazeseq_b200 import _capi as capi
+    m = 300
+    data = oracle.synth(5000, 40, 260, 2, 40, "sanger")
+    gpu = B.GpuParser(True, True, B.parse_schema("sanger"), m)
+    r = gpu.parse_host(data, want=capi.WANT_BATCHES)
+    assert r.n_records == 5000
+    text, offs = gpu.write_records(want_offsets=True)
+    assert np.array_equal(text, data)                                   # synthetic input is canonical FASTQ
+    views, _, _ = oracle.parse_all(data)
+    assert np.array_equal(offs[:-1].astype(np.int64), views["header_start"]) and int(offs[-1]) == data.size
+    # a slice that starts inside a batch and ends inside another, into a caller's device buffer
+    a, n = 257, 1234
+    dev = torch.zeros(int(offs[a + n] - offs[a]) + 7, dtype=torch.uint8, device="cuda")
+    t2, o2 = gpu.write_records(a, n, out_device_ptr=dev.data_ptr(), capacity=dev.numel(), want_offsets=True)
+    assert np.array_equal(t2, data[int(offs[a]):int(offs[a + n])]) and np.array_equal(dev.cpu().numpy()[:t2.size], t2)
+    assert np.array_equal(o2, offs[a:a + n + 1] - offs[a]) and not dev[t2.size:].any()
+    with pytest.raises(Exception):
+        gpu.write_records(a, n, out_device_ptr=dev.data_ptr(), capacity=10)      # too small a buffer
+    b3 = B.DeviceFastqBatch(gpu, 3, gpu.batch_view(3))
+    assert b3.write() == data[int(offs[3 * m]):int(offs[4 * m])].tobytes()
+
+    # CRLF input with '+id' lines and padded ids: the writer emits what FastqRecord.write would
+    recs = []
+    for i in range(700):
+        L = 30 + (i * 7) % 90
+        seq = bytes(b"ACGT"[(i + j) % 4] for j in range(L))
+        qual = bytes(33 + (i * 3 + j) % 40 for j in range(L))
+        recs.append((b"r%d  desc %d" % (i, i), seq, qual))
+    messy = b"".join(b"@" + i + b" \r\n" + s + b"\r\n+" + i + b"\r\n" + q + b"\r\n" for i, s, q in recs)
+    arr = np.frombuffer(messy, np.uint8)
+    gpu.close()
+    gpu = B.GpuParser(False, False, B.parse_schema("sanger"), m)        # ('\r' in the quality line fails check_quality, Q6)
+    r = gpu.parse_host(arr, want=capi.WANT_BATCHES)
+    assert r.n_records == 700
+    text, _ = gpu.write_records()
+    ov, _, _ = oracle.parse_all(arr)
+    ob = oracle.build_batch(arr, ov)
+    ide = np.concatenate([[0], ob[3]]); ee = np.concatenate([[0], ob[4]])
+    want = b"".join(b"@" + ob[0][ide[k]:ide[k + 1]].tobytes() + b"\n" + ob[1][ee[k]:ee[k + 1]].tobytes() + b"\n+\n" +
+                    ob[2][ee[k]:ee[k + 1]].tobytes() + b"\n" for k in range(700))
+    assert text.tobytes() == want
+    # ... and the text parses back to the same records (ids stripped, '\r' kept in sequence / quality as the reference does)
+    r2 = gpu.parse_host(text.copy(), want=capi.WANT_BATCHES)
+    assert r2.n_records == 700
+    for b in range(int(r2.n_batches)):
+        got = gpu.batch_to_host(b)
+        e = oracle.build_batch(arr, ov[b * m:(b + 1) * m])
+        for g, x in zip(got, (e[1], e[2], e[0], e[4], e[3])):
+            assert np.array_equal(g, x)
+    gpu.close()
+
+
 def test_shard_summaries_locate_record_starts(B, oracle):
     """Multi-GPU stitching: summaries of arbitrary byte shards (device) -> where each shard's first
     own record starts (host arithmetic) must match the oracle's record table."""

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(B):
     L = B._capi.lib()
     for name in declared:
         assert getattr(L, name) is not None
-    assert L.bsq_abi_version() == 2
+    assert L.bsq_abi_version() == 3
 
 
 def test_struct_layouts_match_header(B):
