@@ -270,7 +270,7 @@ def main():
     ap.add_argument("--shard-stream", action="store_true",
                     help="strong scaling: ONE stream of --gib cut at arbitrary byte offsets over the ranks (sharding.plan)")
     ap.add_argument("--gzip", action="store_true", help="configs[4]: .fastq.gz / BGZF files through the stream pipeline (--gib 4)")
-    ap.add_argument("--region-mib", type=int, default=256, help="--gzip: region size of the stream pipeline")
+    ap.add_argument("--region-mib", type=int, default=512, help="--gzip: region size of the stream pipeline")
     ap.add_argument("--crlf", action="store_true", help="CRLF line ends: every id needs _strip_spaces (id strip pipeline)")
     ap.add_argument("--read-len", type=int, default=150, help="read length of the synthetic stream (record stride sweeps)")
     ap.add_argument("--id-digits", type=int, default=0, help="zero-padded id width (0: that of the stream's read count)")
@@ -384,7 +384,7 @@ def main():
     # ------------------------------------------------------------------------------------------------
     # configs[4]: a .fastq.gz through the native stream pipeline (bsq_stream_*), file -> results
     # ------------------------------------------------------------------------------------------------
-    def gzip_leg(gib, region_mib=256):
+    def gzip_leg(gib, region_mib=512):
         """Writes `gib` of the 150 bp stream as a plain file, as BGZF (gzip level 6, 64 KiB members) and as an ordinary
         single-member gzip file, and streams each through bsq_stream_next(WANT_BATCHES).  BGZF: the compressed members
         cross PCIe and are inflated on the device (k_inflate_members); ordinary gzip is decoded speculatively in parallel

@@ -499,6 +499,7 @@ __global__ void __launch_bounds__(kInfWarps * 32) k_inflate_members_uniform(cons
         {
             // lane 0 parses the rest of the header and builds the tables; its reader state and verdict are broadcast
             uint32_t herr = 0;
+            __syncwarp();                                                 // every lane is through with the previous block's tables
             if (lane == 0u) {
                 if (btype == 1u) {
                     if (tables != 1) {

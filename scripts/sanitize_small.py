@@ -1,5 +1,6 @@
 """Small end-to-end inputs for compute-sanitizer (scripts/gpu_sanitize.sh): the device inflater on the reference's .bgz
-fixtures and a synthetic BGZF file (all block types), the FASTA path, a 320-byte-stride batch pass (rotated staging)."""
+fixtures and a synthetic BGZF file (all block types), the FASTA path, a 320-byte-stride batch pass (rotated staging), the
+device writer."""
 import os
 import sys
 import tempfile
@@ -40,6 +41,12 @@ arr = np.frombuffer(data, np.uint8)
 res = g.parse_host(arr, want=3)
 views, bases, err = O.parse_all(arr, O.config(True, False))
 assert res.n_records == len(views) == 1500 and res.n_bases == bases
+# the device writer (FastqRecord.write over the SoA) and the whole-batches cut
+res = g.parse_host(arr, want=capi.WANT_BATCHES)
+text, offs = g.write_records(want_offsets=True)
+assert text.tobytes() == data and int(offs[-1]) == len(data)
+res = g.parse_host(arr[:300000], 0, 0, False, capi.WANT_BATCHES | capi.WANT_WHOLE_BATCHES)
+assert res.n_records % 512 == 0 and res.n_records > 0
 fa = b">a desc\nACGT\nAC GT\r\n\n>b\nTTTT" * 50
 r = g.fasta_parse_host(np.frombuffer(fa, np.uint8))
 ids, seqs, e = O.fasta_parse(fa, True)

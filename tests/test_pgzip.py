@@ -153,3 +153,36 @@ def test_damaged_streams_are_refused(tmp_path, fastq):
 def test_trailing_garbage_is_ignored_like_gzip(tmp_path, fastq):
     p = _write(tmp_path, "trail.gz", gzip.compress(fastq[:300_000]) + b"\0" * 512)
     assert read_all(p, 4) == fastq[:300_000]
+
+
+def test_random_streams_differential(tmp_path):
+    """Seeded random payloads x compression level / strategy / flush pattern x chunk size x threads: always zlib's bytes."""
+    rng = np.random.default_rng(20260)
+    alphabets = [b"ACGT", b"ACGTN\n@+!#$%&'()*+,-./0123456789:;<=>?", bytes(range(256)), b"a"]
+    for case in range(24):
+        alpha = alphabets[case % len(alphabets)]
+        n = int(rng.integers(1, 1_200_000))
+        idx = rng.integers(0, len(alpha), n)
+        payload = bytes(np.frombuffer(alpha, np.uint8)[idx])
+        if case % 3 == 0:                         # long repeats at assorted distances
+            piece = payload[: int(rng.integers(1, 5000))]
+            payload = (piece * (n // len(piece) + 1))[:n]
+        level = int(rng.integers(0, 10))
+        strategy = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED][case % 5]
+        co = zlib.compressobj(level, zlib.DEFLATED, 31, int(rng.integers(1, 10)), strategy)
+        parts, pos = [], 0
+        while pos < n:
+            step = int(rng.integers(1, 400_000))
+            parts.append(co.compress(payload[pos:pos + step]))
+            if rng.random() < 0.3:
+                parts.append(co.flush([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH][int(rng.integers(0, 2))]))
+            pos += step
+        parts.append(co.flush())
+        blob = b"".join(parts)
+        if case % 4 == 1:
+            blob = blob + gzip.compress(payload[: n // 3], int(rng.integers(1, 10)))      # a second member
+        p = _write(tmp_path, "r%d.gz" % case, blob)
+        want = gzip.open(p).read()
+        chunk = [CHUNK, 100_000, 333_333, 0][case % 4]
+        threads = [1, 2, 5, 8][case % 4]
+        assert read_all(p, threads, chunk_bytes=chunk, piece=int(rng.integers(1, 1 << 20))) == want, (case, level, strategy, chunk, threads)
