@@ -636,7 +636,7 @@ class Reader {
         failed_ = false; finished_ = n_ == 0; err_.clear();
         crc_ = crc32(0L, Z_NULL, 0); member_len_ = 0; redecoded_ = 0; marker_symbols_ = 0; final_idx_ = 0; chunks_base_ = 0;
         cur_.reset(); cur_off_ = 0; s2_.clear();
-        lookahead_ = (size_t)threads * 2 + 2;
+        lookahead_ = std::min<size_t>((size_t)threads * 2 + 2, 64);   // chunks in flight (each holds its output: ~10-40 MB)
         memset(last_window_, 0, sizeof last_window_);
         if (n_ && n_ < 18) { err_ = "not a gzip stream"; failed_ = true; return false; }
         if (n_ && (z_[0] != 0x1f || z_[1] != 0x8b)) { err_ = "not a gzip stream"; failed_ = true; return false; }
