@@ -25,6 +25,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -456,8 +459,17 @@ inline void inflate_chunk(const uint8_t* z, size_t n, uint64_t from_bit, uint64_
     const size_t est = (size_t)((stop_eff > from_bit ? (stop_eff - from_bit) / 8 : 0) * 4) + (1u << 16);
     uint16_t* o16 = nullptr; size_t p16 = kWin, c16 = 0;
     uint8_t* o8 = nullptr; size_t p8 = kWin, c8 = 0;
-    auto grow16 = [&]() { c16 = std::max<size_t>(c16 * 2, kWin + est); C.m16.resize(c16); o16 = C.m16.data(); };
-    auto grow8 = [&]() { c8 = std::max<size_t>(c8 * 2, kWin + est); C.b8.resize(c8); o8 = C.b8.data(); };
+    // (the vectors may come from a pool with a size of their own: it is used as it is, and only ever grown)
+    auto grow16 = [&]() {
+        c16 = std::max<size_t>(c16 * 2, kWin + est);
+        if (C.m16.size() < c16) C.m16.resize(c16); else c16 = C.m16.size();
+        o16 = C.m16.data();
+    };
+    auto grow8 = [&]() {
+        c8 = std::max<size_t>(c8 * 2, kWin + est);
+        if (C.b8.size() < c8) C.b8.resize(c8); else c8 = C.b8.size();
+        o8 = C.b8.data();
+    };
     auto to_bytes = [&](bool fresh_member) {
         // byte mode from here on: the last kWin symbols (marker free, or irrelevant at a member start) become the prefix
         grow8();
@@ -539,6 +551,24 @@ inline void inflate_chunk(const uint8_t* z, size_t n, uint64_t from_bit, uint64_
     C.ok = true;
 }
 
+// markers -> window bytes, plain symbols -> bytes.  Most 16-symbol groups hold no marker (markers are what was copied,
+// directly or through other copies, from before the chunk): those are packed with two vector instructions.
+inline void resolve_markers(const uint16_t* s, size_t n, const uint8_t* w, uint8_t* d) {
+    size_t i = 0;
+#if defined(__SSE2__)
+    for (; i + 16 <= n; i += 16) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 8));
+        if (_mm_movemask_epi8(_mm_or_si128(a, b)) & 0xAAAA) {
+            for (size_t k = i; k < i + 16; ++k) { const uint16_t v = s[k]; d[k] = (v & kMarker) ? w[v & (kMarker - 1)] : (uint8_t)v; }
+        } else {
+            _mm_storeu_si128(reinterpret_cast<__m128i*>(d + i), _mm_packus_epi16(a, b));
+        }
+    }
+#endif
+    for (; i < n; ++i) { const uint16_t v = s[i]; d[i] = (v & kMarker) ? w[v & (kMarker - 1)] : (uint8_t)v; }
+}
+
 // ---- the reader ---------------------------------------------------------------------------------------------------
 class Reader {
   public:
@@ -590,15 +620,16 @@ class Reader {
                 cur_off_ = 0;
                 if (!cur_) { if (failed_ && !got) return -1; break; }
             }
-            const size_t total = cur_->head.size() + cur_->out.n8;
+            const size_t hn = cur_->out.n16;             // resolved symbols in `head`
+            const size_t total = hn + cur_->out.n8;
             if (cur_off_ >= total) { retire(cur_); cur_ = nullptr; continue; }
             // [head | b8 after its prefix]
             size_t k;
-            if (cur_off_ < cur_->head.size()) {
-                k = std::min(want - got, cur_->head.size() - cur_off_);
+            if (cur_off_ < hn) {
+                k = std::min(want - got, hn - cur_off_);
                 memcpy(dst + got, cur_->head.data() + cur_off_, k);
             } else {
-                const size_t o = cur_off_ - cur_->head.size();
+                const size_t o = cur_off_ - hn;
                 k = std::min(want - got, cur_->out.n8 - o);
                 memcpy(dst + got, cur_->out.b8.data() + kWin + o, k);
             }
@@ -635,7 +666,7 @@ class Reader {
         next_s1_ = 0; next_seq_ = 0; next_out_ = 0; expect_bit_ = 0; expect_member_ = true;
         failed_ = false; finished_ = n_ == 0; err_.clear();
         crc_ = crc32(0L, Z_NULL, 0); member_len_ = 0; redecoded_ = 0; marker_symbols_ = 0; final_idx_ = 0; chunks_base_ = 0;
-        cur_.reset(); cur_off_ = 0; s2_.clear();
+        cur_.reset(); cur_off_ = 0; s2_.clear(); pool_bufs_.clear();
         lookahead_ = std::min<size_t>((size_t)threads * 2 + 2, 64);   // chunks in flight (each holds its output: ~10-40 MB)
         memset(last_window_, 0, sizeof last_window_);
         if (n_ && n_ < 18) { err_ = "not a gzip stream"; failed_ = true; return false; }
@@ -660,6 +691,11 @@ class Reader {
                         c->nominal_begin = (uint64_t)c->idx * chunk_ * 8;
                         c->nominal_end = std::min<uint64_t>((uint64_t)(c->idx + 1) * chunk_, n_) * 8;
                         c->state = 1;
+                        if (!pool_bufs_.empty()) {
+                            Bufs& b = pool_bufs_.back();
+                            c->out.m16.swap(b.m16); c->out.b8.swap(b.b8); c->head.swap(b.head);
+                            pool_bufs_.pop_back();
+                        }
                         chunks_.push_back(c);
                         what = 1;
                         break;
@@ -706,12 +742,8 @@ class Reader {
     // markers -> bytes, CRC-32 of the member segments
     void stage2(Chunk& c) {
         ChunkOut& o = c.out;
-        c.head.resize(o.n16);
-        const uint16_t* s = o.m16.data() + kWin;
-        uint8_t* d = c.head.data();
-        const uint8_t* w = c.window;
-        for (size_t i = 0; i < o.n16; ++i) { const uint16_t v = s[i]; d[i] = (v & kMarker) ? w[v & (kMarker - 1)] : (uint8_t)v; }
-        std::vector<uint16_t>().swap(o.m16);
+        if (c.head.size() < o.n16) c.head.resize(o.n16);              // (buffers come from the pool: grown, never shrunk)
+        resolve_markers(o.m16.data() + kWin, o.n16, c.window, c.head.data());
         // segments: [0, end0), [end0, end1), ..., [end_last, total)
         c.seg_crc.clear(); c.seg_len.clear();
         uint64_t a = 0;
@@ -764,7 +796,7 @@ class Reader {
                     progressed = true;
                     c->abandon.store(true);
                     c->taken = true;
-                    c->head.clear(); c->seg_crc.clear(); c->seg_len.clear();
+                    c->seg_crc.clear(); c->seg_len.clear();
                     c->state = 4; c->skipped = true;
                     if (c->idx + 1 == n_chunks_) { finished_ = true; final_idx_ = c->idx; }
                     ++next_seq_;
@@ -818,7 +850,7 @@ class Reader {
                     ++next_out_;
                     chunks_.pop_front(); ++chunks_base_;
                     cv_work_.notify_all();
-                    if (c->skipped) continue;
+                    if (c->skipped) continue;      // (its buffers die with it: a worker may still be writing into them)
                     return c;
                 }
             }
@@ -845,7 +877,15 @@ class Reader {
         return true;
     }
 
-    void retire(std::shared_ptr<Chunk>&) {}
+    // a consumed (or skipped) chunk's buffers go back to the pool: fresh allocations of this size are page-faulted and
+    // zero-filled by the kernel, which costs a fifth of the decode time
+    struct Bufs { std::vector<uint16_t> m16; std::vector<uint8_t> b8, head; };
+    void retire(std::shared_ptr<Chunk>& c) {
+        Bufs b;
+        b.m16.swap(c->out.m16); b.b8.swap(c->out.b8); b.head.swap(c->head);
+        std::lock_guard<std::mutex> lk(mu_);
+        if (pool_bufs_.size() < lookahead_ + 2) pool_bufs_.push_back(std::move(b));
+    }
     void fail(const std::string& e) { failed_ = true; if (err_.empty()) err_ = e; cv_work_.notify_all(); }
 
     int fd_ = -1;
@@ -860,6 +900,7 @@ class Reader {
     std::deque<std::shared_ptr<Chunk>> chunks_;   // chunks_[i] is chunk chunks_base_ + i
     size_t chunks_base_ = 0;
     std::deque<std::shared_ptr<Chunk>> s2_;
+    std::vector<Bufs> pool_bufs_;
     size_t next_s1_ = 0, next_seq_ = 0, next_out_ = 0;
     uint64_t expect_bit_ = 0;
     bool expect_member_ = true;
