@@ -901,7 +901,7 @@ struct bsq_stream {
     // the 'BC' extra field and its uncompressed size in ISIZE, so members inflate independently.  The
     // reader thread walks the member headers and `inflate_threads` workers inflate a region's members in
     // parallel, each straight into its place in the pinned region (the parallel-decoder role of
-    // RapidgzipReader(parallelism), readers.mojo:380-443; plain gzip members still go through gzread).
+    // RapidgzipReader(parallelism), readers.mojo:380-443; ordinary gzip goes through the speculative decoder of bsq_pgzip.h).
     bool bgzf = false;
     int inflate_threads = 1, io_threads = 1;
     int64_t file_size = -1, file_pos = 0;   // regular plain files: parallel pread

@@ -76,9 +76,10 @@ typedef struct bsq_config {
     int32_t batch_size;            /* FastqParser._batch_size, DEFAULT_BATCH_SIZE = 4096 */
     int64_t h2d_chunk_bytes;       /* staging chunk for bsq_parse_host (default 64 MiB) */
     int32_t force_id_slow_path;    /* tests: always take the id strip pipeline */
-    int32_t inflate_threads;       /* bsq_stream_*: host threads that inflate BGZF members / read slices of a plain
-                                      file (0 = all cores, at most 8 for plain reads); the
-                                      parallelism argument of RapidgzipReader, readers.mojo:380-443 */
+    int32_t inflate_threads;       /* bsq_stream_*: host threads that decode an ordinary gzip stream (1 = zlib's gzread) /
+                                      inflate BGZF members with host_inflate / read slices of a plain file (0 = all cores,
+                                      at most 8 for plain reads); the parallelism argument of RapidgzipReader,
+                                      readers.mojo:380-443 */
     int32_t compat_q5_width;       /* 0: quality bytes are valid iff LOWER <= b <= UPPER (the documented intent).
                                       W > 0: reproduce Validator._validate_quality_range as written
                                       (fastq/record.mojo:90-102) for a host whose SIMD width is W bytes: the first

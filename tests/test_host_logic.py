@@ -243,3 +243,84 @@ def test_bgzf_writer_members():
             pos += size
             n += 1
         assert pos == len(blob) and total == len(data) and isize == 0 and n == -(-len(data) // bgzf.BLOCK) + 1
+
+
+def test_host_batch_pipeline_sequencing_with_stand_in_parsers(B, oracle):
+    """HostBatchPipeline's host logic (two handles alternating regions, the whole-batches cut, output offsets, error
+    hand-over) with stand-in parser handles that answer from the oracle -- the device passes themselves are covered by
+    tests/test_gpu_parity.py::test_whole_batches_regions_and_the_host_batch_pipeline."""
+    import threading
+    import time
+    from types import SimpleNamespace
+    from blazeseq_b200 import _capi as capi
+    m = 250
+    data = oracle.synth(9000, 40, 220, 2, 40, "sanger")
+    views, bases, err = oracle.parse_all(data)
+    exp = [oracle.build_batch(data, views[a:a + m]) for a in range(0, len(views), m)]
+    active = {"n": 0, "max": 0}
+    lock = threading.Lock()
+
+    class StandIn:
+        def __init__(self):
+            self.cur = None
+            self.closed = False
+
+        def parse_host(self, region, stream_offset, first_record, is_last, want):
+            assert want == capi.WANT_BATCHES | capi.WANT_WHOLE_BATCHES
+            with lock:
+                active["n"] += 1
+                active["max"] = max(active["max"], active["n"])
+            assert active["n"] == 1, "two regions were parsed at once: the cut of region k+1 needs region k's result"
+            time.sleep(0.002)
+            if not is_last:                       # a region that does not end the stream: its complete records only
+                nl = np.flatnonzero(region == 10)
+                k = len(nl) // 4 * 4
+                region = region[:int(nl[k - 1]) + 1] if k else region[:0]
+            v, _, e = oracle.parse_all(region, oracle.config(True, False, "sanger"))
+            assert e.code == capi.EOF
+            n = len(v)
+            stop = SimpleNamespace(code=capi.EOF if is_last else capi.OK, text="", message=b"")
+            if not is_last:
+                n -= n % m
+            consumed = region.size if is_last else (int(v[n]["header_start"]) if n < len(v) else region.size if n else 0)
+            self.cur = (region, v[:n])
+            with lock:
+                active["n"] -= 1
+            return SimpleNamespace(n_records=n, bytes_consumed=consumed, stop=stop)
+
+        def soa_view(self):
+            region, v = self.cur
+            return SimpleNamespace(sequence_bytes=int(v["seq_len"].sum()), seq_len=int(v["qual_len"].sum()),
+                                   total_id_bytes=int(v["id_len"].sum()))
+
+        def soa_to_host(self, seq, qual, idb, ends, id_ends):
+            region, v = self.cur
+            time.sleep(0.003)                     # the other handle parses the next region meanwhile
+            so = qo = io = ro = 0
+            for a in range(0, len(v), m):
+                i_, s_, q_, ie_, e_ = oracle.build_batch(region, v[a:a + m])
+                seq[so:so + s_.size] = s_; qual[qo:qo + q_.size] = q_; idb[io:io + i_.size] = i_
+                ends[ro:ro + e_.size] = e_; id_ends[ro:ro + ie_.size] = ie_
+                so += s_.size; qo += q_.size; io += i_.size; ro += e_.size
+
+        def close(self):
+            self.closed = True
+
+    tot = {k: sum(e[i].size for e in exp) for k, i in (("id", 0), ("seq", 1), ("qual", 2))}
+    for region_bytes in (90_000, 400_000, 10 ** 9):
+        pipe = B.HostBatchPipeline(StandIn, region_bytes=region_bytes)
+        seq = np.zeros(tot["seq"], np.uint8); qual = np.zeros(tot["qual"], np.uint8); idb = np.zeros(tot["id"], np.uint8)
+        ends = np.zeros(len(views), np.int64); id_ends = np.zeros(len(views), np.int64)
+        got = pipe.run(data, seq, qual, idb, ends, id_ends)
+        assert got == (len(views), tot["seq"], tot["qual"], tot["id"]) and pipe.stop.code == capi.EOF
+        assert np.array_equal(seq, np.concatenate([e[1] for e in exp])) and np.array_equal(qual, np.concatenate([e[2] for e in exp]))
+        assert np.array_equal(idb, np.concatenate([e[0] for e in exp]))
+        assert np.array_equal(ends, np.concatenate([e[4] for e in exp])) and np.array_equal(id_ends, np.concatenate([e[3] for e in exp]))
+        parsers = list(pipe.parsers)
+        pipe.close()
+        assert all(p.closed for p in parsers)
+    # a region smaller than one batch cannot make progress: reported, not looped on
+    pipe = B.HostBatchPipeline(StandIn, region_bytes=5_000)
+    with pytest.raises(ValueError):
+        pipe.run(data, None, None, None, None, None)
+    pipe.close()
