@@ -20,7 +20,7 @@ cap k_resolve_stride320 k_resolve --id-digits 9
 cap k_resolve_validate k_resolve --validate
 cap k_summarize_validate k_summarize --validate
 cap k_resolve_mixed k_resolve --mixed
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_inflate_members -s 2 -c 1 -f -o gpurun_out/${R}_prof_k_inflate python bench.py --gzip --gib 0.5 > gpurun_out/ncu_k_inflate.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_inflate_members -s 3 -c 1 -f -o gpurun_out/${R}_prof_k_inflate python bench.py --gzip --gib 1 --region-mib 256 > gpurun_out/ncu_k_inflate.log 2>&1
 timeout 120 python scripts/profile_summary.py gpurun_out/${R}_prof_k_inflate.ncu-rep k_inflate > gpurun_out/${R}_k_inflate_members.txt 2>&1
 # keep two reports for reading source pages later; the rest stays on the box
 find gpurun_out -name "*.ncu-rep" ! -name "${R}_prof_k_resolve.ncu-rep" ! -name "${R}_prof_k_inflate.ncu-rep" -delete
