@@ -668,6 +668,39 @@ def test_device_writer_round_trip(B, oracle):
     gpu.close()
 
 
+def test_cpp_runner_counts_and_errors(B, oracle, tmp_path, golden_dir):
+    """examples/run_blazeseq.cpp over include/blazeseq_gpu.hpp: the "<records> <base_pairs>" line of the reference's benchmark
+    runners (run_blazeseq.mojo / _batch / _gzip) in every mode, on plain / gzip / BGZF files, and the reference's error text
+    after the records before the error."""
+    import gzip
+    import subprocess
+    from blazeseq_b200 import bgzf
+    from test_host_logic import _build_cpp_runner
+    exe = _build_cpp_runner(str(tmp_path))
+    data = oracle.synth(30000, 50, 250, 2, 40, "sanger")
+    views, bases, err = oracle.parse_all(data)
+    (tmp_path / "a.fastq").write_bytes(data.tobytes())
+    (tmp_path / "a.fastq.gz").write_bytes(gzip.compress(data.tobytes(), 6))
+    (tmp_path / "b.fastq.bgz").write_bytes(bgzf.compress(data.tobytes(), level=6))
+    want = [str(len(views)), str(bases)]
+    for name in ("a.fastq", "a.fastq.gz", "b.fastq.bgz"):
+        for mode in ("views", "batches", "device_batches"):
+            r = subprocess.run([exe, str(tmp_path / name), mode, "1000"], capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0 and r.stdout.split() == want, (name, mode, r.stdout, r.stderr)
+    r = subprocess.run([exe, os.path.join(golden_dir, "corpus", "example.fastq"), "views", "4096", "validate"], capture_output=True, text=True)
+    ev, eb, _ = oracle.parse_all(np.fromfile(os.path.join(golden_dir, "corpus", "example.fastq"), np.uint8), oracle.config(True, True))
+    assert r.returncode == 0 and r.stdout.split() == [str(len(ev)), str(eb)]
+    # an error: the records before it are counted, then the reference's message
+    bad = data.copy()
+    bad[int(views[12345]["header_start"])] = ord("X")
+    (tmp_path / "bad.fastq").write_bytes(bad.tobytes())
+    bv, bb, berr = oracle.parse_all(bad)
+    for mode in ("views", "batches"):
+        r = subprocess.run([exe, str(tmp_path / "bad.fastq"), mode, "1000"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 2 and r.stdout.split() == [str(len(bv)), str(bb)], (mode, r.stdout)
+        assert r.stderr.strip() == berr.message.decode().strip()
+
+
 def test_shard_summaries_locate_record_starts(B, oracle):
     """Multi-GPU stitching: summaries of arbitrary byte shards (device) -> where each shard's first
     own record starts (host arithmetic) must match the oracle's record table."""

@@ -324,3 +324,31 @@ def test_host_batch_pipeline_sequencing_with_stand_in_parsers(B, oracle):
     with pytest.raises(ValueError):
         pipe.run(data, None, None, None, None, None)
     pipe.close()
+
+
+def _build_cpp_runner(tmp_path):
+    import subprocess
+    exe = os.path.join(tmp_path, "run_blazeseq")
+    lib = os.path.join(ROOT, "blazeseq_b200", "lib")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "run_blazeseq.cpp"), "-L" + lib, "-lblazeseq_gpu", "-Wl,-rpath," + lib, "-o", exe],
+                   check=True, capture_output=True)
+    return exe
+
+
+def test_cpp_host_mirror_builds_and_never_parses_on_the_cpu(B, tmp_path, golden_dir):
+    """include/blazeseq_gpu.hpp (C++ host mirror over the C ABI) + examples/run_blazeseq.cpp (the reference's benchmark
+    runners) compile warning-free against the library; without a device the runner reports that and parses nothing."""
+    import subprocess
+    B._capi.lib()      # the library is built
+    exe = _build_cpp_runner(str(tmp_path))
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    r = subprocess.run([exe, os.path.join(golden_dir, "corpus", "example.fastq")], capture_output=True, text=True)
+    if has_gpu:
+        assert r.returncode == 0 and r.stdout.split()[0] == "3", (r.stdout, r.stderr)
+    else:
+        assert r.returncode != 0 and r.stdout.split() == ["0", "0"] and "no usable CUDA device" in r.stderr
