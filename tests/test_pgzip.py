@@ -186,3 +186,35 @@ def test_random_streams_differential(tmp_path):
         chunk = [CHUNK, 100_000, 333_333, 0][case % 4]
         threads = [1, 2, 5, 8][case % 4]
         assert read_all(p, threads, chunk_bytes=chunk, piece=int(rng.integers(1, 1 << 20))) == want, (case, level, strategy, chunk, threads)
+
+
+def test_corrupted_streams_fuzz(tmp_path, fastq):
+    """Seeded corruption of a multi-chunk stream (bit flips, overwritten runs, truncations, inserted garbage): the decoder
+    either refuses the stream or -- when the damage is not in bytes that matter -- delivers exactly what zlib delivers;
+    it never hangs and never hands out bytes of a stream whose CRC-32 does not hold."""
+    rng = np.random.default_rng(4242)
+    blob = gzip.compress(fastq[:3_000_000], 6) + gzip.compress(fastq[3_000_000:4_000_000], 1)
+    for case in range(40):
+        bad = bytearray(blob)
+        kind = case % 4
+        at = int(rng.integers(12, len(bad) - 12))
+        if kind == 0:
+            bad[at] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:
+            n = int(rng.integers(1, 2000))
+            bad[at:at + n] = rng.integers(0, 256, min(n, len(bad) - at), dtype=np.uint8).tobytes()
+        elif kind == 2:
+            del bad[at:]
+        else:
+            bad[at:at] = rng.integers(0, 256, int(rng.integers(1, 300)), dtype=np.uint8).tobytes()
+        p = _write(tmp_path, "f%d.gz" % case, bytes(bad))
+        try:
+            want = gzip.open(p).read()
+        except Exception:
+            want = None
+        try:
+            got = read_all(p, 4)
+        except B.BlazeSeqError:
+            got = None
+        if got is not None:
+            assert want is not None and got == want, (case, kind, at)
