@@ -649,7 +649,7 @@ class Reader {
         ChunkOut out;
         int state = 0;       // 0 queued, 1 stage 1 running, 2 stage 1 done, 3 accepted (stage 2 queued/running), 4 ready
         uint8_t window[kWin];
-        bool have_window = false, skipped = false;
+        bool skipped = false;
         bool found = false;                 // stage 1 has a block start and is inflating from it
         std::atomic<bool> abandon{false};   // the sequencer got here first and decodes the chunk itself
         bool taken = false;
@@ -826,7 +826,6 @@ class Reader {
                     c->out = std::move(fresh);
                 }
                 memcpy(c->window, last_window_, kWin);
-                c->have_window = true;
                 marker_symbols_ += c->out.n16;
                 {
                     uint8_t nw[kWin];
