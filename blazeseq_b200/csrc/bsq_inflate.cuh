@@ -6,10 +6,13 @@
 // the trailer -- tens of thousands of independent streams per GiB.  Here the COMPRESSED members cross PCIe
 // and ONE WARP inflates ONE member straight into the parse window in HBM:
 //
-//   lane 0 owns the bit reader and the Huffman tables of the member (shared memory, rebuilt per block) and
-//   decodes symbols; literals are single byte stores; for a match the (length, distance) pair is broadcast
-//   and the whole warp copies it (LZ77 history is the member's own output, read back from L1 / L2);
-//   stored blocks are warp copies as well.
+//   k_inflate_members_uniform (shipped): every lane of the warp runs the decode loop on identical state -- one
+//   broadcast load per input word, one broadcast shared-memory lookup per Huffman code (tables rebuilt per block
+//   by lane 0) -- so that a match needs no hand-off: every lane already knows (position, length, distance) and
+//   lane i copies byte i (LZ77 history is the member's own output, read back from L1 / L2); a literal is one
+//   store; stored blocks are warp copies.
+//   k_inflate_members (tuning builds, BSQ_INF_LANES lanes per member): the group's first lane decodes and
+//   broadcasts every match to its group.
 //
 // The decode chain of one member is serial by nature; the parallelism is across members (a 256 MiB region is
 // ~4,000 warps of work).  Output is bit-exact zlib (tests compare with zlib.decompress on the reference's own
