@@ -79,7 +79,8 @@ constexpr int kHalo = 1024;               // bytes before the tile kept in share
 // back with TMA bulk stores; 0 = destination-ordered direct copy to global memory (no stage buffer)
 constexpr bool kCopyStaged = BSQ_COPY_STAGED != 0;
 #ifndef BSQ_ROT
-#define BSQ_ROT 1          // staged copy: lanes whose lines start in the same bank start at different words
+#define BSQ_ROT 2          // staged copy: lanes whose lines start in the same bank start at different words
+                           // (2: the rank comes from the line distance; 1: from a per-warp bank census, REDUX + MATCH.ANY)
 #endif
 #ifndef BSQ_INTERLEAVE
 #define BSQ_INTERLEAVE 1   // staged copy: sequence and quality lines alternate over the lanes
@@ -1041,7 +1042,10 @@ __device__ __forceinline__ void stage_line(const uint8_t* __restrict__ data, uin
     // bank: those get distinct start words (rank among the lanes of their bank).  The common case (at most
     // ~2 lanes per bank) takes no rotation and pays one warp reduction.
     uint32_t rot = 0;
-#if BSQ_ROT
+#if BSQ_ROT == 2
+    rot = lanes;           // (the caller's arithmetic rank: see the call site)
+    (void)src4;
+#elif BSQ_ROT
     const uint32_t bank = (src4 >> 2) & 31u;
     const uint32_t occupied = __reduce_or_sync(lanes, 1u << bank);
     if (3u * __popc(occupied) < __popc(lanes)) {
@@ -1406,9 +1410,20 @@ __global__ void __launch_bounds__(kThreads, kPack ? kResolveCtas : kViewCtas) k_
                     const bool in_step = BSQ_INTERLEAVE && n1 > 2u && ((S.ssrc[1][1] - S.ssrc[1][0]) & 15u) == 0u &&
                                          ((S.ssrc[1][2] - S.ssrc[1][1]) & 15u) == 0u;
                     const uint32_t npair = in_step ? 2u * (n1 < n2 ? n1 : n2) : 0u, nitem = n1 + n2 + n0;
+#if BSQ_ROT == 2
+                    // lines a multiple of 16 bytes apart start in few banks: with q = (distance in words) mod 32 (a multiple of
+                    // 4 here) a warp's sixteen lines of a stream fall into P = 32 / gcd(q, 32) banks, line i' = lane / 2 of the
+                    // warp being the (i' / P)-th on its bank -- that rank is the word its copy starts from
+                    const uint32_t qd = in_step ? ((S.ssrc[1][1] - S.ssrc[1][0]) >> 2) & 31u : 4u;
+                    const uint32_t lg_p = qd == 0u ? 0u : ((qd & 4u) ? 3u : ((qd & 8u) ? 2u : 1u));
+#endif
                     for (uint32_t w0 = 0; w0 < nitem; w0 += kThreads) {
                         const uint32_t w = w0 + tid;
+#if BSQ_ROT == 2
+                        const uint32_t lanes = (in_step && w < npair) ? ((tid & 31u) >> 1) >> lg_p : 0u;
+#else
                         const uint32_t lanes = __ballot_sync(0xFFFFFFFFu, w < nitem);
+#endif
                         if (w < nitem) {
                             uint32_t st, i, so, A;
                             if (w < npair) { st = 1u + (w & 1u); i = w >> 1; }
